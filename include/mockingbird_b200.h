@@ -1,0 +1,183 @@
+/*
+ * mockingbird_b200 - C ABI of the B200-native (sm_100a) vocoder / mel-synthesizer hot path.
+ *
+ * This is the drop-in boundary.  The reference (babysor/MockingBird) has no
+ * FFI of its own: its callers talk to duck-typed Python module singletons.  The Python host layer
+ * in mockingbird_b200/ presents exactly those surfaces and binds the entry points below through
+ * ctypes (INTEGRATION.md shows the stub).  Each group cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = OK, non-zero = error; mb_last_error() gives the
+ *     message for the calling thread.  No exceptions cross the ABI.
+ *   - handles are opaque; one handle must not be used from two threads at once.
+ *   - all tensor arguments are caller-owned DEVICE pointers unless the name ends in _host.
+ *   - no hidden device allocation after *_create: packed weights live in a caller-provided arena
+ *     (mb_*_arena_bytes), temporaries in a caller-provided workspace (mb_*_workspace_bytes).
+ *   - every launch goes to the cudaStream_t passed as `stream` (void* here so that the header
+ *     needs no CUDA include); functions are asynchronous with respect to the host unless stated.
+ */
+#ifndef MOCKINGBIRD_B200_H
+#define MOCKINGBIRD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_OK 0
+#define MB_ERR_INVALID 1   /* bad argument / unknown weight name / shape mismatch */
+#define MB_ERR_STATE 2     /* call order violated (e.g. forward before finalize) */
+#define MB_ERR_CUDA 3      /* a CUDA runtime call or kernel launch failed        */
+#define MB_ERR_WORKSPACE 4 /* workspace / arena too small                        */
+
+/* library-wide ----------------------------------------------------------------------------- */
+const char* mb_last_error(void);
+/* "mockingbird_b200 <ver> sm_100a"; never NULL */
+const char* mb_version(void);
+/* number of kernel launches issued by this library since load (all handles); used by bench.py
+ * to report gpu_launches from a counter rather than from a guess */
+uint64_t mb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GAN vocoder generators: HiFi-GAN and Fre-GAN
+ *   replaces  models/vocoder/hifigan/models.py:96-162  Generator.{__init__,forward,remove_weight_norm}
+ *             models/vocoder/fregan/generator.py:79-179 FreGAN.{__init__,forward,remove_weight_norm}
+ *   driven by models/vocoder/hifigan/inference.py:22-73 and fregan/inference.py:22-73
+ * ------------------------------------------------------------------------------------------- */
+#define MB_GAN_HIFIGAN 0
+#define MB_GAN_FREGAN 1
+
+/* arithmetic of the channel-mixing convolutions */
+#define MB_PREC_FP32 0      /* FP32 FFMA everywhere (parity anchor, ~1e-6 of the reference)     */
+#define MB_PREC_F16TC 1     /* tcgen05 tensor cores: fp16 operands, fp32 accumulate, fp32
+                               residual stream; conv_post in fp32 (tolerance 1e-3) */
+
+typedef struct mb_gan_config {
+  int32_t kind;                 /* MB_GAN_HIFIGAN | MB_GAN_FREGAN                                  */
+  int32_t num_mels;             /* 80 (models.py:99 hard-codes 80)                                 */
+  int32_t upsample_initial_channel;
+  int32_t num_upsamples;        /* len(h.upsample_rates) <= 8                                      */
+  int32_t upsample_rates[8];
+  int32_t upsample_kernel_sizes[8];
+  int32_t num_kernels;          /* len(h.resblock_kernel_sizes) <= 4                               */
+  int32_t resblock_kernel_sizes[4];
+  int32_t num_dilations;        /* dilations per resblock <= 4                                     */
+  int32_t resblock_dilation_sizes[4][4];
+  int32_t resblock_type;        /* 1 = ResBlock1 (models.py:11), 2 = ResBlock2 (models.py:50)      */
+  int32_t fregan_top_k;         /* FreGAN(h, top_k=4); ignored for HiFi-GAN                        */
+  int32_t precision;            /* MB_PREC_*                                                       */
+} mb_gan_config;
+
+typedef struct mb_gan mb_gan;
+
+int mb_gan_create(const mb_gan_config* cfg, mb_gan** out);
+void mb_gan_destroy(mb_gan* h);
+
+/* bytes of device memory the packed weights need; pass such a buffer to mb_gan_set_arena */
+size_t mb_gan_arena_bytes(const mb_gan* h);
+int mb_gan_set_arena(mb_gan* h, void* arena, size_t bytes);
+
+/* Feed one tensor of ckpt['generator'] (hifigan/inference.py:51) AFTER weight-norm folding
+ * (w = g*v/||v||, models.py:152-162 - the host layer folds): name as in state_dict
+ * ("conv_pre.weight", "ups.0.bias", "resblocks.3.convs1.0.weight", "cond_up.1.weight",
+ * "res_output.0.1.weight" ...), fp32, contiguous, reference shape.  Packs into the arena on
+ * `stream`.  */
+int mb_gan_set_weight(mb_gan* h, const char* name, const float* w, const int64_t* dims, int32_t ndim,
+                      void* stream);
+/* verifies that every tensor the config needs has been set */
+int mb_gan_finalize(mb_gan* h);
+
+/* samples produced per mel frame = prod(upsample_rates) */
+int32_t mb_gan_hop(const mb_gan* h);
+size_t mb_gan_workspace_bytes(const mb_gan* h, int32_t batch, int32_t frames);
+
+/* Generator.forward (models.py:134-150):  mel [B, num_mels, T] fp32  ->  wav [B, 1, T*hop] fp32.
+ * lengths (optional, int32 [B], device): valid frames per utterance; rows beyond are treated as
+ * zero padding at every layer so each utterance equals its own batch-1 reference call, and
+ * wav[b, lengths[b]*hop:] = 0.   */
+int mb_gan_forward(mb_gan* h, const float* mel, const int32_t* lengths, int32_t batch, int32_t frames,
+                   float* wav, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Measurement hook for bench.py's roofline: same as mb_gan_forward, but brackets every layer launch
+ * with CUDA events on `stream`, synchronises, and writes the device time of layer i (milliseconds)
+ * to ms_per_layer_host[i] (host array of mb_gan_num_layers entries). */
+int mb_gan_forward_profiled(mb_gan* h, const float* mel, const int32_t* lengths, int32_t batch,
+                            int32_t frames, float* wav, void* workspace, size_t workspace_bytes,
+                            void* stream, float* ms_per_layer_host);
+/* algorithmic work of layer i for a [batch, frames] call: multiply-accumulates, and fp32
+ * layer-granular bytes (input elements read + output elements written, x4) */
+int mb_gan_layer_work(const mb_gan* h, int32_t layer_index, int32_t batch, int32_t frames,
+                      double* macs, double* layer_bytes);
+
+/* test hook: run ONE convolution layer of the plan in isolation through the selected precision
+ * path.  Used only by tests/ to compare the tensor-core kernels with the FP32 kernels layer by
+ * layer.  x/y are [B, C, L] fp32 (reference layout). */
+int mb_gan_debug_layer(mb_gan* h, int32_t layer_index, const float* x, const float* residual,
+                       int32_t batch, int32_t frames_in, float* y, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int32_t mb_gan_num_layers(const mb_gan* h);
+/* fills a short description "name Cin Cout k dil stride" for layer i; returns 0 on success */
+int mb_gan_layer_info(const mb_gan* h, int32_t layer_index, char* buf, size_t buflen);
+
+/* ---------------------------------------------------------------------------------------------
+ * fatchord WaveRNN
+ *   replaces  models/vocoder/wavernn/models/fatchord_version.py:88-257 (WaveRNN.generate and the
+ *             UpsampleNetwork/MelResNet conditioning :27-85), driven by wavernn/inference.py:8-64
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mb_wavernn_config {
+  int32_t rnn_dims;      /* 512 hparams.voc_rnn_dims */
+  int32_t fc_dims;       /* 512 */
+  int32_t bits;          /* 9 -> 512 classes */
+  int32_t pad;           /* 2 */
+  int32_t num_upsample;  /* 3 */
+  int32_t upsample_factors[4]; /* (5,5,8) */
+  int32_t feat_dims;     /* 80 */
+  int32_t compute_dims;  /* 128 */
+  int32_t res_out_dims;  /* 128 */
+  int32_t res_blocks;    /* 10 */
+} mb_wavernn_config;
+
+typedef struct mb_wavernn mb_wavernn;
+
+int mb_wavernn_create(const mb_wavernn_config* cfg, mb_wavernn** out);
+void mb_wavernn_destroy(mb_wavernn* h);
+size_t mb_wavernn_arena_bytes(const mb_wavernn* h);
+int mb_wavernn_set_arena(mb_wavernn* h, void* arena, size_t bytes);
+/* tensors of ckpt['model_state'] (wavernn/inference.py:36-37), reference names and shapes
+ * (SURVEY.md appendix B), fp32 */
+int mb_wavernn_set_weight(mb_wavernn* h, const char* name, const float* w, const int64_t* dims,
+                          int32_t ndim, void* stream);
+int mb_wavernn_finalize(mb_wavernn* h, void* stream);
+
+size_t mb_wavernn_workspace_bytes(const mb_wavernn* h, int32_t frames, int32_t folds, int32_t steps);
+
+/* UpsampleNetwork.forward on the padded mel (fatchord_version.py:168-170): mel [80, T] fp32
+ * (already divided by mel_max_abs_value, inference.py:60-61) -> frame-rate conditioning kept in
+ * the workspace (aux [T,128]; the mel FIR ladder is evaluated on the fly by the sample loop's
+ * conditioning stage, the 200x upsampled tensors are never materialised in full). */
+int mb_wavernn_condition(mb_wavernn* h, const float* mel, int32_t frames, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* The sample loop (fatchord_version.py:190-234) over `folds` independent rows, each `steps` long,
+ * row r starting at upsampled-time offset fold_starts[r] (fold_with_overlap, :288-338; positions
+ * past the end of the conditioning read zeros like the reference's zero padding).
+ *   noise  : Exp(1) draws, fp32 [steps_in_call, folds, 512] in the reference's draw order
+ *            (Categorical.sample == argmax(p/q)), or NULL to use the built-in
+ *            counter-based generator seeded by `seed`.
+ *   step0/nsteps: run steps [step0, step0+nsteps) - state (h1,h2,x) persists in the workspace
+ *            between calls so the host can call the progress callback every 100 steps
+ *            (fatchord_version.py:232-234); step0 == 0 resets the state to zeros (:178-185).
+ *   out_idx: int16 [folds, steps] class indices (row-major, written at [r, step0+i]).      */
+int mb_wavernn_generate(mb_wavernn* h, const int32_t* fold_starts_host, int32_t folds, int32_t steps,
+                        int32_t step0, int32_t nsteps, const float* noise, uint64_t seed,
+                        int16_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
+/* debug/test hook: logits [folds, 512] fp32 of the LAST step executed by mb_wavernn_generate */
+int mb_wavernn_last_logits(mb_wavernn* h, float* logits, int32_t folds, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOCKINGBIRD_B200_H */

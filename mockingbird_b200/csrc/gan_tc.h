@@ -1,0 +1,60 @@
+// Tensor-core (tcgen05 / TMEM / bulk-TMA) execution of the GAN generator plan (MB_PREC_F16TC).
+// Host-side interface used by gan_api.cu; the kernels live in gan_tc.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "gan_kernels.h"
+
+namespace mb {
+
+// per-layer packing decision, filled by tc_plan_layers
+struct TcLayer {
+  int use_tc = 0;        // 1: tcgen05 kernel, 0: FP32 kernel on blocked layouts
+  int kc = 0;            // input channels per K-chunk (<= 64, multiple of 16)
+  int n_cchunks = 0;     // Cin / kc
+  int mt = 1;            // 128-row accumulator tiles per work item
+  size_t slab_bytes = 0; // one (kernel index, chunk) weight image: [kc/8][Cout][8] fp16
+  size_t w16_off = 0;    // byte offset of this layer's images in the tensor-core arena section
+};
+
+struct TcLayerDesc {
+  bool is_conv;
+  const TapConv* taps;
+  int k;
+  TcLayer* tc;
+};
+
+int tc_plan_layers(std::vector<TcLayerDesc>& layers, size_t* tc_arena_bytes);
+
+// pack one layer's fp16 weight images from the fp32 slabs [K][Cin][Cout]
+int tc_pack_weights(const TcLayer& tc, const TapConv& taps, const float* w32_slabs, char* tc_arena,
+                    cudaStream_t stream);
+
+struct TcBufReq {
+  size_t cr;  // max channels * rows-per-frame of plan buffer i
+};
+
+size_t tc_workspace_bytes(const std::vector<TcBufReq>& bufs, int B, int T, int num_mels, int hop);
+
+struct TcOp {
+  bool is_conv;
+  TapConv taps;
+  TcLayer tc;
+  const char* name;
+  int src, dst, res, dst2;
+  int cin, cout, rate_in, rate_out;
+  const float* w32;  // fp32 slabs (FP32-kernel layers)
+  const float* b32;
+};
+
+int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, const char* tc_arena,
+               const float* mel, const int32_t* lengths, int B, int T, int num_mels, int hop, float* wav,
+               void* workspace, cudaStream_t stream, cudaEvent_t* events /* nullptr or [ops+1] */);
+
+int tc_debug_layer(const TcOp& op, const char* tc_arena, const float* x, const float* residual, int B, int Lin,
+                   float* y, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+}  // namespace mb

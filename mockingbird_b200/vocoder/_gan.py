@@ -1,0 +1,247 @@
+"""Host side of the GAN vocoder generators (HiFi-GAN, Fre-GAN) over the mb_gan_* C ABI.
+
+Mirrors the reference's ``Generator`` / ``FreGAN`` module surface (hifigan/models.py:96-162,
+fregan/generator.py:79-179): construct from an AttrDict-like ``h``, ``load_state_dict`` with the
+checkpoint's ``weight_g`` / ``weight_v`` keys, ``eval()``, ``remove_weight_norm()``, ``to(device)``,
+call with ``mel [B, 80, T]`` -> ``wav [B, 1, T*hop]``.  All arithmetic runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from .. import _lib
+
+
+def _cfg_get(h, key, default=None):
+    if isinstance(h, dict):
+        return h.get(key, default)
+    return getattr(h, key, default)
+
+
+def fold_weight_norm(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """``remove_weight_norm`` (hifigan/models.py:152-162): w = g * v / ||v|| with the norm over all
+    dims but 0 (weight_norm's default dim=0: C_out for Conv1d, C_in for ConvTranspose1d).
+    Load-time only, evaluated with torch ops on the tensors' own device."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if k.endswith(".weight_g"):
+            base = k[: -len(".weight_g")]
+            wv = sd[base + ".weight_v"].float()
+            norm = wv.reshape(wv.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (wv.dim() - 1)))
+            out[base + ".weight"] = wv * (v.float() / norm)
+        elif k.endswith(".weight_v"):
+            continue
+        else:
+            out[k] = v
+    return out
+
+
+class GanGenerator:
+    """Common implementation; subclasses set KIND."""
+
+    KIND = _lib.MB_GAN_HIFIGAN
+
+    def __init__(self, h, precision: str = "f16tc", top_k: int = 4):
+        self.h = h
+        if _cfg_get(h, "sampling_rate", 16000) == 24000 and self.KIND == _lib.MB_GAN_HIFIGAN:
+            raise NotImplementedError("the 24 kHz InterpolationBlock variant (hifigan/models.py:105-117) "
+                                      "is not part of the B200 path")
+        rates = list(_cfg_get(h, "upsample_rates"))
+        kernels = list(_cfg_get(h, "upsample_kernel_sizes"))
+        rks = list(_cfg_get(h, "resblock_kernel_sizes"))
+        rds = [list(d) for d in _cfg_get(h, "resblock_dilation_sizes")]
+        cfg = _lib.GanConfig()
+        cfg.kind = self.KIND
+        cfg.num_mels = 80  # hifigan/models.py:99 hard-codes 80 input channels
+        cfg.upsample_initial_channel = int(_cfg_get(h, "upsample_initial_channel"))
+        cfg.num_upsamples = len(rates)
+        for i, (u, k) in enumerate(zip(rates, kernels)):
+            cfg.upsample_rates[i] = int(u)
+            cfg.upsample_kernel_sizes[i] = int(k)
+        cfg.num_kernels = len(rks)
+        cfg.num_dilations = len(rds[0])
+        for j, (k, d) in enumerate(zip(rks, rds)):
+            cfg.resblock_kernel_sizes[j] = int(k)
+            if len(d) != len(rds[0]):
+                raise ValueError("resblock_dilation_sizes must be rectangular")
+            for m, dd in enumerate(d):
+                cfg.resblock_dilation_sizes[j][m] = int(dd)
+        cfg.resblock_type = 1 if str(_cfg_get(h, "resblock")) == "1" else 2
+        cfg.fregan_top_k = int(top_k)
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        cfg.precision = _lib.PRECISIONS[precision]
+        self.precision = precision
+        self._cfg = cfg
+        self.num_kernels = len(rks)
+        self.num_upsamples = len(rates)
+        self._handle = C.c_void_p()
+        _lib.check(_lib.lib().mb_gan_create(C.byref(cfg), C.byref(self._handle)))
+        self.hop = int(_lib.lib().mb_gan_hop(self._handle))
+        self._state: Optional[Dict[str, torch.Tensor]] = None  # host-side copy of the checkpoint
+        self._arena: Optional[torch.Tensor] = None
+        self._workspace: Optional[torch.Tensor] = None
+        self._device: Optional[torch.device] = None
+        self._ready = False
+        self.training = True
+
+    # -- nn.Module-like surface ------------------------------------------------------------------
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        self._state = {k: v.detach() for k, v in state_dict.items()}
+        self._ready = False
+        return self
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return dict(self._state or {})
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        self.training = mode
+        return self
+
+    def to(self, device):
+        self._device = torch.device(device)
+        if self._device.type != "cuda":
+            raise _lib.MbError("mockingbird_b200 generators run on CUDA only (no CPU fallback)")
+        self._ready = False
+        return self
+
+    def cuda(self):
+        return self.to(_lib.require_cuda())
+
+    def remove_weight_norm(self):
+        """Fold weight-norm and upload/pack the weights (hifigan/inference.py:53)."""
+        if self._state is None:
+            raise _lib.MbError("load_state_dict must be called before remove_weight_norm")
+        self._state = fold_weight_norm(self._state)
+        self._upload()
+        return self
+
+    # -- weights ---------------------------------------------------------------------------------
+    def _upload(self):
+        dev = self._device or _lib.require_cuda()
+        self._device = dev
+        L = _lib.lib()
+        nbytes = int(L.mb_gan_arena_bytes(self._handle))
+        with torch.cuda.device(dev):
+            self._arena = torch.zeros(nbytes + 256, dtype=torch.uint8, device=dev)
+            base = (self._arena.data_ptr() + 255) // 256 * 256
+            _lib.check(L.mb_gan_set_arena(self._handle, C.c_void_p(base), nbytes))
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            keep = []
+            for name, t in fold_weight_norm(self._state).items():
+                if not (name.endswith(".weight") or name.endswith(".bias")):
+                    continue
+                d = t.to(device=dev, dtype=torch.float32).contiguous()
+                keep.append(d)
+                dims = (C.c_int64 * d.dim())(*d.shape)
+                _lib.check(L.mb_gan_set_weight(self._handle, name.encode(), C.c_void_p(d.data_ptr()), dims,
+                                               d.dim(), C.c_void_p(stream)))
+            torch.cuda.current_stream(dev).synchronize()
+            _lib.check(L.mb_gan_finalize(self._handle))
+        self._ready = True
+
+    def packed_arena(self) -> torch.Tensor:
+        """The packed device weights as one uint8 tensor (what multi-GPU start-up broadcasts)."""
+        if not self._ready:
+            self._upload()
+        return self._arena
+
+    # -- forward ---------------------------------------------------------------------------------
+    def _ensure_workspace(self, B: int, T: int) -> torch.Tensor:
+        need = int(_lib.lib().mb_gan_workspace_bytes(self._handle, B, T)) + 256
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self._device)
+        return self._workspace
+
+    def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """mel [B, 80, T] (cuda fp32) -> wav [B, 1, T*hop].  ``lengths`` (int32 [B], optional, an
+        extension over the reference) gives valid frames per utterance for padded batches."""
+        if not self._ready:
+            if self._state is None:
+                raise _lib.MbError("Generator has no weights: call load_state_dict first")
+            self._upload()
+        if x.device.type != "cuda":
+            raise _lib.MbError("Generator.forward expects a CUDA tensor (no CPU fallback)")
+        if x.dim() != 3 or x.shape[1] != 80:
+            raise ValueError(f"expected mel of shape [B, 80, T], got {tuple(x.shape)}")
+        x = x.to(torch.float32).contiguous()
+        B, _, T = x.shape
+        out = torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=x.device)
+        if B == 0 or T == 0:
+            return out
+        with torch.cuda.device(x.device):
+            ws = self._ensure_workspace(B, T)
+            lp = None
+            if lengths is not None:
+                lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+                lp = C.c_void_p(lengths.data_ptr())
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(_lib.lib().mb_gan_forward(self._handle, C.c_void_p(x.data_ptr()), lp, B, T,
+                                                 C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                                 ws.numel(), C.c_void_p(stream)))
+        return out
+
+    __call__ = forward
+
+    # -- measurement hooks (bench.py roofline) ---------------------------------------------------
+    def forward_profiled(self, x: torch.Tensor):
+        """forward with CUDA events around every layer; returns (wav, [ms per layer])."""
+        if not self._ready:
+            self._upload()
+        x = x.to(torch.float32).contiguous()
+        B, _, T = x.shape
+        out = torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=x.device)
+        n = self.num_layers()
+        ms = (C.c_float * n)()
+        with torch.cuda.device(x.device):
+            ws = self._ensure_workspace(B, T)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(_lib.lib().mb_gan_forward_profiled(self._handle, C.c_void_p(x.data_ptr()), None, B, T,
+                                                          C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                                          ws.numel(), C.c_void_p(stream), ms))
+        return out, list(ms)
+
+    def layer_work(self, i: int, B: int, T: int):
+        macs, nbytes = C.c_double(), C.c_double()
+        _lib.check(_lib.lib().mb_gan_layer_work(self._handle, i, B, T, C.byref(macs), C.byref(nbytes)))
+        return macs.value, nbytes.value
+
+    # -- test hooks ------------------------------------------------------------------------------
+    def num_layers(self) -> int:
+        return int(_lib.lib().mb_gan_num_layers(self._handle))
+
+    def layer_info(self, i: int) -> str:
+        buf = C.create_string_buffer(256)
+        _lib.check(_lib.lib().mb_gan_layer_info(self._handle, i, buf, 256))
+        return buf.value.decode()
+
+    def debug_layer(self, i: int, x: torch.Tensor, residual: Optional[torch.Tensor], out_rows: int) -> torch.Tensor:
+        if not self._ready:
+            self._upload()
+        x = x.contiguous().float()
+        B, _, L = x.shape
+        info = self.layer_info(i)
+        cout = int(info.split("cout=")[1].split()[0])
+        y = torch.zeros(B, cout, out_rows, dtype=torch.float32, device=x.device)
+        ws = torch.empty(max(1 << 20, 64 * (x.numel() + y.numel()) + (1 << 20)), dtype=torch.uint8, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rp = C.c_void_p(residual.contiguous().data_ptr()) if residual is not None else None
+        _lib.check(_lib.lib().mb_gan_debug_layer(self._handle, i, C.c_void_p(x.data_ptr()), rp, B, L,
+                                                 C.c_void_p(y.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                 C.c_void_p(stream)))
+        return y
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                _lib.lib().mb_gan_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass

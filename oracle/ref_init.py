@@ -1,0 +1,158 @@
+"""Seeded re-creation of the reference's random-init weights WITHOUT the reference tree
+(TEST INFRASTRUCTURE - used by tests/, bench.py's baseline legs and smoke() only).
+
+The reference ships no checkpoints, so every parity case uses the weights
+``torch.manual_seed(seed); Model(...)`` would produce.  /root/reference does not exist on the GPU
+box and 13 M parameters are too large to commit as fixtures, so this file restates the *order in
+which the reference constructors consume the global torch RNG* (module construction order and the
+``.apply(init_weights)`` passes) and rebuilds the tensors from plain ``torch.nn`` layers:
+
+  HiFi-GAN  Generator.__init__   models/vocoder/hifigan/models.py:96-132
+  Fre-GAN   FreGAN.__init__      models/vocoder/fregan/generator.py:79-135
+  WaveRNN   WaveRNN.__init__     models/vocoder/wavernn/models/fatchord_version.py:88-116
+
+tests/test_oracle_pinned.py checks (in the build container, where the reference can be imported)
+that these dicts are bit-identical to the reference modules' state_dicts, and the committed golden
+outputs under tests/golden/ pin them on the GPU box.
+
+Note: ``init_weights`` (utils/util.py:55-58) runs ``m.weight.data.normal_(0, 0.01)`` on modules that
+are already wrapped by the old ``torch.nn.utils.weight_norm``; there ``m.weight`` is the derived
+attribute, not ``weight_v``, so the draw is consumed from the RNG but does not change the
+effective weights - they keep Conv1d's default kaiming-uniform init.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+
+def _fold(w: torch.Tensor) -> torch.Tensor:
+    """what remove_weight_norm leaves behind: _weight_norm(v, g=||v||, dim=0)."""
+    g = torch.norm_except_dim(w, 2, 0)
+    return torch._weight_norm(w, g, 0)
+
+
+def _burn_normal(shape) -> None:
+    torch.empty(shape).normal_(0.0, 0.01)
+
+
+def _put(sd, name, m) -> None:
+    sd[name + ".weight"] = _fold(m.weight.detach())
+    sd[name + ".bias"] = m.bias.detach().clone()
+
+
+def _resblocks(sd, cfg, n_stages: int) -> None:
+    C0 = cfg["upsample_initial_channel"]
+    ks, ds = cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"]
+    nk = len(ks)
+    for i in range(n_stages):
+        ch = C0 // (2 ** (i + 1))
+        for j, (k, d) in enumerate(zip(ks, ds)):
+            base = f"resblocks.{i * nk + j}"
+            if str(cfg["resblock"]) == "1":
+                for group in ("convs1", "convs2"):
+                    mods = [torch.nn.Conv1d(ch, ch, k) for _ in d]
+                    for m_i, m in enumerate(mods):
+                        _put(sd, f"{base}.{group}.{m_i}", m)
+                    for m in mods:
+                        _burn_normal(m.weight.shape)
+            else:
+                mods = [torch.nn.Conv1d(ch, ch, k) for _ in d]
+                for m_i, m in enumerate(mods):
+                    _put(sd, f"{base}.convs.{m_i}", m)
+                for m in mods:
+                    _burn_normal(m.weight.shape)
+
+
+def hifigan_state_dict(cfg: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Folded (weight-norm removed) generator weights of ``torch.manual_seed(seed); Generator(h)``."""
+    torch.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    C0 = cfg["upsample_initial_channel"]
+    _put(sd, "conv_pre", torch.nn.Conv1d(80, C0, 7))
+    ups = []
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        m = torch.nn.ConvTranspose1d(C0 // (2 ** i), C0 // (2 ** (i + 1)), k, u)
+        ups.append(m)
+        _put(sd, f"ups.{i}", m)
+    _resblocks(sd, cfg, len(ups))
+    post = torch.nn.Conv1d(C0 // (2 ** len(ups)), 1, 7)
+    _put(sd, "conv_post", post)
+    for m in ups:
+        _burn_normal(m.weight.shape)
+    _burn_normal(post.weight.shape)
+    return sd
+
+
+def fregan_state_dict(cfg: dict, seed: int = 0, top_k: int = 4) -> Dict[str, torch.Tensor]:
+    torch.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    C0 = cfg["upsample_initial_channel"]
+    rates, kernels = cfg["upsample_rates"], cfg["upsample_kernel_sizes"]
+    n_up = len(rates)
+    _put(sd, "conv_pre", torch.nn.Conv1d(80, C0, 7))
+    ups, cond_up, res_out = [], [], []
+    kr = 80
+    for i, (u, k) in enumerate(zip(rates, kernels)):
+        m = torch.nn.ConvTranspose1d(C0 // (2 ** i), C0 // (2 ** (i + 1)), k, u)
+        ups.append(m)
+        _put(sd, f"ups.{i}", m)
+        if i > (n_up - top_k):
+            r = torch.nn.Conv1d(C0 // (2 ** i), C0 // (2 ** (i + 1)), 1)
+            _put(sd, f"res_output.{len(res_out)}.1", r)
+            res_out.append(r)
+        if i >= (n_up - top_k):
+            c = torch.nn.ConvTranspose1d(kr, C0 // (2 ** i), kernels[i - 1], rates[i - 1])
+            _put(sd, f"cond_up.{len(cond_up)}", c)
+            cond_up.append(c)
+            kr = C0 // (2 ** i)
+    _resblocks(sd, cfg, n_up)
+    post = torch.nn.Conv1d(C0 // (2 ** n_up), 1, 7)
+    _put(sd, "conv_post", post)
+    for m in ups:
+        _burn_normal(m.weight.shape)
+    _burn_normal(post.weight.shape)
+    for m in cond_up:
+        _burn_normal(m.weight.shape)
+    for m in res_out:
+        _burn_normal(m.weight.shape)
+    return sd
+
+
+HIFIGAN_CONFIG_16K = {
+    "resblock": "1", "seed": 1234,
+    "upsample_rates": [5, 5, 4, 2], "upsample_kernel_sizes": [10, 10, 8, 4],
+    "upsample_initial_channel": 512, "resblock_kernel_sizes": [3, 7, 11],
+    "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+    "num_mels": 80, "hop_size": 200, "sampling_rate": 16000,
+}
+
+FREGAN_CONFIG = {
+    "resblock": "1", "seed": 1234,
+    "upsample_rates": [5, 5, 2, 2, 2], "upsample_kernel_sizes": [10, 10, 4, 4, 4],
+    "upsample_initial_channel": 512, "resblock_kernel_sizes": [3, 7, 11],
+    "resblock_dilation_sizes": [[1, 3, 5, 7], [1, 3, 5, 7], [1, 3, 5, 7]],
+    "num_mels": 80, "hop_size": 200, "sampling_rate": 16000,
+}
+
+
+def rescale_variance_preserving(sd: Dict[str, torch.Tensor], gain: float, seed: int = 7) -> Dict[str, torch.Tensor]:
+    """A second, harder parity init: re-draw every conv weight with std = gain/sqrt(fan_in) and
+    N(0,0.05) biases so activations stay O(1) through the stack like a trained model's."""
+    import math
+
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k, v in sd.items():
+        if k.endswith(".weight"):
+            if k.startswith("ups.") or k.startswith("cond_up."):
+                # ConvTranspose1d [Cin, Cout, K]: each output sees Cin*K/stride taps
+                stride = max(1, v.shape[2] // 2)
+                fan_in = v.shape[0] * v.shape[2] / stride
+            else:
+                fan_in = v.shape[1] * v.shape[2]
+            out[k] = torch.randn(v.shape, generator=g) * (gain / math.sqrt(fan_in))
+        else:
+            out[k] = torch.randn(v.shape, generator=g) * 0.05
+    return out

@@ -1,0 +1,108 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/mockingbird_b200.h declares;
+handle creation / plan building / error paths work without a GPU (no compute calls)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+from mockingbird_b200 import _lib
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "mockingbird_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    lib = _lib.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in the header but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert lib.mb_version().startswith(b"mockingbird_b200")
+
+
+def _hifigan_cfg(precision=_lib.MB_PREC_FP32):
+    from mockingbird_b200.vocoder.hifigan.models import DEFAULT_CONFIG_16K as h
+
+    cfg = _lib.GanConfig()
+    cfg.kind = _lib.MB_GAN_HIFIGAN
+    cfg.num_mels = 80
+    cfg.upsample_initial_channel = h["upsample_initial_channel"]
+    cfg.num_upsamples = 4
+    for i in range(4):
+        cfg.upsample_rates[i] = h["upsample_rates"][i]
+        cfg.upsample_kernel_sizes[i] = h["upsample_kernel_sizes"][i]
+    cfg.num_kernels = 3
+    cfg.num_dilations = 3
+    for j in range(3):
+        cfg.resblock_kernel_sizes[j] = h["resblock_kernel_sizes"][j]
+        for m in range(3):
+            cfg.resblock_dilation_sizes[j][m] = h["resblock_dilation_sizes"][j][m]
+    cfg.resblock_type = 1
+    cfg.fregan_top_k = 4
+    cfg.precision = precision
+    return cfg
+
+
+@pytest.mark.parametrize("precision", [_lib.MB_PREC_FP32, _lib.MB_PREC_F16TC])
+def test_gan_plan_shape(precision):
+    lib = _lib.lib()
+    h = C.c_void_p()
+    cfg = _hifigan_cfg(precision)
+    _lib.check(lib.mb_gan_create(C.byref(cfg), C.byref(h)))
+    try:
+        assert lib.mb_gan_hop(h) == 200
+        # conv_pre + 4 ups + 72 resblock convs + conv_post
+        assert lib.mb_gan_num_layers(h) == 78
+        buf = C.create_string_buffer(256)
+        _lib.check(lib.mb_gan_layer_info(h, 0, buf, 256))
+        assert b"conv_pre" in buf.value and b"cin=80" in buf.value
+        assert lib.mb_gan_arena_bytes(h) >= 12_975_745 * 4
+        assert lib.mb_gan_workspace_bytes(h, 2, 16) > 0
+        # forward before weights are set must fail loudly, not compute
+        rc = lib.mb_gan_forward(h, C.c_void_p(256), None, 1, 8, C.c_void_p(256), C.c_void_p(256), 1 << 30, None)
+        assert rc == 2 and b"finalized" in lib.mb_last_error()
+    finally:
+        lib.mb_gan_destroy(h)
+
+
+def test_gan_bad_config_rejected():
+    lib = _lib.lib()
+    h = C.c_void_p()
+    cfg = _hifigan_cfg()
+    cfg.upsample_kernel_sizes[0] = 11  # (k=11,u=5) does not give u*L samples
+    assert lib.mb_gan_create(C.byref(cfg), C.byref(h)) == 1
+    assert b"upsample" in lib.mb_last_error()
+    cfg = _hifigan_cfg()
+    cfg.resblock_kernel_sizes[0] = 13
+    assert lib.mb_gan_create(C.byref(cfg), C.byref(h)) == 1
+
+
+def test_fregan_plan():
+    from mockingbird_b200.vocoder.fregan.models import DEFAULT_CONFIG, FreGAN
+
+    g = FreGAN(DEFAULT_CONFIG, precision="fp32")
+    assert g.hop == 200
+    infos = [g.layer_info(i) for i in range(g.num_layers())]
+    assert sum("cond_up" in s for s in infos) == 4
+    assert sum("res_output" in s for s in infos) == 3
+    assert sum("resblocks" in s for s in infos) == 120
+
+
+def test_generator_without_cuda_fails_loudly():
+    import torch
+    from mockingbird_b200.vocoder.hifigan.models import DEFAULT_CONFIG_16K, Generator
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    g = Generator(DEFAULT_CONFIG_16K, precision="fp32")
+    with pytest.raises(_lib.MbError):
+        g.cuda()
+    with pytest.raises(_lib.MbError):
+        g.to("cpu")

@@ -1,0 +1,91 @@
+"""CPU tests: the oracle restatements are pinned (a) against the committed golden vectors that
+oracle/make_golden.py produced from the LIVE reference and (b), where /root/reference exists
+(build container), directly against the reference modules."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gan_oracle as go
+import ref_harness as rh
+import ref_init as ri
+
+needs_ref = pytest.mark.skipif(not rh.reference_available(), reason="/root/reference not present")
+
+
+def test_hifigan_oracle_matches_golden(golden_dir):
+    z = np.load(golden_dir / "hifigan_seed0.npz")
+    sd = ri.hifigan_state_dict(ri.HIFIGAN_CONFIG_16K, 0)
+    with torch.no_grad():
+        wav = go.hifigan_forward(sd, ri.HIFIGAN_CONFIG_16K, torch.from_numpy(z["mel_small"]))
+    e = go.rel_errors(wav, torch.from_numpy(z["wav_small"]))
+    # same torch build -> bit-identical; other CPU capability / thread count -> last-ulp noise only
+    assert e["max_rel"] < 1e-5 and e["rms_rel"] < 1e-5, (e, json.loads(str(z["meta"])))
+
+
+def test_hifigan_oracle_matches_golden_full_length(golden_dir):
+    z = np.load(golden_dir / "hifigan_seed0.npz")
+    sd = ri.hifigan_state_dict(ri.HIFIGAN_CONFIG_16K, 0)
+    mel = torch.rand(32, 80, 256, generator=torch.Generator().manual_seed(2)) * 8 - 4
+    with torch.no_grad():
+        wav = go.hifigan_forward(sd, ri.HIFIGAN_CONFIG_16K, mel[[int(i) for i in z["full_pick"]]])
+    e = go.rel_errors(wav, torch.from_numpy(z["wav_full"]))
+    assert e["max_rel"] < 1e-5, e
+
+
+def test_fregan_oracle_matches_golden(golden_dir):
+    z = np.load(golden_dir / "fregan_seed0.npz")
+    sd = ri.fregan_state_dict(ri.FREGAN_CONFIG, 0)
+    with torch.no_grad():
+        wav = go.fregan_forward(sd, ri.FREGAN_CONFIG, torch.from_numpy(z["mel"]))
+    e = go.rel_errors(wav, torch.from_numpy(z["wav"]))
+    assert e["max_rel"] < 1e-5, e
+
+
+def test_work_figures_match_survey():
+    w = go.hifigan_work(ri.HIFIGAN_CONFIG_16K, 256)
+    assert w["macs"] == 45_068_779_520
+    assert w["params"] == 12_975_745
+    assert w["act_elems"] == 168_433_664
+    assert w["samples"] == 51_200
+
+
+def test_fold_weight_norm_identity():
+    v = torch.randn(8, 4, 3)
+    g = v.reshape(8, -1).norm(dim=1).reshape(8, 1, 1) * 2.0
+    out = go.fold_weight_norm({"c.weight_g": g, "c.weight_v": v, "c.bias": torch.zeros(8)})
+    assert torch.allclose(out["c.weight"], 2.0 * v, rtol=1e-6, atol=1e-7)
+
+
+@needs_ref
+@pytest.mark.reference
+def test_ref_init_bit_identical_to_reference_constructors():
+    rh.install()
+    rh.hide_cuda()
+    g = rh.build_hifigan(seed=5)
+    sd = ri.hifigan_state_dict(ri.HIFIGAN_CONFIG_16K, 5)
+    ref = g.state_dict()
+    assert set(sd) == set(ref)
+    assert all(torch.equal(sd[k], ref[k]) for k in sd)
+    f = rh.build_fregan(seed=6)
+    sd = ri.fregan_state_dict(ri.FREGAN_CONFIG, 6)
+    ref = f.state_dict()
+    assert set(sd) == set(ref)
+    assert all(torch.equal(sd[k], ref[k]) for k in sd)
+    assert rh.hifigan_config()["upsample_rates"] == ri.HIFIGAN_CONFIG_16K["upsample_rates"]
+    assert rh.fregan_config()["resblock_dilation_sizes"] == ri.FREGAN_CONFIG["resblock_dilation_sizes"]
+
+
+@needs_ref
+@pytest.mark.reference
+def test_gan_oracles_bit_identical_to_reference_forward():
+    rh.install()
+    rh.hide_cuda()
+    x = torch.rand(2, 80, 24, generator=torch.Generator().manual_seed(3)) * 8 - 4
+    g = rh.build_hifigan(seed=1)
+    f = rh.build_fregan(seed=1)
+    with torch.no_grad():
+        assert torch.equal(go.hifigan_forward(dict(g.state_dict()), rh.hifigan_config(), x), g(x))
+        assert torch.equal(go.fregan_forward(dict(f.state_dict()), rh.fregan_config(), x), f(x))
