@@ -17,7 +17,7 @@ LIB_PATH = PKG_DIR / "libmockingbird_b200.so"
 STAMP = PKG_DIR / ".libmockingbird_b200.hash"
 
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 

@@ -192,6 +192,11 @@ int build_plan(mb_gan* h) {
     if (c.resblock_kernel_sizes[j] > kMaxTaps || c.resblock_kernel_sizes[j] % 2 == 0)
       return fail(MB_ERR_INVALID, "mb_gan_create: resblock kernel size %d unsupported (odd, <= %d)",
                   c.resblock_kernel_sizes[j], kMaxTaps);
+  for (int j = 0; j < c.num_kernels; ++j)
+    for (int m = 0; m < c.num_dilations; ++m)
+      if ((c.resblock_kernel_sizes[j] - 1) * c.resblock_dilation_sizes[j][m] > 96)
+        return fail(MB_ERR_INVALID, "mb_gan_create: receptive field of resblock kernel %d dilation %d too wide",
+                    c.resblock_kernel_sizes[j], c.resblock_dilation_sizes[j][m]);
   for (int i = 0; i < c.num_upsamples; ++i) {
     const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
     if (u < 1 || u > kMaxPhases) return fail(MB_ERR_INVALID, "mb_gan_create: upsample rate %d unsupported", u);
@@ -316,10 +321,20 @@ std::vector<size_t> buf_offsets(const mb_gan* h, size_t B, size_t T, size_t* tot
   return offs;
 }
 
+TRef ncl(const void* p, int C, int L) {
+  TRef t;
+  t.p = const_cast<void*>(p);
+  t.layout = p ? LAYOUT_NCL : LAYOUT_NONE;
+  t.C = C;
+  t.L = L;
+  return t;
+}
+
 int run_layer_f32(mb_gan* h, const Layer& L, const float* src, const float* res, float* dst, float* dst2,
                   const int32_t* lengths, int B, int T, cudaStream_t st) {
   if (L.kind == OP_ADD) {
-    cudaError_t e = launch_add_inplace_f32(dst, src, (size_t)B * L.cout * L.rate_out * T, st);
+    cudaError_t e = launch_add_inplace_f32(ncl(dst, L.cout, L.rate_out * T), ncl(src, L.cout, L.rate_out * T),
+                                           TRef{}, 1.f, B, st);
     if (e != cudaSuccess) return fail(MB_ERR_CUDA, "add kernel: %s", cudaGetErrorString(e));
     count_launch();
     return MB_OK;
@@ -329,7 +344,14 @@ int run_layer_f32(mb_gan* h, const Layer& L, const float* src, const float* res,
   p.Lin = T * L.rate_in;
   p.Lout = T * L.rate_out;
   p.lengths = lengths;
-  cudaError_t e = launch_tapconv_f32(p, src, h->arena + L.w_off, h->arena + L.b_off, res, dst, dst2, st);
+  TapConvIO io;
+  io.x = ncl(src, L.cin, p.Lin);
+  io.res = ncl(res, L.cout, p.Lout);
+  io.y32 = ncl(dst, L.cout, p.Lout);
+  io.y2_32 = ncl(dst2, L.cout, p.Lout);
+  cudaError_t e = (L.cout == 1 && p.stride == 1)
+                      ? launch_tapconv_cout1_f32(p, io, h->arena + L.w_off, h->arena + L.b_off, st)
+                      : launch_tapconv_f32(p, io, h->arena + L.w_off, h->arena + L.b_off, st);
   if (e != cudaSuccess) return fail(MB_ERR_CUDA, "tapconv_f32 (%s): %s", L.name.c_str(), cudaGetErrorString(e));
   count_launch();
   return MB_OK;
@@ -351,6 +373,7 @@ int mb_gan_create(const mb_gan_config* cfg, mb_gan** out) {
     for (Layer& L : h->layers) {
       TcLayerDesc d{};
       d.is_conv = (L.kind == OP_CONV);
+      d.force_f32 = (L.dst2 != BUF_NONE) || (L.nearest > 1);
       d.taps = &L.taps;
       d.k = L.k;
       d.tc = &L.tc;

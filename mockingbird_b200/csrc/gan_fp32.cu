@@ -1,7 +1,9 @@
-// FP32 FFMA implementation of the tap-conv op (MB_PREC_FP32): the parity anchor of the GAN path.
-// Register-tiled direct convolution, 64(co) x 64(l) output tile per CTA, 4x4 per thread, input
-// window and weight slabs staged through shared memory in chunks of 8 input channels.
-// Reference semantics: hifigan/models.py:35-42, :134-150; fregan/generator.py:137-166.
+// FP32 FFMA implementation of the tap-conv op: the parity anchor of the GAN path (MB_PREC_FP32)
+// and the executor of the few layers the tensor-core path keeps in FP32 (conv_pre: Cin=80,
+// conv_post: Cout=1).  Register-tiled direct convolution, 64(co) x 64(l) output tile per CTA,
+// 4x4 per thread, input window and weight slabs staged through shared memory in chunks of 8
+// input channels.  Reference semantics: hifigan/models.py:35-42, :134-150;
+// fregan/generator.py:137-166.
 #include "gan_kernels.h"
 
 namespace mb {
@@ -11,14 +13,41 @@ namespace {
 constexpr int CO_T = 64;
 constexpr int L_T = 64;
 constexpr int CI_T = 8;
-constexpr int XW_MAX = L_T + 64;  // window: tile + tap span (<= 50 for k=11,d=5)
+constexpr int XW_MAX = L_T + 96;  // window: tile + tap span (70 for k=11,d=7 in Fre-GAN)
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
-__global__ void __launch_bounds__(256) tapconv_f32_kernel(TapConv p, const float* __restrict__ x,
-                                                          const float* __restrict__ w,
-                                                          const float* __restrict__ bias,
-                                                          const float* res, float* y, float* y2) {
+__device__ __forceinline__ float tload(const TRef& t, int b, int c, int l) {
+  const size_t i = tref_index(t, b, c, l);
+  if (t.layout == LAYOUT_F16B) return __half2float(reinterpret_cast<const __half*>(t.p)[i]);
+  return reinterpret_cast<const float*>(t.p)[i];
+}
+
+__device__ __forceinline__ void tstore(const TRef& t, int b, int c, int l, float v) {
+  const size_t i = tref_index(t, b, c, l);
+  if (t.layout == LAYOUT_F16B) reinterpret_cast<__half*>(t.p)[i] = __float2half_rn(v);
+  else reinterpret_cast<float*>(t.p)[i] = v;
+}
+
+// shared epilogue of both FP32 kernels
+__device__ __forceinline__ void epilogue_store(const TapConv& p, const TapConvIO& io, int b, int co, int lo,
+                                               int valid_out, float v) {
+  if (io.res.p) v += tload(io.res, b, co, lo);
+  if (p.mode == EPI_ADD) v = tload(io.y32, b, co, lo) + v;
+  else if (p.mode == EPI_ADD_DIV) v = (tload(io.y32, b, co, lo) + v) / p.div;
+  if (p.act_tanh) v = tanhf(v);
+  if (lo >= valid_out) v = 0.f;
+  if (io.y32.p) tstore(io.y32, b, co, lo, v);
+  if (io.y16.p) tstore(io.y16, b, co, lo, lrelu(v, io.out16_slope));
+  if (io.y2_32.p) {
+    const float s = (lo >= valid_out) ? 0.f : tload(io.y2_32, b, co, lo) + v;
+    tstore(io.y2_32, b, co, lo, s);
+    if (io.y2_16.p) tstore(io.y2_16, b, co, lo, lrelu(s, io.y2_16_slope));
+  }
+}
+
+__global__ void __launch_bounds__(256) tapconv_f32_kernel(TapConv p, TapConvIO io, const float* __restrict__ w,
+                                                          const float* __restrict__ bias) {
   __shared__ float xs[CI_T][XW_MAX];
   __shared__ __align__(16) float ws[kMaxTaps][CI_T][CO_T];
 
@@ -39,6 +68,7 @@ __global__ void __launch_bounds__(256) tapconv_f32_kernel(TapConv p, const float
   const int XW = L_T + (omax - omin);
   const int valid_in = p.lengths ? min(p.Lin, p.lengths[b] * p.len_mul_in) : p.Lin;
   const int valid_out = p.lengths ? min(p.Lout, p.lengths[b] * p.len_mul_out) : p.Lout;
+  const float in_slope = (io.x.layout == LAYOUT_F16B) ? 1.f : p.in_slope;
 
   float acc[4][4];
 #pragma unroll
@@ -46,14 +76,13 @@ __global__ void __launch_bounds__(256) tapconv_f32_kernel(TapConv p, const float
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const float* xb = x + (size_t)b * p.Cin * p.Lin;
   for (int ci0 = 0; ci0 < p.Cin; ci0 += CI_T) {
     // stage input window (activation applied once here)
     for (int i = tid; i < CI_T * XW; i += 256) {
       const int ci = i / XW, j = i - ci * XW;
       const int l = q0 + omin + j;
       float v = 0.f;
-      if (ci0 + ci < p.Cin && l >= 0 && l < valid_in) v = lrelu(xb[(size_t)(ci0 + ci) * p.Lin + l], p.in_slope);
+      if (ci0 + ci < p.Cin && l >= 0 && l < valid_in) v = lrelu(tload(io.x, b, ci0 + ci, l), in_slope);
       xs[ci][j] = v;
     }
     // stage weight slabs
@@ -87,7 +116,6 @@ __global__ void __launch_bounds__(256) tapconv_f32_kernel(TapConv p, const float
     __syncthreads();
   }
 
-  // epilogue
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int co = co0 + ty * 4 + i;
@@ -97,24 +125,105 @@ __global__ void __launch_bounds__(256) tapconv_f32_kernel(TapConv p, const float
     for (int j = 0; j < 4; ++j) {
       const int q = q0 + tx + 16 * j;
       if (q >= p.Lin) continue;
-      const int lo = q * p.stride + r;
-      const size_t idx = ((size_t)b * p.Cout + co) * p.Lout + lo;
-      float v = acc[i][j] + bv;
-      if (res) v += res[idx];
-      if (p.mode == EPI_ADD) v = y[idx] + v;
-      else if (p.mode == EPI_ADD_DIV) v = (y[idx] + v) / p.div;
-      if (p.act_tanh) v = tanhf(v);
-      if (lo >= valid_out) v = 0.f;
-      y[idx] = v;
-      if (y2) y2[idx] = (lo >= valid_out) ? 0.f : y2[idx] + v;
+      epilogue_store(p, io, b, co, q * p.stride + r, valid_out, acc[i][j] + bv);
     }
   }
 }
 
-__global__ void add_inplace_kernel(float* dst, const float* __restrict__ src, size_t n) {
+// Cout == 1: one thread per output row, weights [taps][Cin] in shared memory
+__global__ void __launch_bounds__(256) tapconv_cout1_kernel(TapConv p, TapConvIO io, const float* __restrict__ w,
+                                                            const float* __restrict__ bias) {
+  extern __shared__ float wsm[];  // [ntaps][Cin]
+  const int b = blockIdx.y;
+  const int nt = p.ntaps[0];
+  for (int i = threadIdx.x; i < nt * p.Cin; i += blockDim.x) {
+    const int t = i / p.Cin, ci = i - t * p.Cin;
+    wsm[i] = w[((size_t)p.slab[0][t] * p.Cin + ci) * p.Cout];
+  }
+  __syncthreads();
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= p.Lin) return;
+  const int valid_in = p.lengths ? min(p.Lin, p.lengths[b] * p.len_mul_in) : p.Lin;
+  const int valid_out = p.lengths ? min(p.Lout, p.lengths[b] * p.len_mul_out) : p.Lout;
+  const float in_slope = (io.x.layout == LAYOUT_F16B) ? 1.f : p.in_slope;
+  float acc = 0.f;
+  if (io.x.layout == LAYOUT_F32B) {
+    const float4* xp = reinterpret_cast<const float4*>(io.x.p);
+    for (int c4 = 0; c4 < (p.Cin >> 2); ++c4) {
+      const float4* run = xp + ((size_t)b * (p.Cin >> 2) + c4) * p.Lin;
+      for (int t = 0; t < nt; ++t) {
+        const int li = l + p.off[0][t];
+        if (li < 0 || li >= valid_in) continue;
+        const float4 v = run[li];
+        const float* wt = &wsm[t * p.Cin + c4 * 4];
+        acc = fmaf(wt[0], lrelu(v.x, in_slope), acc);
+        acc = fmaf(wt[1], lrelu(v.y, in_slope), acc);
+        acc = fmaf(wt[2], lrelu(v.z, in_slope), acc);
+        acc = fmaf(wt[3], lrelu(v.w, in_slope), acc);
+      }
+    }
+  } else {
+    for (int ci = 0; ci < p.Cin; ++ci)
+      for (int t = 0; t < nt; ++t) {
+        const int li = l + p.off[0][t];
+        if (li < 0 || li >= valid_in) continue;
+        acc = fmaf(wsm[t * p.Cin + ci], lrelu(tload(io.x, b, ci, li), in_slope), acc);
+      }
+  }
+  epilogue_store(p, io, b, 0, l, valid_out, acc + (bias ? bias[0] : 0.f));
+}
+
+__global__ void add_inplace_kernel(TRef dst32, TRef src32, TRef dst16, float slope, int B) {
+  const size_t n = (size_t)B * dst32.C * dst32.L;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) dst[i] += src[i];
+  float* d = reinterpret_cast<float*>(dst32.p);
+  const float* s = reinterpret_cast<const float*>(src32.p);
+  for (; i < n; i += stride) {
+    const float v = d[i] + s[i];
+    d[i] = v;
+    if (dst16.p) {
+      // decode (b, c, l) from the fp32 layout's linear index
+      int b, c, l;
+      if (dst32.layout == LAYOUT_NCL) {
+        l = (int)(i % dst32.L);
+        c = (int)((i / dst32.L) % dst32.C);
+        b = (int)(i / ((size_t)dst32.L * dst32.C));
+      } else {
+        const int e = (int)(i & 3);
+        const size_t j = i >> 2;
+        l = (int)(j % dst32.L);
+        const size_t g = j / dst32.L;
+        c = (int)(g % (dst32.C >> 2)) * 4 + e;
+        b = (int)(g / (dst32.C >> 2));
+      }
+      tstore(dst16, b, c, l, lrelu(v, slope));
+    }
+  }
+}
+
+__global__ void zero_pads_kernel(TRef plane, int B) {
+  // one thread per (run, pad row, 16-byte lane)
+  const int Lp = plane.L + 2 * kPadRows;
+  const size_t runs = (size_t)B * (plane.C >> 3);
+  const size_t n = runs * (2 * kPadRows);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t run = i / (2 * kPadRows);
+  const int pr = (int)(i % (2 * kPadRows));
+  const int row = pr < kPadRows ? pr : plane.L + pr;  // [0,PAD) and [PAD+L, PAD+L+PAD)
+  uint4* ptr = reinterpret_cast<uint4*>(plane.p) + run * Lp + row;
+  *ptr = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void convert_layout_kernel(TRef src, TRef dst, int B, float slope) {
+  const size_t n = (size_t)B * src.C * src.L;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = (int)(i % src.L);
+  const int c = (int)((i / src.L) % src.C);
+  const int b = (int)(i / ((size_t)src.L * src.C));
+  tstore(dst, b, c, l, lrelu(tload(src, b, c, l), slope));
 }
 
 __global__ void pack_slabs_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin,
@@ -131,18 +240,44 @@ __global__ void pack_slabs_kernel(const float* __restrict__ w, float* __restrict
 
 }  // namespace
 
-cudaError_t launch_tapconv_f32(const TapConv& p, const float* x, const float* w, const float* bias,
-                               const float* res, float* y, float* y2, cudaStream_t stream) {
+cudaError_t launch_tapconv_f32(const TapConv& p, const TapConvIO& io, const float* w, const float* bias,
+                               cudaStream_t stream) {
   dim3 grid((p.Lin + L_T - 1) / L_T, (p.Cout + CO_T - 1) / CO_T, p.B * p.stride);
-  tapconv_f32_kernel<<<grid, 256, 0, stream>>>(p, x, w, bias, res, y, y2);
+  tapconv_f32_kernel<<<grid, 256, 0, stream>>>(p, io, w, bias);
   return cudaGetLastError();
 }
 
-cudaError_t launch_add_inplace_f32(float* dst, const float* src, size_t n, cudaStream_t stream) {
+cudaError_t launch_tapconv_cout1_f32(const TapConv& p, const TapConvIO& io, const float* w, const float* bias,
+                                     cudaStream_t stream) {
+  if (p.Cout != 1 || p.stride != 1) return cudaErrorInvalidValue;
+  dim3 grid((p.Lin + 255) / 256, p.B);
+  const size_t smem = sizeof(float) * p.ntaps[0] * p.Cin;
+  tapconv_cout1_kernel<<<grid, 256, smem, stream>>>(p, io, w, bias);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_inplace_f32(const TRef& dst32, const TRef& src32, const TRef& dst16, float slope, int B,
+                                   cudaStream_t stream) {
+  const size_t n = (size_t)B * dst32.C * dst32.L;
   const int threads = 256;
   size_t blocks = (n + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  add_inplace_kernel<<<(unsigned)blocks, threads, 0, stream>>>(dst, src, n);
+  if (blocks == 0) return cudaSuccess;
+  add_inplace_kernel<<<(unsigned)blocks, threads, 0, stream>>>(dst32, src32, dst16, slope, B);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zero_pads_f16(const TRef& plane, int B, cudaStream_t stream) {
+  const size_t n = (size_t)B * (plane.C >> 3) * (2 * kPadRows);
+  if (n == 0) return cudaSuccess;
+  zero_pads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(plane, B);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert_layout(const TRef& src, const TRef& dst, int B, float slope, cudaStream_t stream) {
+  const size_t n = (size_t)B * src.C * src.L;
+  if (n == 0) return cudaSuccess;
+  convert_layout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, B, slope);
   return cudaGetLastError();
 }
 

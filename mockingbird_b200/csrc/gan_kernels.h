@@ -10,6 +10,7 @@
 // followed by a fused epilogue (residual add, MRF accumulate / mean, tanh, length mask).
 // reference: hifigan/models.py:35-42 (ResBlock1), :134-150 (Generator.forward).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -17,6 +18,7 @@ namespace mb {
 
 constexpr int kMaxTaps = 11;    // resblock kernel sizes are (3,7,11)
 constexpr int kMaxPhases = 8;   // upsample rates are (5,5,4,2) / (5,5,2,2,2)
+constexpr int kPadRows = 40;    // zero rows on both sides of every run of an fp16 activation plane
 
 enum EpiMode : int {
   EPI_STORE = 0,     // y = v
@@ -42,14 +44,54 @@ struct TapConv {
   int len_mul_in, len_mul_out;
 };
 
-// ---- FP32 path: tensors are [B][C][L] fp32 (reference layout) ------------------------------
-// w: [kernel_size slabs][Cin][Cout] fp32 ; bias [Cout] or nullptr ; res [B][Cout][Lout] or nullptr
-// y2 (optional): second destination receiving y2 += v_final (Fre-GAN "x += cond_up(mel)")
-cudaError_t launch_tapconv_f32(const TapConv& p, const float* x, const float* w, const float* bias,
-                               const float* res, float* y, float* y2, cudaStream_t stream);
+// Activation tensor layouts ------------------------------------------------------------------
+//   LAYOUT_NCL : fp32 [B][C][L]                      (the reference's layout; API boundary)
+//   LAYOUT_F32B: fp32 [B][C/4][L][4]                 (residual streams of the tensor-core path)
+//   LAYOUT_F16B: fp16 [B][C/8][L + 2*kPadRows][8]    (MMA operand planes: already activated,
+//                 rows [kPadRows, kPadRows+L) hold data, pad rows are zero so that a conv window
+//                 can be fetched with one bulk copy per 8-channel run)
+enum Layout : int { LAYOUT_NONE = 0, LAYOUT_NCL = 1, LAYOUT_F32B = 2, LAYOUT_F16B = 3 };
 
-// dst[i] += src[i]
-cudaError_t launch_add_inplace_f32(float* dst, const float* src, size_t n, cudaStream_t stream);
+struct TRef {
+  void* p = nullptr;
+  int layout = LAYOUT_NONE;
+  int C = 0, L = 0;
+};
+
+__host__ __device__ inline size_t tref_index(const TRef& t, int b, int c, int l) {
+  if (t.layout == LAYOUT_NCL) return ((size_t)b * t.C + c) * t.L + l;
+  if (t.layout == LAYOUT_F32B) return (((size_t)b * (t.C >> 2) + (c >> 2)) * t.L + l) * 4 + (c & 3);
+  return (((size_t)b * (t.C >> 3) + (c >> 3)) * (t.L + 2 * kPadRows) + kPadRows + l) * 8 + (c & 7);
+}
+
+// ---- FP32 FFMA kernels ------------------------------------------------------------------------
+// w: [kernel_size slabs][Cin][Cout] fp32 ; bias [Cout] or nullptr.
+//   x      input (any layout; an F16B input is already activated: in_slope is ignored for it)
+//   res    residual (fp32 layouts) or none
+//   y32    fp32 destination (NCL / F32B) or none: receives v per the epilogue mode
+//   y16    fp16 destination plane or none: receives leaky_relu(v_final, out16_slope)
+//   y2_32 / y2_16: second destination (Fre-GAN "x += cond_up(mel)"): y2 += v, y2_16 = lrelu(y2)
+struct TapConvIO {
+  TRef x, res, y32, y16, y2_32, y2_16;
+  float out16_slope = 1.f;
+  float y2_16_slope = 1.f;
+};
+cudaError_t launch_tapconv_f32(const TapConv& p, const TapConvIO& io, const float* w, const float* bias,
+                               cudaStream_t stream);
+
+// Cout == 1 special case (conv_post, models.py:146-148): one thread per output sample
+cudaError_t launch_tapconv_cout1_f32(const TapConv& p, const TapConvIO& io, const float* w, const float* bias,
+                                     cudaStream_t stream);
+
+// dst32 += src32 (same layout), optionally refresh dst16 = lrelu(dst32, slope)
+cudaError_t launch_add_inplace_f32(const TRef& dst32, const TRef& src32, const TRef& dst16, float slope, int B,
+                                   cudaStream_t stream);
+
+// zero the pad rows of an fp16 plane of geometry (B, C, L)
+cudaError_t launch_zero_pads_f16(const TRef& plane, int B, cudaStream_t stream);
+
+// layout conversion (debug/test hook only): NCL fp32 <-> blocked planes
+cudaError_t launch_convert_layout(const TRef& src, const TRef& dst, int B, float slope, cudaStream_t stream);
 
 // weight repack: Conv1d weight [Cout][Cin][K] or ConvTranspose1d weight [Cin][Cout][K]
 //   -> slabs [K][Cin][Cout]

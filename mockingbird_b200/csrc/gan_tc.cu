@@ -1,10 +1,730 @@
-// placeholder - replaced by the tcgen05 implementation
+// Tensor-core execution of the GAN generator plan (MB_PREC_F16TC), sm_100a only.
+//
+// tc_conv_kernel: the tap conv (gan_kernels.h) as an implicit GEMM on tcgen05 tensor cores.
+//   D[128 rows x Cout] (fp32, TMEM) += A[128 rows x 16 ci] (fp16, smem) * B[Cout x 16 ci]^T (fp16, smem)
+//   * M = 128 consecutive time rows, N = Cout, K = (tap, input channel).
+//   * activations live in HBM as "F16B" planes [B][C/8][L + 2*pad][8] (already leaky-relu'd by the
+//     producer's epilogue).  One bulk-TMA copy (cp.async.bulk) per 8-channel run fetches the rows
+//     [m0 + omin, m0 + MT*128 + omax) of a work item into shared memory as [c8][row][16 B]: the
+//     canonical K-major SWIZZLE_NONE operand layout (8 rows x 16 B core matrices, SBO = 128 B,
+//     LBO = W*16 B).  Because consecutive rows are 16 B apart, the operand of tap t is the SAME
+//     buffer with the descriptor start address advanced by off_t rows - every tap and both
+//     convolution directions (polyphase transposed conv) reuse one window, zero padding comes from
+//     the zero pad rows of the plane.
+//   * weights: per (kernel index, 64-channel chunk) an fp16 image [ci/8][Cout][8] streamed through
+//     a ring of shared-memory stages by bulk copies, or kept resident when the layer's whole
+//     weight set fits (all C<=64 layers).
+//   * warp roles: warp 0 = copy producer, warp 1 = MMA issuer (one thread) + TMEM allocator,
+//     warps 2-5 = epilogue (TMEM -> registers -> bias/residual/MRF/leaky-relu -> fp32 F32B plane
+//     and/or fp16 F16B plane, fully coalesced 16 B per thread per 8 channels).
+//   * accumulators double-buffered in TMEM (2 x MT x Cout columns <= 512) so the epilogue of work
+//     item i overlaps the MMAs of item i+1; persistent CTAs, one per SM, static round-robin.
+// reference semantics: hifigan/models.py:35-42 (ResBlock1), :134-150 (Generator.forward)
 #include "gan_tc.h"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+
 #include "mb_common.h"
+
 namespace mb {
-int tc_plan_layers(std::vector<TcLayerDesc>&, size_t* b) { *b = 0; return fail(MB_ERR_STATE, "MB_PREC_F16TC not built"); }
-int tc_pack_weights(const TcLayer&, const TapConv&, const float*, char*, cudaStream_t) { return fail(MB_ERR_STATE, "MB_PREC_F16TC not built"); }
-size_t tc_workspace_bytes(const std::vector<TcBufReq>&, int, int, int, int) { return 0; }
-int tc_forward(const std::vector<TcOp>&, const std::vector<TcBufReq>&, const char*, const float*, const int32_t*, int, int, int, int, float*, void*, cudaStream_t, cudaEvent_t*) { return fail(MB_ERR_STATE, "MB_PREC_F16TC not built"); }
-int tc_debug_layer(const TcOp&, const char*, const float*, const float*, int, int, float*, void*, size_t, cudaStream_t) { return fail(MB_ERR_STATE, "MB_PREC_F16TC not built"); }
+
+namespace {
+
+constexpr int kTcThreads = 192;
+constexpr int kAStages = 2;
+constexpr int kAccStages = 2;
+constexpr int kMaxWStages = 16;
+constexpr uint32_t kSmemMax = 227 * 1024;
+constexpr size_t kPlaneSlack = 16 * 1024;
+
+struct TcParams {
+  int B, Lin, Lout, Cin, Cout;
+  int stride;
+  int ntaps[kMaxPhases];
+  int off[kMaxPhases][kMaxTaps];
+  int slab[kMaxPhases][kMaxTaps];
+  int omin, W, MT;
+  int c8_per_chunk, nk16, n_cchunks;
+  int slab_bytes, wstages, resident;
+  int tiles_per_utt, n_work;
+  uint32_t a_stage_bytes, a_off, w_off, bias_off, bar_off;
+  const __half* x16;
+  int x_Lp;
+  const __half* w16;
+  const float* bias;
+  const float* res32;
+  float* y32;
+  __half* y16;
+  int y_Lp;
+  float out_slope;
+  int mode;
+  float div;
+  const int32_t* lengths;
+  int len_mul_out;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MB_DONE_%=;\n"
+      "bra MB_WAIT_%=;\n"
+      "MB_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+struct WorkItem {
+  int b, m0, r;
+};
+__device__ __forceinline__ WorkItem decode_work(const TcParams& p, int work) {
+  WorkItem w;
+  w.r = work % p.stride;
+  const int t = work / p.stride;
+  w.m0 = (t % p.tiles_per_utt) * (p.MT * 128);
+  w.b = t / p.tiles_per_utt;
+  return w;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* a_base = smem + p.a_off;
+  uint8_t* w_base = smem + p.w_off;
+  float* bias_s = reinterpret_cast<float*>(smem + p.bias_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kAStages;
+  uint64_t* w_full = a_empty + kAStages;
+  uint64_t* w_empty = w_full + kMaxWStages;
+  uint64_t* acc_full = w_empty + kMaxWStages;
+  uint64_t* acc_empty = acc_full + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kAStages; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kMaxWStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.Cout; i += kTcThreads) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int Cin8 = p.Cin >> 3;
+
+  if (warp == 0) {
+    // ===================== copy producer =====================
+    if (lane == 0) {
+      int a_stage = 0, a_phase = 0, w_stage = 0, w_phase = 0;
+      uint32_t resident_loaded = 0;
+      for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
+        const WorkItem wi = decode_work(p, work);
+        for (int c = 0; c < p.n_cchunks; ++c) {
+          mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+          mbar_expect_tx(&a_full[a_stage], (uint32_t)(p.c8_per_chunk * p.W * 16));
+          const uint32_t dst0 = smem_u32(a_base + (size_t)a_stage * p.a_stage_bytes);
+          for (int j = 0; j < p.c8_per_chunk; ++j) {
+            const __half* src = p.x16 + (((size_t)wi.b * Cin8 + c * p.c8_per_chunk + j) * p.x_Lp +
+                                         (size_t)(kPadRows + wi.m0 + p.omin)) * 8;
+            bulk_g2s(dst0 + (uint32_t)(j * p.W * 16), src, (uint32_t)(p.W * 16), &a_full[a_stage]);
+          }
+          if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1; }
+          for (int t = 0; t < p.ntaps[wi.r]; ++t) {
+            const int sid = p.slab[wi.r][t] * p.n_cchunks + c;
+            const __half* src = p.w16 + (size_t)sid * (p.slab_bytes >> 1);
+            if (p.resident) {
+              if (!(resident_loaded & (1u << sid))) {
+                resident_loaded |= (1u << sid);
+                mbar_expect_tx(&w_full[sid], (uint32_t)p.slab_bytes);
+                bulk_g2s(smem_u32(w_base + (size_t)sid * p.slab_bytes), src, (uint32_t)p.slab_bytes, &w_full[sid]);
+              }
+            } else {
+              mbar_wait(&w_empty[w_stage], w_phase ^ 1);
+              mbar_expect_tx(&w_full[w_stage], (uint32_t)p.slab_bytes);
+              bulk_g2s(smem_u32(w_base + (size_t)w_stage * p.slab_bytes), src, (uint32_t)p.slab_bytes,
+                       &w_full[w_stage]);
+              if (++w_stage == p.wstages) { w_stage = 0; w_phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int a_stage = 0, a_phase = 0, w_stage = 0, w_phase = 0, acc_stage = 0, acc_phase = 0;
+      const uint32_t a_lbo = (uint32_t)p.W * 16, b_lbo = (uint32_t)p.Cout * 16;
+      for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
+        const WorkItem wi = decode_work(p, work);
+        mbar_wait(&acc_empty[acc_stage], acc_phase ^ 1);
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int c = 0; c < p.n_cchunks; ++c) {
+          mbar_wait(&a_full[a_stage], a_phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_base + (size_t)a_stage * p.a_stage_bytes);
+          for (int t = 0; t < p.ntaps[wi.r]; ++t) {
+            uint32_t w_addr;
+            if (p.resident) {
+              const int sid = p.slab[wi.r][t] * p.n_cchunks + c;
+              mbar_wait(&w_full[sid], 0);
+              w_addr = smem_u32(w_base + (size_t)sid * p.slab_bytes);
+            } else {
+              mbar_wait(&w_full[w_stage], w_phase);
+              w_addr = smem_u32(w_base + (size_t)w_stage * p.slab_bytes);
+            }
+            tc_fence_after();
+            const int row_shift = p.off[wi.r][t] - p.omin;
+            for (int s = 0; s < p.nk16; ++s) {
+              const uint64_t bdesc = make_desc(w_addr + (uint32_t)(2 * s) * b_lbo, b_lbo, 128);
+              for (int mt = 0; mt < p.MT; ++mt) {
+                const uint64_t adesc =
+                    make_desc(a_addr + (uint32_t)(2 * s) * a_lbo + (uint32_t)(mt * 128 + row_shift) * 16, a_lbo, 128);
+                tc_mma_f16(tmem_base + (uint32_t)((acc_stage * p.MT + mt) * p.Cout), adesc, bdesc, idesc, accumulate);
+              }
+              accumulate = 1;
+            }
+            if (!p.resident) {
+              tc_commit(&w_empty[w_stage]);
+              if (++w_stage == p.wstages) { w_stage = 0; w_phase ^= 1; }
+            }
+          }
+          tc_commit(&a_empty[a_stage]);
+          if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1; }
+        }
+        tc_commit(&acc_full[acc_stage]);
+        if (++acc_stage == kAccStages) { acc_stage = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    const int row_in_tile = quarter * 32 + lane;
+    int acc_stage = 0, acc_phase = 0;
+    const int C4 = p.Cout >> 2, C8 = p.Cout >> 3;
+    for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
+      const WorkItem wi = decode_work(p, work);
+      const int valid_out = p.lengths ? min(p.Lout, p.lengths[wi.b] * p.len_mul_out) : p.Lout;
+      mbar_wait(&acc_full[acc_stage], acc_phase);
+      tc_fence_after();
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int q = wi.m0 + mt * 128 + row_in_tile;
+        const int lo = q * p.stride + wi.r;
+        const bool inb = q < p.Lin;
+        const bool live = inb && lo < valid_out;
+        for (int col0 = 0; col0 < p.Cout; col0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc_stage * p.MT + mt) * p.Cout + col0),
+                    raw);
+          if (!inb) continue;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + bias_s[col0 + i];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const size_t i32 = (((size_t)wi.b * C4 + (col0 >> 2) + g) * p.Lout + lo);
+            if (p.res32) {
+              const float4 rv = reinterpret_cast<const float4*>(p.res32)[i32];
+              v[4 * g + 0] += rv.x; v[4 * g + 1] += rv.y; v[4 * g + 2] += rv.z; v[4 * g + 3] += rv.w;
+            }
+            if (p.mode != EPI_STORE) {
+              const float4 ov = reinterpret_cast<const float4*>(p.y32)[i32];
+              v[4 * g + 0] += ov.x; v[4 * g + 1] += ov.y; v[4 * g + 2] += ov.z; v[4 * g + 3] += ov.w;
+              if (p.mode == EPI_ADD_DIV) {
+                v[4 * g + 0] /= p.div; v[4 * g + 1] /= p.div; v[4 * g + 2] /= p.div; v[4 * g + 3] /= p.div;
+              }
+            }
+            if (!live) { v[4 * g + 0] = 0.f; v[4 * g + 1] = 0.f; v[4 * g + 2] = 0.f; v[4 * g + 3] = 0.f; }
+            if (p.y32)
+              reinterpret_cast<float4*>(p.y32)[i32] = make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          }
+          if (p.y16) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              __half2 h0 = __floats2half2_rn(lrelu(v[8 * g + 0], p.out_slope), lrelu(v[8 * g + 1], p.out_slope));
+              __half2 h1 = __floats2half2_rn(lrelu(v[8 * g + 2], p.out_slope), lrelu(v[8 * g + 3], p.out_slope));
+              __half2 h2 = __floats2half2_rn(lrelu(v[8 * g + 4], p.out_slope), lrelu(v[8 * g + 5], p.out_slope));
+              __half2 h3 = __floats2half2_rn(lrelu(v[8 * g + 6], p.out_slope), lrelu(v[8 * g + 7], p.out_slope));
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              const size_t i16 = (((size_t)wi.b * C8 + (col0 >> 3) + g) * p.y_Lp + kPadRows + lo);
+              reinterpret_cast<uint4*>(p.y16)[i16] = pk;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc_stage]);
+      if (++acc_stage == kAccStages) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// fp32 slabs [K][Cin][Cout] -> fp16 images [K][n_cchunks][kc/8][Cout][8]
+__global__ void pack_w16_kernel(const float* __restrict__ w32, __half* __restrict__ dst, int K, int Cin, int Cout,
+                                int kc) {
+  const size_t n = (size_t)K * Cin * Cout;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // destination-linear index -> (k, chunk, j, co, e)
+  const int e = (int)(i & 7);
+  size_t r = i >> 3;
+  const int co = (int)(r % Cout);
+  r /= Cout;
+  const int c8 = kc >> 3;
+  const int j = (int)(r % c8);
+  r /= c8;
+  const int nch = Cin / kc;
+  const int c = (int)(r % nch);
+  const int k = (int)(r / nch);
+  const int ci = c * kc + j * 8 + e;
+  dst[i] = __float2half_rn(w32[((size_t)k * Cin + ci) * Cout + co]);
+}
+
+int pick_kc(int Cin) {
+  if (Cin % 64 == 0) return 64;
+  if (Cin <= 64 && Cin % 16 == 0) return Cin;
+  return 0;
+}
+
+bool tc_capable(const TapConv& t) {
+  if (t.Cout < 32 || t.Cout > 256 || (t.Cout % 32) != 0) return false;
+  if (pick_kc(t.Cin) == 0) return false;
+  if (t.act_tanh) return false;
+  return true;
+}
+
+int pick_mt(int Cout) { return Cout >= 256 ? 1 : (Cout >= 64 ? 2 : 4); }
+
+struct SmemPlan {
+  uint32_t a_stage_bytes, a_off, w_off, bias_off, bar_off, total;
+  int wstages, resident, W, omin;
+};
+
+bool plan_smem(const TapConv& t, const TcLayer& tc, int total_slabs, SmemPlan* sp) {
+  int omin = 0x7fffffff, omax = -0x7fffffff;
+  for (int r = 0; r < t.stride; ++r)
+    for (int i = 0; i < t.ntaps[r]; ++i) {
+      omin = std::min(omin, t.off[r][i]);
+      omax = std::max(omax, t.off[r][i]);
+    }
+  if (-omin > kPadRows || omax > kPadRows) return false;
+  sp->omin = omin;
+  sp->W = tc.mt * 128 + (omax - omin);
+  sp->a_stage_bytes = (uint32_t)align_up((size_t)(tc.kc / 8) * sp->W * 16, 128);
+  sp->a_off = 0;
+  sp->w_off = sp->a_off + kAStages * sp->a_stage_bytes;
+  const uint32_t tail = (uint32_t)align_up((size_t)t.Cout * 4, 128) + 1024;
+  if (sp->w_off + tail + 2 * tc.slab_bytes > kSmemMax) return false;
+  int ws = (int)((kSmemMax - sp->w_off - tail) / tc.slab_bytes);
+  ws = std::min(ws, kMaxWStages);
+  sp->resident = (total_slabs <= ws) ? 1 : 0;
+  sp->wstages = sp->resident ? total_slabs : ws;
+  sp->bias_off = sp->w_off + (uint32_t)sp->wstages * (uint32_t)tc.slab_bytes;
+  sp->bar_off = sp->bias_off + (uint32_t)align_up((size_t)t.Cout * 4, 128);
+  sp->total = sp->bar_off + 1024;
+  return sp->total <= kSmemMax;
+}
+
+int kernel_count(const TapConv& t) {
+  int k = 0;
+  for (int r = 0; r < t.stride; ++r)
+    for (int i = 0; i < t.ntaps[r]; ++i) k = std::max(k, t.slab[r][i] + 1);
+  return k;
+}
+
+struct Plane {
+  TRef ref;  // current geometry
+};
+
+size_t f16_plane_bytes(size_t B, size_t T, size_t cr) {
+  // worst case pads: C = 512 channels -> 64 runs per utterance
+  return align_up(2 * B * T * cr + B * 64 * (2 * kPadRows) * 16 + kPlaneSlack, 256);
+}
+size_t f32_plane_bytes(size_t B, size_t T, size_t cr) { return align_up(4 * B * T * cr + 256, 256); }
+
+int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef& res32, const TRef& y32,
+              const TRef& y16, float out_slope, const int32_t* lengths, int B, int Lin, cudaStream_t st) {
+  const TapConv& t = op.taps;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.Lin = Lin;
+  p.Lout = Lin * t.stride;
+  p.Cin = t.Cin;
+  p.Cout = t.Cout;
+  p.stride = t.stride;
+  memcpy(p.ntaps, t.ntaps, sizeof(p.ntaps));
+  memcpy(p.off, t.off, sizeof(p.off));
+  memcpy(p.slab, t.slab, sizeof(p.slab));
+  SmemPlan sp;
+  const int total_slabs = kernel_count(t) * op.tc.n_cchunks;
+  if (!plan_smem(t, op.tc, total_slabs, &sp)) return fail(MB_ERR_INVALID, "tc_conv(%s): shared memory plan failed", op.name);
+  p.omin = sp.omin;
+  p.W = sp.W;
+  p.MT = op.tc.mt;
+  p.c8_per_chunk = op.tc.kc / 8;
+  p.nk16 = op.tc.kc / 16;
+  p.n_cchunks = op.tc.n_cchunks;
+  p.slab_bytes = (int)op.tc.slab_bytes;
+  p.wstages = sp.wstages;
+  p.resident = sp.resident;
+  p.tiles_per_utt = (Lin + p.MT * 128 - 1) / (p.MT * 128);
+  p.n_work = B * p.tiles_per_utt * p.stride;
+  p.a_stage_bytes = sp.a_stage_bytes;
+  p.a_off = sp.a_off;
+  p.w_off = sp.w_off;
+  p.bias_off = sp.bias_off;
+  p.bar_off = sp.bar_off;
+  p.x16 = reinterpret_cast<const __half*>(x16.p);
+  p.x_Lp = x16.L + 2 * kPadRows;
+  p.w16 = reinterpret_cast<const __half*>(tc_arena + op.tc.w16_off);
+  p.bias = op.b32;
+  p.res32 = reinterpret_cast<const float*>(res32.p);
+  p.y32 = reinterpret_cast<float*>(y32.p);
+  p.y16 = reinterpret_cast<__half*>(y16.p);
+  p.y_Lp = y16.L + 2 * kPadRows;
+  p.out_slope = out_slope;
+  p.mode = t.mode;
+  p.div = t.div;
+  p.lengths = lengths;
+  p.len_mul_out = t.len_mul_out;
+  if (p.mode != EPI_STORE && !p.y32) return fail(MB_ERR_INVALID, "tc_conv(%s): accumulate mode without fp32 plane", op.name);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MB_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(p.n_work, sms);
+  if (grid <= 0) return MB_OK;
+  tc_conv_kernel<<<grid, kTcThreads, sp.total, st>>>(p);
+  MB_LAUNCH_CHECK("tc_conv_kernel");
+  return MB_OK;
+}
+
+TRef make_ref(void* p, int layout, int C, int L) {
+  TRef t;
+  t.p = p;
+  t.layout = p ? layout : LAYOUT_NONE;
+  t.C = C;
+  t.L = L;
+  return t;
+}
+
+}  // namespace
+
+int tc_plan_layers(std::vector<TcLayerDesc>& layers, size_t* tc_arena_bytes) {
+  size_t off = 0;
+  for (TcLayerDesc& d : layers) {
+    if (!d.is_conv) continue;
+    TcLayer& tc = *d.tc;
+    const TapConv& t = *d.taps;
+    tc = TcLayer{};
+    if (d.force_f32 || !tc_capable(t)) continue;
+    tc.kc = pick_kc(t.Cin);
+    tc.n_cchunks = t.Cin / tc.kc;
+    tc.mt = pick_mt(t.Cout);
+    tc.slab_bytes = (size_t)tc.kc * t.Cout * 2;
+    SmemPlan sp;
+    if (!plan_smem(t, tc, d.k * tc.n_cchunks, &sp)) continue;  // falls back to the FP32 kernel
+    if (sp.resident && d.k * tc.n_cchunks > 32) continue;
+    tc.use_tc = 1;
+    tc.w16_off = off;
+    off += align_up((size_t)d.k * tc.n_cchunks * tc.slab_bytes, 256);
+  }
+  *tc_arena_bytes = off;
+  return MB_OK;
+}
+
+int tc_pack_weights(const TcLayer& tc, const TapConv& taps, const float* w32_slabs, char* tc_arena,
+                    cudaStream_t stream) {
+  if (!tc.use_tc) return MB_OK;
+  const int K = kernel_count(taps);
+  const size_t n = (size_t)K * taps.Cin * taps.Cout;
+  pack_w16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+      w32_slabs, reinterpret_cast<__half*>(tc_arena + tc.w16_off), K, taps.Cin, taps.Cout, tc.kc);
+  MB_LAUNCH_CHECK("pack_w16_kernel");
+  return MB_OK;
+}
+
+size_t tc_workspace_bytes(const std::vector<TcBufReq>& bufs, int B, int T, int num_mels, int hop) {
+  (void)num_mels;
+  (void)hop;
+  size_t total = 512;
+  for (const TcBufReq& b : bufs) total += f16_plane_bytes(B, T, b.cr) + f32_plane_bytes(B, T, b.cr);
+  return total;
+}
+
+int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, const char* tc_arena,
+               const float* mel, const int32_t* lengths, int B, int T, int num_mels, int hop, float* wav,
+               void* workspace, cudaStream_t st, cudaEvent_t* events) {
+  (void)hop;
+  constexpr int BUF_IN = 100, BUF_OUT = 101;
+  const int nb = (int)bufs.size();
+  // carve planes
+  std::vector<char*> p16(nb), p32(nb);
+  std::vector<TRef> cur16(nb), cur32(nb);  // geometry each plane currently holds
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  for (int i = 0; i < nb; ++i) {
+    p16[i] = ws;
+    ws += f16_plane_bytes(B, T, bufs[i].cr);
+    p32[i] = ws;
+    ws += f32_plane_bytes(B, T, bufs[i].cr);
+  }
+  const int n = (int)ops.size();
+  for (int i = 0; i < n; ++i) {
+    const TcOp& op = ops[i];
+    if (events) MB_CUDA_CHECK(cudaEventRecord(events[i], st));
+    const int Lin = T * op.rate_in, Lout = T * op.rate_out;
+    if (!op.is_conv) {
+      // dst32 += src32 ; refresh dst16 if a tensor-core consumer follows
+      if (op.dst < 0 || op.dst >= nb || op.src < 0 || op.src >= nb) return fail(MB_ERR_INVALID, "tc_forward: bad add op");
+      bool need16 = false;
+      float slope16 = 1.f;
+      for (int j = i + 1; j < n; ++j) {
+        if (ops[j].is_conv && ops[j].src == op.dst && ops[j].tc.use_tc) { need16 = true; slope16 = ops[j].taps.in_slope; }
+        if (ops[j].is_conv && ops[j].dst == op.dst) break;
+      }
+      TRef d32 = make_ref(p32[op.dst], LAYOUT_F32B, op.cout, Lout);
+      TRef s32 = make_ref(p32[op.src], LAYOUT_F32B, op.cout, Lout);
+      TRef d16 = need16 ? make_ref(p16[op.dst], LAYOUT_F16B, op.cout, Lout) : TRef{};
+      cudaError_t e = launch_add_inplace_f32(d32, s32, d16, slope16, B, st);
+      if (e != cudaSuccess) return fail(MB_ERR_CUDA, "add kernel: %s", cudaGetErrorString(e));
+      count_launch();
+      continue;
+    }
+    // ---- which planes must this op produce? (scan the consumers of dst until it is overwritten)
+    bool need16 = false, need32 = false;
+    float slope16 = 1.f;
+    bool have_slope = false;
+    auto scan = [&](int buf, bool& n16, bool& n32, float& s16, bool& hs) -> int {
+      for (int j = i + 1; j < n; ++j) {
+        const TcOp& c = ops[j];
+        if (c.is_conv) {
+          if (c.src == buf) {
+            if (c.tc.use_tc) {
+              if (hs && s16 != c.taps.in_slope) return fail(MB_ERR_INVALID, "tc_forward: consumers of one buffer disagree on slope");
+              n16 = true;
+              s16 = c.taps.in_slope;
+              hs = true;
+            } else {
+              n32 = true;
+            }
+          }
+          if (c.res == buf) n32 = true;
+          if (c.dst2 == buf) n32 = true;
+          if (c.dst == buf) {
+            if (c.taps.mode != EPI_STORE) n32 = true;
+            break;
+          }
+        } else {
+          if (c.src == buf || c.dst == buf) n32 = true;
+        }
+      }
+      return MB_OK;
+    };
+    TRef y32, y16, y2_32, y2_16;
+    float y2_slope = 1.f;
+    if (op.dst == BUF_OUT) {
+      y32 = make_ref(wav, LAYOUT_NCL, op.cout, Lout);
+    } else {
+      if (op.dst < 0 || op.dst >= nb) return fail(MB_ERR_INVALID, "tc_forward: bad dst");
+      int rc = scan(op.dst, need16, need32, slope16, have_slope);
+      if (rc != MB_OK) return rc;
+      if (op.taps.mode != EPI_STORE) need32 = true;
+      if (need32) y32 = make_ref(p32[op.dst], LAYOUT_F32B, op.cout, Lout);
+      if (need16) {
+        y16 = make_ref(p16[op.dst], LAYOUT_F16B, op.cout, Lout);
+        if (cur16[op.dst].C != op.cout || cur16[op.dst].L != Lout) {
+          cudaError_t e = launch_zero_pads_f16(y16, B, st);
+          if (e != cudaSuccess) return fail(MB_ERR_CUDA, "zero_pads: %s", cudaGetErrorString(e));
+          count_launch();
+          cur16[op.dst] = y16;
+        }
+      }
+    }
+    if (op.dst2 >= 0) {
+      if (op.dst2 >= nb) return fail(MB_ERR_INVALID, "tc_forward: bad dst2");
+      bool n16 = false, n32 = true, hs = false;
+      int rc = scan(op.dst2, n16, n32, y2_slope, hs);
+      if (rc != MB_OK) return rc;
+      y2_32 = make_ref(p32[op.dst2], LAYOUT_F32B, op.cout, Lout);
+      if (n16) y2_16 = make_ref(p16[op.dst2], LAYOUT_F16B, op.cout, Lout);
+    }
+    TRef res32 = (op.res >= 0) ? make_ref(p32[op.res], LAYOUT_F32B, op.cout, Lout) : TRef{};
+    if (op.tc.use_tc) {
+      if (op.src < 0 || op.src >= nb) return fail(MB_ERR_INVALID, "tc_forward: tensor-core layer %s reads an external buffer", op.name);
+      TRef x16 = make_ref(p16[op.src], LAYOUT_F16B, op.cin, Lin);
+      int rc = launch_tc(op, tc_arena, x16, res32, y32, y16, slope16, lengths, B, Lin, st);
+      if (rc != MB_OK) return rc;
+    } else {
+      TapConv p = op.taps;
+      p.B = B;
+      p.Lin = Lin;
+      p.Lout = Lout;
+      p.lengths = lengths;
+      TapConvIO io;
+      if (op.src == BUF_IN) io.x = make_ref(const_cast<float*>(mel), LAYOUT_NCL, num_mels, Lin);
+      else if (op.src >= 0 && op.src < nb) io.x = make_ref(p32[op.src], LAYOUT_F32B, op.cin, Lin);
+      else return fail(MB_ERR_INVALID, "tc_forward: bad src");
+      io.res = res32;
+      io.y32 = y32;
+      io.y16 = y16;
+      io.out16_slope = slope16;
+      io.y2_32 = y2_32;
+      io.y2_16 = y2_16;
+      io.y2_16_slope = y2_slope;
+      cudaError_t e = (op.cout == 1 && p.stride == 1) ? launch_tapconv_cout1_f32(p, io, op.w32, op.b32, st)
+                                                      : launch_tapconv_f32(p, io, op.w32, op.b32, st);
+      if (e != cudaSuccess) return fail(MB_ERR_CUDA, "tapconv_f32 (%s): %s", op.name, cudaGetErrorString(e));
+      count_launch();
+    }
+  }
+  if (events) MB_CUDA_CHECK(cudaEventRecord(events[n], st));
+  return MB_OK;
+}
+
+int tc_debug_layer(const TcOp& op, const char* tc_arena, const float* x, const float* residual, int B, int Lin,
+                   float* y, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const TapConv& t = op.taps;
+  const int Lout = Lin * t.stride;
+  TRef xn = make_ref(const_cast<float*>(x), LAYOUT_NCL, t.Cin, Lin);
+  TRef yn = make_ref(y, LAYOUT_NCL, t.Cout, Lout);
+  if (!op.tc.use_tc) {
+    TapConv p = t;
+    p.B = B;
+    p.Lin = Lin;
+    p.Lout = Lout;
+    p.lengths = nullptr;
+    TapConvIO io;
+    io.x = xn;
+    io.res = make_ref(const_cast<float*>(residual), LAYOUT_NCL, t.Cout, Lout);
+    io.y32 = yn;
+    cudaError_t e = (t.Cout == 1 && p.stride == 1) ? launch_tapconv_cout1_f32(p, io, op.w32, op.b32, st)
+                                                   : launch_tapconv_f32(p, io, op.w32, op.b32, st);
+    if (e != cudaSuccess) return fail(MB_ERR_CUDA, "tapconv_f32: %s", cudaGetErrorString(e));
+    count_launch();
+    return MB_OK;
+  }
+  // planes: x16 (activated), res32, y32
+  const size_t b_x16 = align_up((size_t)B * (t.Cin / 8) * (Lin + 2 * kPadRows) * 16 + kPlaneSlack, 256);
+  const size_t b_r32 = align_up((size_t)B * t.Cout * Lout * 4, 256);
+  if (workspace_bytes < b_x16 + 2 * b_r32 + 512) return fail(MB_ERR_WORKSPACE, "tc_debug_layer: workspace too small");
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  TRef x16 = make_ref(ws, LAYOUT_F16B, t.Cin, Lin);
+  TRef r32 = residual ? make_ref(ws + b_x16, LAYOUT_F32B, t.Cout, Lout) : TRef{};
+  TRef y32 = make_ref(ws + b_x16 + b_r32, LAYOUT_F32B, t.Cout, Lout);
+  MB_CUDA_CHECK(cudaMemsetAsync(ws, 0, b_x16, st));
+  cudaError_t e = launch_convert_layout(xn, x16, B, t.in_slope, st);
+  if (e != cudaSuccess) return fail(MB_ERR_CUDA, "convert: %s", cudaGetErrorString(e));
+  if (residual) {
+    e = launch_convert_layout(make_ref(const_cast<float*>(residual), LAYOUT_NCL, t.Cout, Lout), r32, B, 1.f, st);
+    if (e != cudaSuccess) return fail(MB_ERR_CUDA, "convert: %s", cudaGetErrorString(e));
+  }
+  int rc = launch_tc(op, tc_arena, x16, r32, y32, TRef{}, 1.f, nullptr, B, Lin, st);
+  if (rc != MB_OK) return rc;
+  e = launch_convert_layout(y32, yn, B, 1.f, st);
+  if (e != cudaSuccess) return fail(MB_ERR_CUDA, "convert: %s", cudaGetErrorString(e));
+  count_launch(3);
+  return MB_OK;
+}
+
+}  // namespace mb

@@ -22,6 +22,7 @@ struct TcLayer {
 
 struct TcLayerDesc {
   bool is_conv;
+  bool force_f32;  // layer shapes the tensor-core kernel does not cover (second destination, nearest-upsample)
   const TapConv* taps;
   int k;
   TcLayer* tc;

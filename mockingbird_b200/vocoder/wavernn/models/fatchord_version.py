@@ -1,0 +1,275 @@
+"""fatchord ``WaveRNN`` on the B200 path (reference: models/vocoder/wavernn/models/fatchord_version.py:88-257).
+
+Same constructor and ``generate(mels, batched, target, overlap, mu_law, progress_callback)`` surface.
+The conditioning network and the whole sample loop run in the CUDA library (mb_wavernn_*); the host
+keeps only what the reference also does on the host in float64 numpy: cross-fade/unfold, mu-law
+decoding, de-emphasis and the fade-out (fatchord_version.py:236-253).
+
+Sampling noise.  ``Categorical(p).sample()`` is ``argmax(p / q)`` with ``q = empty_like(p).exponential_(1)``
+drawn from the global torch generator.  ``rng="torch"`` (default) replays exactly
+that stream on the host - two ``nn.GRUCell`` constructions, then one ``exponential_([B,512])`` per
+step - and feeds it to the kernel, so under ``torch.manual_seed(s)`` the integer samples equal the
+reference's CPU run.  ``rng="device"`` uses the library's counter-based generator (no host noise,
+the throughput mode).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .... import _lib
+from .. import hparams as hp
+
+CHUNK = 100  # steps per kernel call == the reference's progress cadence (fatchord_version.py:232-234)
+
+
+def fold_geometry(total_len: int, target: int, overlap: int):
+    """fold_with_overlap (:314-336): number of folds and their start offsets (the zero padding past
+    the end is produced on the device)."""
+    num_folds = (total_len - overlap) // (target + overlap)
+    extended_len = num_folds * (overlap + target) + overlap
+    remaining = total_len - extended_len
+    if remaining != 0:
+        num_folds += 1
+    return num_folds, np.arange(num_folds, dtype=np.int32) * (target + overlap)
+
+
+def xfade_and_unfold(y: np.ndarray, target: int, overlap: int) -> np.ndarray:
+    """Equal-power cross-fade and overlap-add of the folds (:340-402), float64 like the reference."""
+    num_folds, length = y.shape
+    target = length - 2 * overlap
+    total_len = num_folds * (target + overlap) + overlap
+    silence_len = overlap // 2
+    fade_len = overlap - silence_len
+    t = np.linspace(-1, 1, fade_len, dtype=np.float64)
+    fade_in = np.concatenate([np.zeros(silence_len, dtype=np.float64), np.sqrt(0.5 * (1 + t))])
+    fade_out = np.concatenate([np.sqrt(0.5 * (1 - t)), np.zeros(silence_len, dtype=np.float64)])
+    y[:, :overlap] *= fade_in
+    y[:, -overlap:] *= fade_out
+    unfolded = np.zeros(total_len, dtype=np.float64)
+    for i in range(num_folds):
+        start = i * (target + overlap)
+        unfolded[start:start + target + 2 * overlap] += y[i]
+    return unfolded
+
+
+def decode_mu_law(y: np.ndarray, mu: int) -> np.ndarray:
+    """wavernn/audio.py:102-107 with from_labels=False"""
+    mu = mu - 1
+    return np.sign(y) / mu * ((1 + mu) ** np.abs(y) - 1)
+
+
+def de_emphasis(x: np.ndarray) -> np.ndarray:
+    """wavernn/audio.py:92-93"""
+    from scipy.signal import lfilter
+
+    return lfilter([1], [1, -hp.preemphasis], x)
+
+
+class WaveRNN:
+    def __init__(self, rnn_dims, fc_dims, bits, pad, upsample_factors, feat_dims, compute_dims, res_out_dims,
+                 res_blocks, hop_length, sample_rate, mode='RAW'):
+        if mode != 'RAW':
+            raise NotImplementedError("only voc_mode='RAW' (the reference default, wavernn/hparams.py:24) is built; "
+                                      "the MOL sampler is out of scope")
+        self.mode = mode
+        self.pad = pad
+        self.n_classes = 2 ** bits
+        self.rnn_dims = rnn_dims
+        self.aux_dims = res_out_dims // 4
+        self.hop_length = hop_length
+        self.sample_rate = sample_rate
+        cfg = _lib.WaveRNNConfig()
+        cfg.rnn_dims, cfg.fc_dims, cfg.bits, cfg.pad = rnn_dims, fc_dims, bits, pad
+        cfg.num_upsample = len(upsample_factors)
+        for i, s in enumerate(upsample_factors):
+            cfg.upsample_factors[i] = int(s)
+        cfg.feat_dims, cfg.compute_dims, cfg.res_out_dims, cfg.res_blocks = feat_dims, compute_dims, res_out_dims, res_blocks
+        self._total_scale = int(np.prod(upsample_factors))
+        self._handle = C.c_void_p()
+        _lib.check(_lib.lib().mb_wavernn_create(C.byref(cfg), C.byref(self._handle)))
+        self._state: Optional[Dict[str, torch.Tensor]] = None
+        self._arena = None
+        self._ws = None
+        self._device = None
+        self._ready = False
+        self.training = True
+        self.rng = "torch"
+        self.seed = 0
+        self.step = torch.zeros(1).long()
+
+    # -- nn.Module-like surface ------------------------------------------------------------------
+    def load_state_dict(self, sd, strict: bool = True):
+        self._state = {k: v.detach() for k, v in sd.items()}
+        if "step" in self._state:
+            self.step = self._state["step"].clone()
+        self._ready = False
+        return self
+
+    def state_dict(self):
+        return dict(self._state or {})
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        self.training = mode
+        return self
+
+    def cuda(self):
+        self._device = _lib.require_cuda()
+        self._ready = False
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.MbError("mockingbird_b200 WaveRNN runs on CUDA only (no CPU fallback)")
+        self._device = device
+        self._ready = False
+        return self
+
+    def get_step(self):
+        return self.step.data.item()
+
+    def _upload(self):
+        if self._state is None:
+            raise _lib.MbError("WaveRNN has no weights: call load_state_dict first")
+        dev = self._device or _lib.require_cuda()
+        self._device = dev
+        L = _lib.lib()
+        nbytes = int(L.mb_wavernn_arena_bytes(self._handle))
+        with torch.cuda.device(dev):
+            self._arena = torch.zeros(nbytes + 256, dtype=torch.uint8, device=dev)
+            base = (self._arena.data_ptr() + 255) // 256 * 256
+            _lib.check(L.mb_wavernn_set_arena(self._handle, C.c_void_p(base), nbytes))
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            keep = []
+            for name, t in self._state.items():
+                if name == "step" or name.endswith("num_batches_tracked"):
+                    continue
+                d = t.to(device=dev, dtype=torch.float32).contiguous()
+                keep.append(d)
+                dims = (C.c_int64 * max(1, d.dim()))(*d.shape)
+                _lib.check(L.mb_wavernn_set_weight(self._handle, name.encode(), C.c_void_p(d.data_ptr()), dims, d.dim(),
+                                                   C.c_void_p(stream)))
+            _lib.check(L.mb_wavernn_finalize(self._handle, C.c_void_p(stream)))
+            torch.cuda.current_stream(dev).synchronize()
+        self._ready = True
+
+    def packed_arena(self) -> torch.Tensor:
+        if not self._ready:
+            self._upload()
+        return self._arena
+
+    # -- generate --------------------------------------------------------------------------------
+    def generate_indices(self, mels: torch.Tensor, batched: bool, target: int, overlap: int, progress_callback=None,
+                         noise: Optional[torch.Tensor] = None) -> np.ndarray:
+        """the device part of generate(): class indices int16 [folds, steps]"""
+        if not self._ready:
+            self._upload()
+        L = _lib.lib()
+        dev = self._device
+        mel = mels[0].to(device=dev, dtype=torch.float32).contiguous()  # [80, T]
+        T = int(mel.shape[1])
+        total = T * self._total_scale
+        if batched:
+            B, starts = fold_geometry(total, target, overlap)
+            steps = target + 2 * overlap
+        else:
+            B, starts, steps = 1, np.zeros(1, dtype=np.int32), total
+        if B <= 0 or steps <= 0:
+            return np.zeros((max(B, 0), max(steps, 0)), np.int16)
+        start_t = time.time()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            need = int(L.mb_wavernn_workspace_bytes(self._handle, T, B, steps)) + 256
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            ws = self._ws
+            _lib.check(L.mb_wavernn_condition(self._handle, C.c_void_p(mel.data_ptr()), T, C.c_void_p(ws.data_ptr()),
+                                              ws.numel(), C.c_void_p(stream.cuda_stream)))
+            out = torch.empty(B, steps, dtype=torch.int16, device=dev)
+            starts_c = (C.c_int32 * B)(*[int(s) for s in starts])
+            use_host_noise = noise is not None or self.rng == "torch"
+            if use_host_noise and noise is None:
+                # the reference constructs two GRUCells before the loop: they consume the global RNG
+                # (fatchord_version.py:160-161, 265-271)
+                nn.GRUCell(self.rnn_dims, self.rnn_dims)
+                nn.GRUCell(self.rnn_dims + self.aux_dims, self.rnn_dims)
+            bufs = [torch.empty(CHUNK, B, self.n_classes, dtype=torch.float32).pin_memory() for _ in range(2)] \
+                if use_host_noise and noise is None else None
+            dbufs = [torch.empty(CHUNK, B, self.n_classes, dtype=torch.float32, device=dev) for _ in range(2)] \
+                if use_host_noise else None
+            evs = [torch.cuda.Event(), torch.cuda.Event()]
+            step0 = 0
+            ci = 0
+            while step0 < steps:
+                n = min(CHUNK, steps - step0)
+                nptr = None
+                if use_host_noise:
+                    slot = ci & 1
+                    if noise is not None:
+                        dbufs[slot][:n].copy_(noise[step0:step0 + n].to(torch.float32), non_blocking=True)
+                    else:
+                        if ci >= 2:
+                            evs[slot].synchronize()  # the H2D that last used this pinned buffer is done
+                        hb = bufs[slot]
+                        for j in range(n):
+                            hb[j].exponential_(1)  # same draw order as Categorical.sample(), one per step
+                        dbufs[slot][:n].copy_(hb[:n], non_blocking=True)
+                        evs[slot].record(stream)
+                    nptr = C.c_void_p(dbufs[slot].data_ptr())
+                _lib.check(L.mb_wavernn_generate(self._handle, starts_c, B, steps, step0, n, nptr, C.c_uint64(self.seed),
+                                                 C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                 C.c_void_p(stream.cuda_stream)))
+                if progress_callback is not None:
+                    gen_rate = (step0 + 1) / max(time.time() - start_t, 1e-9) * B / 1000
+                    progress_callback(step0, steps, B, gen_rate)
+                step0 += n
+                ci += 1
+            idx = out.cpu().numpy()
+        return idx
+
+    def generate(self, mels, batched, target, overlap, mu_law, progress_callback=None):
+        mu_law = mu_law if self.mode == 'RAW' else False
+        progress_callback = progress_callback or self.gen_display
+        self.eval()
+        wave_len = (mels.size(-1) - 1) * self.hop_length
+        idx = self.generate_indices(mels, batched, target, overlap, progress_callback)
+        # sample = 2 * idx.float() / (n_classes - 1.) - 1.  (float32, :226) then float64 (:238)
+        output = (2 * idx.astype(np.float32) / np.float32(self.n_classes - 1.) - np.float32(1.)).astype(np.float64)
+        if batched:
+            output = xfade_and_unfold(output, target, overlap)
+        else:
+            output = output[0]
+        if mu_law:
+            output = decode_mu_law(output, self.n_classes)
+        if hp.apply_preemphasis:
+            output = de_emphasis(output)
+        fade_out = np.linspace(1, 0, 20 * self.hop_length)
+        output = output[:wave_len]
+        output[-20 * self.hop_length:] *= fade_out
+        self.train()  # side effect kept (:255)
+        return output
+
+    def gen_display(self, i, seq_len, b_size, gen_rate):
+        pbar_len = 16
+        done = int(pbar_len * (i + 1) / max(seq_len, 1))
+        bar = '█' * done + '░' * (pbar_len - done)
+        print(f'\r| {bar} {i * b_size}/{seq_len * b_size} | Batch Size: {b_size} | Gen Rate: {gen_rate:.1f}kHz | ',
+              end='', flush=True)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                _lib.lib().mb_wavernn_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass

@@ -156,3 +156,82 @@ def rescale_variance_preserving(sd: Dict[str, torch.Tensor], gain: float, seed: 
         else:
             out[k] = torch.randn(v.shape, generator=g) * 0.05
     return out
+
+
+# ---- WaveRNN (fatchord_version.py:88-116; hparams models/vocoder/wavernn/hparams.py) ----------
+WAVERNN_HP = dict(rnn_dims=512, fc_dims=512, bits=9, pad=2, upsample_factors=(5, 5, 8), feat_dims=80,
+                  compute_dims=128, res_out_dims=128, res_blocks=10, hop_length=256, sample_rate=16000,
+                  mu_law=True, apply_preemphasis=True, preemphasis=0.97, mel_max_abs_value=4.0)
+
+
+def wavernn_state_dict(seed: int = 0, randomize_bn: bool = True) -> Dict[str, torch.Tensor]:
+    """``torch.manual_seed(seed); WaveRNN(...)`` state_dict, rebuilt from stock torch layers in the
+    reference's construction order (UpsampleNetwork -> I -> rnn1 -> rnn2 -> fc1..3).  With
+    ``randomize_bn`` the BatchNorm affine parameters and running statistics (which a fresh module
+    leaves at identity) are overwritten from a side generator so that parity cases exercise them;
+    oracle/make_golden.py applies the same overwrite to the live reference module."""
+    hp = WAVERNN_HP
+    torch.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    cd, fd, ro = hp["compute_dims"], hp["feat_dims"], hp["res_out_dims"]
+    k = hp["pad"] * 2 + 1
+    sd["upsample.resnet.conv_in.weight"] = torch.nn.Conv1d(fd, cd, k, bias=False).weight.detach()
+    bns = ["upsample.resnet.batch_norm"]
+    for i in range(hp["res_blocks"]):
+        sd[f"upsample.resnet.layers.{i}.conv1.weight"] = torch.nn.Conv1d(cd, cd, 1, bias=False).weight.detach()
+        sd[f"upsample.resnet.layers.{i}.conv2.weight"] = torch.nn.Conv1d(cd, cd, 1, bias=False).weight.detach()
+        bns += [f"upsample.resnet.layers.{i}.batch_norm1", f"upsample.resnet.layers.{i}.batch_norm2"]
+    co = torch.nn.Conv1d(cd, ro, 1)
+    sd["upsample.resnet.conv_out.weight"], sd["upsample.resnet.conv_out.bias"] = co.weight.detach(), co.bias.detach()
+    for j, s in enumerate(hp["upsample_factors"]):
+        c2 = torch.nn.Conv2d(1, 1, (1, 2 * s + 1), padding=(0, s), bias=False)  # consumes RNG, then filled
+        sd[f"upsample.up_layers.{2 * j + 1}.weight"] = torch.full_like(c2.weight.detach(), 1.0 / (2 * s + 1))
+    aux = ro // 4
+    lin = torch.nn.Linear(fd + aux + 1, hp["rnn_dims"])
+    sd["I.weight"], sd["I.bias"] = lin.weight.detach(), lin.bias.detach()
+    for name, insz in (("rnn1", hp["rnn_dims"]), ("rnn2", hp["rnn_dims"] + aux)):
+        g = torch.nn.GRU(insz, hp["rnn_dims"], batch_first=True)
+        for p in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"):
+            sd[f"{name}.{p}"] = getattr(g, p).detach()
+    for name, insz, outsz in (("fc1", hp["rnn_dims"] + aux, hp["fc_dims"]), ("fc2", hp["fc_dims"] + aux, hp["fc_dims"]),
+                              ("fc3", hp["fc_dims"], 2 ** hp["bits"])):
+        lin = torch.nn.Linear(insz, outsz)
+        sd[f"{name}.weight"], sd[f"{name}.bias"] = lin.weight.detach(), lin.bias.detach()
+    sd["step"] = torch.zeros(1).long()
+    for b in bns:
+        sd[b + ".weight"], sd[b + ".bias"] = torch.ones(cd), torch.zeros(cd)
+        sd[b + ".running_mean"], sd[b + ".running_var"] = torch.zeros(cd), torch.ones(cd)
+        sd[b + ".num_batches_tracked"] = torch.tensor(0)
+    if randomize_bn:
+        randomize_batchnorm_(sd, seed)
+    return sd
+
+
+def randomize_batchnorm_(sd: Dict[str, torch.Tensor], seed: int) -> None:
+    g = torch.Generator().manual_seed(10_000 + seed)
+    for k in sorted(sd):
+        if k.endswith(".running_var"):
+            sd[k] = torch.rand(sd[k].shape, generator=g) * 1.5 + 0.25
+        elif k.endswith(".running_mean"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.3
+        elif "batch_norm" in k and k.endswith(".weight"):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+        elif "batch_norm" in k and k.endswith(".bias"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.2
+    # learned FIR taps are Parameters too (SURVEY.md appendix A.3): perturb them off the box filter
+    for k in sorted(sd):
+        if k.startswith("upsample.up_layers."):
+            sd[k] = sd[k] * (1.0 + 0.3 * torch.randn(sd[k].shape, generator=g))
+
+
+def wavernn_noise(seed: int, B: int, steps: int) -> torch.Tensor:
+    """The Exp(1) stream WaveRNN.generate consumes from the global torch generator under
+    ``torch.manual_seed(seed)``: two nn.GRUCell constructions
+    (fatchord_version.py:160-161, 265-271) and then one exponential_([B,512]) per step (:223-226)."""
+    torch.manual_seed(seed)
+    torch.nn.GRUCell(512, 512)
+    torch.nn.GRUCell(544, 512)
+    out = torch.empty(steps, B, 512)
+    for i in range(steps):
+        out[i] = torch.empty(B, 512).exponential_(1)
+    return out
