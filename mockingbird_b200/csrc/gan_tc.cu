@@ -495,7 +495,8 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(p.n_work, sms);
   if (grid <= 0) return MB_OK;
-  tc_conv_kernel<<<grid, kTcThreads, sp.total, st>>>(p);
+  // always claim the whole shared memory: one CTA per SM, so the 512-column TMEM allocation never contends
+  tc_conv_kernel<<<grid, kTcThreads, kSmemMax, st>>>(p);
   MB_LAUNCH_CHECK("tc_conv_kernel");
   return MB_OK;
 }
