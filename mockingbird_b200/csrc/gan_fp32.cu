@@ -203,16 +203,21 @@ __global__ void add_inplace_kernel(TRef dst32, TRef src32, TRef dst16, float slo
 }
 
 __global__ void zero_pads_kernel(TRef plane, int B) {
-  // one thread per (run, pad row, 16-byte lane)
-  const int Lp = plane.L + 2 * kPadRows;
-  const size_t runs = (size_t)B * (plane.C >> 3);
-  const size_t n = runs * (2 * kPadRows);
+  // one thread per (run, pad row, 16-byte chunk)
+  const int cw = f16_cw(plane.C);
+  const int Lp = f16_lp(plane.L);
+  const int npad = Lp - plane.L;            // kPadRows in front, the rest behind
+  const int cpr = cw >> 3;                  // 16-byte chunks per row
+  const size_t runs = (size_t)B * (plane.C / cw);
+  const size_t n = runs * npad * cpr;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const size_t run = i / (2 * kPadRows);
-  const int pr = (int)(i % (2 * kPadRows));
-  const int row = pr < kPadRows ? pr : plane.L + pr;  // [0,PAD) and [PAD+L, PAD+L+PAD)
-  uint4* ptr = reinterpret_cast<uint4*>(plane.p) + run * Lp + row;
+  const int ch = (int)(i % cpr);
+  const size_t j = i / cpr;
+  const size_t run = j / npad;
+  const int pr = (int)(j % npad);
+  const int row = pr < kPadRows ? pr : plane.L + pr;
+  uint4* ptr = reinterpret_cast<uint4*>(plane.p) + (run * Lp + row) * cpr + ch;
   *ptr = make_uint4(0, 0, 0, 0);
 }
 
@@ -268,7 +273,7 @@ cudaError_t launch_add_inplace_f32(const TRef& dst32, const TRef& src32, const T
 }
 
 cudaError_t launch_zero_pads_f16(const TRef& plane, int B, cudaStream_t stream) {
-  const size_t n = (size_t)B * (plane.C >> 3) * (2 * kPadRows);
+  const size_t n = (size_t)B * (plane.C >> 3) * (f16_lp(plane.L) - plane.L);
   if (n == 0) return cudaSuccess;
   zero_pads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(plane, B);
   return cudaGetLastError();

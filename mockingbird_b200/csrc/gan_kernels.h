@@ -47,9 +47,12 @@ struct TapConv {
 // Activation tensor layouts ------------------------------------------------------------------
 //   LAYOUT_NCL : fp32 [B][C][L]                      (the reference's layout; API boundary)
 //   LAYOUT_F32B: fp32 [B][C/4][L][4]                 (residual streams of the tensor-core path)
-//   LAYOUT_F16B: fp16 [B][C/8][L + 2*kPadRows][8]    (MMA operand planes: already activated,
-//                 rows [kPadRows, kPadRows+L) hold data, pad rows are zero so that a conv window
-//                 can be fetched with one bulk copy per 8-channel run)
+//   LAYOUT_F16B: fp16 [B][C/CW][Lp][CW], CW = min(C,64), Lp = ceil8(L + 2*kPadRows)
+//                 (MMA operand planes: already activated; rows [kPadRows, kPadRows+L) hold data, pad
+//                 rows are zero.  Each row of a run is CW*2 = 128 (or 64) bytes and its 16-byte chunks
+//                 are stored XOR-swizzled by the row index exactly like the UMMA SWIZZLE_128B
+//                 (SWIZZLE_64B) shared-memory layouts, so a conv window is ONE contiguous bulk copy
+//                 per 64-channel chunk that lands in shared memory already in tensor-core layout.)
 enum Layout : int { LAYOUT_NONE = 0, LAYOUT_NCL = 1, LAYOUT_F32B = 2, LAYOUT_F16B = 3 };
 
 struct TRef {
@@ -58,10 +61,18 @@ struct TRef {
   int C = 0, L = 0;
 };
 
+__host__ __device__ inline int f16_cw(int C) { return C >= 64 ? 64 : C; }
+__host__ __device__ inline int f16_lp(int L) { return (L + 2 * kPadRows + 7) & ~7; }
+// swizzle phase of padded row r for a row of cw channels (128-byte rows: r & 7, 64-byte rows: (r>>1) & 3)
+__host__ __device__ inline int f16_swz(int cw, int r) { return cw == 64 ? (r & 7) : (cw == 32 ? ((r >> 1) & 3) : 0); }
+
 __host__ __device__ inline size_t tref_index(const TRef& t, int b, int c, int l) {
   if (t.layout == LAYOUT_NCL) return ((size_t)b * t.C + c) * t.L + l;
   if (t.layout == LAYOUT_F32B) return (((size_t)b * (t.C >> 2) + (c >> 2)) * t.L + l) * 4 + (c & 3);
-  return (((size_t)b * (t.C >> 3) + (c >> 3)) * (t.L + 2 * kPadRows) + kPadRows + l) * 8 + (c & 7);
+  const int cw = f16_cw(t.C);
+  const int r = kPadRows + l;
+  const int chunk = c / cw, cc = c - chunk * cw;
+  return (((size_t)b * (t.C / cw) + chunk) * f16_lp(t.L) + r) * cw + (size_t)((((cc >> 3) ^ f16_swz(cw, r)) << 3) + (cc & 7));
 }
 
 // ---- FP32 FFMA kernels ------------------------------------------------------------------------

@@ -3,19 +3,23 @@
 // tc_conv_kernel: the tap conv (gan_kernels.h) as an implicit GEMM on tcgen05 tensor cores.
 //   D[128 rows x Cout] (fp32, TMEM) += A[128 rows x 16 ci] (fp16, smem) * B[Cout x 16 ci]^T (fp16, smem)
 //   * M = 128 consecutive time rows, N = Cout, K = (tap, input channel).
-//   * activations live in HBM as "F16B" planes [B][C/8][L + 2*pad][8] (already leaky-relu'd by the
-//     producer's epilogue).  One bulk-TMA copy (cp.async.bulk) per 8-channel run fetches the rows
-//     [m0 + omin, m0 + MT*128 + omax) of a work item into shared memory as [c8][row][16 B]: the
-//     canonical K-major SWIZZLE_NONE operand layout (8 rows x 16 B core matrices, SBO = 128 B,
-//     LBO = W*16 B).  Because consecutive rows are 16 B apart, the operand of tap t is the SAME
-//     buffer with the descriptor start address advanced by off_t rows - every tap and both
-//     convolution directions (polyphase transposed conv) reuse one window, zero padding comes from
-//     the zero pad rows of the plane.
-//   * weights: per (kernel index, 64-channel chunk) an fp16 image [ci/8][Cout][8] streamed through
-//     a ring of shared-memory stages by bulk copies, or kept resident when the layer's whole
-//     weight set fits (all C<=64 layers).
+//   * activations live in HBM as "F16B" planes [B][C/64][Lp][64] (already leaky-relu'd by the
+//     producer's epilogue) whose rows are stored PRE-SWIZZLED: the 16-byte chunks of every 128-byte
+//     row are XOR-permuted by (row & 7) exactly like the UMMA SWIZZLE_128B shared-memory layout
+//     (64-byte rows / SWIZZLE_64B when C = 32).  One bulk-TMA copy (cp.async.bulk) per 64-channel
+//     chunk fetches the rows [floor8(m0 + omin), ... + W) of a work item; because the copy starts at
+//     a row that is a multiple of 8 and lands 1024-byte aligned, it arrives in shared memory already
+//     in the canonical K-major swizzled operand layout (SBO = 1024 B) - no tensor map, no repack.
+//     The operand of tap t is the SAME buffer with the descriptor start address advanced by off_t
+//     rows (matrix base offset = address bits 7..9): every tap, every dilation and every phase of a
+//     transposed conv reuse one window; zero padding comes from the zero pad rows of the plane.
+//     (A first version used the SWIZZLE_NONE 8x16 B core-matrix layout: correct, but the tensor core
+//     fetches such operands at 32 B/clk - 128 cycles per 128x16 A tile, profiles/r01_*swizzle_none*.)
+//   * weights: per (kernel index, 64-channel chunk) an fp16 image [Cout][64] with the same swizzle,
+//     streamed through a ring of shared-memory stages by bulk copies, or kept resident when the
+//     layer's whole weight set fits (all C<=64 layers).
 //   * warp roles: warp 0 = copy producer, warp 1 = MMA issuer (one thread) + TMEM allocator,
-//     warps 2-5 = epilogue (TMEM -> registers -> bias/residual/MRF/leaky-relu -> fp32 F32B plane
+//     warps 2-9 = epilogue (TMEM -> registers -> bias/residual/MRF/leaky-relu -> fp32 F32B plane
 //     and/or fp16 F16B plane, fully coalesced 16 B per thread per 8 channels).
 //   * accumulators double-buffered in TMEM (2 x MT x Cout columns <= 512) so the epilogue of work
 //     item i overlaps the MMAs of item i+1; persistent CTAs, one per SM, static round-robin.
@@ -25,6 +29,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -34,12 +39,13 @@ namespace mb {
 
 namespace {
 
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kAStages = 2;
 constexpr int kAccStages = 2;
 constexpr int kMaxWStages = 16;
 constexpr uint32_t kSmemMax = 227 * 1024;
-constexpr size_t kPlaneSlack = 16 * 1024;
+constexpr size_t kPlaneSlack = 128 * 1024;
 
 struct TcParams {
   int B, Lin, Lout, Cin, Cout;
@@ -48,7 +54,9 @@ struct TcParams {
   int off[kMaxPhases][kMaxTaps];
   int slab[kMaxPhases][kMaxTaps];
   int omin, W, MT;
-  int c8_per_chunk, nk16, n_cchunks;
+  int cw, row_bytes, nk16, n_cchunks;   // channels per K-chunk (64 or 32), bytes per operand row
+  int layout_type;                     // UMMA layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+  int baseoff_mode;                    // 1: descriptor base_offset = start address bits 7..9
   int slab_bytes, wstages, resident;
   int tiles_per_utt, n_work;
   uint32_t a_stage_bytes, a_off, w_off, bias_off, bar_off;
@@ -114,13 +122,17 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// start address, LBO = 1 (unused for swizzled K-major), SBO = 8 rows, base offset, layout type
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type,
+                                              uint32_t base_offset) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)1 << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7) << 49;
+  d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
@@ -151,7 +163,8 @@ __device__ __forceinline__ WorkItem decode_work(const TcParams& p, int work) {
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024 B alignment
   uint8_t* a_base = smem + p.a_off;
   uint8_t* w_base = smem + p.w_off;
   float* bias_s = reinterpret_cast<float*>(smem + p.bias_off);
@@ -178,7 +191,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 32 * kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -194,7 +207,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int Cin8 = p.Cin >> 3;
 
   if (warp == 0) {
     // ===================== copy producer =====================
@@ -205,13 +217,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         const WorkItem wi = decode_work(p, work);
         for (int c = 0; c < p.n_cchunks; ++c) {
           mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-          mbar_expect_tx(&a_full[a_stage], (uint32_t)(p.c8_per_chunk * p.W * 16));
-          const uint32_t dst0 = smem_u32(a_base + (size_t)a_stage * p.a_stage_bytes);
-          for (int j = 0; j < p.c8_per_chunk; ++j) {
-            const __half* src = p.x16 + (((size_t)wi.b * Cin8 + c * p.c8_per_chunk + j) * p.x_Lp +
-                                         (size_t)(kPadRows + wi.m0 + p.omin)) * 8;
-            bulk_g2s(dst0 + (uint32_t)(j * p.W * 16), src, (uint32_t)(p.W * 16), &a_full[a_stage]);
-          }
+          const uint32_t bytes = (uint32_t)(p.W * p.row_bytes);
+          mbar_expect_tx(&a_full[a_stage], bytes);
+          const int row0 = (kPadRows + wi.m0 + p.omin) & ~7;  // multiple of 8: swizzle phases line up
+          const __half* src = p.x16 + (((size_t)wi.b * p.n_cchunks + c) * p.x_Lp + (size_t)row0) * p.cw;
+          bulk_g2s(smem_u32(a_base + (size_t)a_stage * p.a_stage_bytes), src, bytes, &a_full[a_stage]);
           if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1; }
           for (int t = 0; t < p.ntaps[wi.r]; ++t) {
             const int sid = p.slab[wi.r][t] * p.n_cchunks + c;
@@ -238,12 +248,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int a_stage = 0, a_phase = 0, w_stage = 0, w_phase = 0, acc_stage = 0, acc_phase = 0;
-      const uint32_t a_lbo = (uint32_t)p.W * 16, b_lbo = (uint32_t)p.Cout * 16;
+      const uint32_t sbo = 8u * (uint32_t)p.row_bytes;
       for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
         const WorkItem wi = decode_work(p, work);
         mbar_wait(&acc_empty[acc_stage], acc_phase ^ 1);
         tc_fence_after();
         uint32_t accumulate = 0;
+        const int delta = (kPadRows + wi.m0 + p.omin) & 7;  // rows the window start was rounded down by
         for (int c = 0; c < p.n_cchunks; ++c) {
           mbar_wait(&a_full[a_stage], a_phase);
           tc_fence_after();
@@ -259,12 +270,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
               w_addr = smem_u32(w_base + (size_t)w_stage * p.slab_bytes);
             }
             tc_fence_after();
-            const int row_shift = p.off[wi.r][t] - p.omin;
+            const int row_shift = delta + p.off[wi.r][t] - p.omin;
             for (int s = 0; s < p.nk16; ++s) {
-              const uint64_t bdesc = make_desc(w_addr + (uint32_t)(2 * s) * b_lbo, b_lbo, 128);
+              const uint64_t bdesc = make_desc(w_addr + (uint32_t)s * 32u, sbo, (uint32_t)p.layout_type, 0);
               for (int mt = 0; mt < p.MT; ++mt) {
-                const uint64_t adesc =
-                    make_desc(a_addr + (uint32_t)(2 * s) * a_lbo + (uint32_t)(mt * 128 + row_shift) * 16, a_lbo, 128);
+                const uint32_t aa = a_addr + (uint32_t)(mt * 128 + row_shift) * (uint32_t)p.row_bytes + (uint32_t)s * 32u;
+                const uint64_t adesc = make_desc(aa, sbo, (uint32_t)p.layout_type, p.baseoff_mode ? ((aa >> 7) & (p.layout_type == 2 ? 7u : 3u)) : 0u);
                 tc_mma_f16(tmem_base + (uint32_t)((acc_stage * p.MT + mt) * p.Cout), adesc, bdesc, idesc, accumulate);
               }
               accumulate = 1;
@@ -282,64 +293,101 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // Two groups of four warps; a group covers all four TMEM lane quarters and takes every other
+    // (row tile, 32-column) unit.  Per unit the residual / running-sum loads are issued FIRST (they do
+    // not depend on the accumulator, so for the first unit they overlap the MMAs of this work item),
+    // then the accumulator is read from TMEM, then everything is stored: 16 independent 16-byte
+    // loads in flight per thread instead of one.
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    const int grp = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     int acc_stage = 0, acc_phase = 0;
-    const int C4 = p.Cout >> 2, C8 = p.Cout >> 3;
+    const int C4 = p.Cout >> 2;
+    const int ocw = f16_cw(p.Cout);  // output plane: channels per row chunk
+    const int units_per_tile = p.Cout >> 5;
+    const int n_units = p.MT * units_per_tile;
     for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
       const WorkItem wi = decode_work(p, work);
       const int valid_out = p.lengths ? min(p.Lout, p.lengths[wi.b] * p.len_mul_out) : p.Lout;
-      mbar_wait(&acc_full[acc_stage], acc_phase);
-      tc_fence_after();
-      for (int mt = 0; mt < p.MT; ++mt) {
+      bool waited = false;
+      for (int u = grp; u < n_units; u += 2) {
+        const int mt = u / units_per_tile;
+        const int col0 = (u - mt * units_per_tile) << 5;
         const int q = wi.m0 + mt * 128 + row_in_tile;
         const int lo = q * p.stride + wi.r;
         const bool inb = q < p.Lin;
         const bool live = inb && lo < valid_out;
-        for (int col0 = 0; col0 < p.Cout; col0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc_stage * p.MT + mt) * p.Cout + col0),
-                    raw);
-          if (!inb) continue;
-          float v[32];
+        const size_t i32 = ((size_t)wi.b * C4 + (col0 >> 2)) * p.Lout + lo;  // + g * Lout per 4 channels
+        float4 rv[8], ov[8];
+        if (inb && p.res32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + bias_s[col0 + i];
+          for (int g = 0; g < 8; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.Lout];
+        }
+        if (inb && p.mode != EPI_STORE) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) ov[g] = reinterpret_cast<const float4*>(p.y32)[i32 + (size_t)g * p.Lout];
+        }
+        if (!waited) {
+          mbar_wait(&acc_full[acc_stage], acc_phase);
+          tc_fence_after();
+          waited = true;
+        }
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc_stage * p.MT + mt) * p.Cout + col0), raw);
+        if (!inb) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + bias_s[col0 + i];
+        if (p.res32) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const size_t i32 = (((size_t)wi.b * C4 + (col0 >> 2) + g) * p.Lout + lo);
-            if (p.res32) {
-              const float4 rv = reinterpret_cast<const float4*>(p.res32)[i32];
-              v[4 * g + 0] += rv.x; v[4 * g + 1] += rv.y; v[4 * g + 2] += rv.z; v[4 * g + 3] += rv.w;
-            }
-            if (p.mode != EPI_STORE) {
-              const float4 ov = reinterpret_cast<const float4*>(p.y32)[i32];
-              v[4 * g + 0] += ov.x; v[4 * g + 1] += ov.y; v[4 * g + 2] += ov.z; v[4 * g + 3] += ov.w;
-              if (p.mode == EPI_ADD_DIV) {
-                v[4 * g + 0] /= p.div; v[4 * g + 1] /= p.div; v[4 * g + 2] /= p.div; v[4 * g + 3] /= p.div;
-              }
-            }
-            if (!live) { v[4 * g + 0] = 0.f; v[4 * g + 1] = 0.f; v[4 * g + 2] = 0.f; v[4 * g + 3] = 0.f; }
-            if (p.y32)
-              reinterpret_cast<float4*>(p.y32)[i32] = make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-          }
-          if (p.y16) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              __half2 h0 = __floats2half2_rn(lrelu(v[8 * g + 0], p.out_slope), lrelu(v[8 * g + 1], p.out_slope));
-              __half2 h1 = __floats2half2_rn(lrelu(v[8 * g + 2], p.out_slope), lrelu(v[8 * g + 3], p.out_slope));
-              __half2 h2 = __floats2half2_rn(lrelu(v[8 * g + 4], p.out_slope), lrelu(v[8 * g + 5], p.out_slope));
-              __half2 h3 = __floats2half2_rn(lrelu(v[8 * g + 6], p.out_slope), lrelu(v[8 * g + 7], p.out_slope));
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              const size_t i16 = (((size_t)wi.b * C8 + (col0 >> 3) + g) * p.y_Lp + kPadRows + lo);
-              reinterpret_cast<uint4*>(p.y16)[i16] = pk;
-            }
+            v[4 * g + 0] += rv[g].x; v[4 * g + 1] += rv[g].y; v[4 * g + 2] += rv[g].z; v[4 * g + 3] += rv[g].w;
           }
         }
+        if (p.mode != EPI_STORE) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            v[4 * g + 0] += ov[g].x; v[4 * g + 1] += ov[g].y; v[4 * g + 2] += ov[g].z; v[4 * g + 3] += ov[g].w;
+          }
+          if (p.mode == EPI_ADD_DIV) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] /= p.div;
+          }
+        }
+        if (!live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (p.y32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            reinterpret_cast<float4*>(p.y32)[i32 + (size_t)g * p.Lout] =
+                make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+        if (p.y16) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            __half2 h0 = __floats2half2_rn(lrelu(v[8 * g + 0], p.out_slope), lrelu(v[8 * g + 1], p.out_slope));
+            __half2 h1 = __floats2half2_rn(lrelu(v[8 * g + 2], p.out_slope), lrelu(v[8 * g + 3], p.out_slope));
+            __half2 h2 = __floats2half2_rn(lrelu(v[8 * g + 4], p.out_slope), lrelu(v[8 * g + 5], p.out_slope));
+            __half2 h3 = __floats2half2_rn(lrelu(v[8 * g + 6], p.out_slope), lrelu(v[8 * g + 7], p.out_slope));
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            const int rr = kPadRows + lo;
+            const int cc = (col0 & (ocw - 1)) + 8 * g;  // channel within the row chunk
+            const size_t i16 = (((size_t)wi.b * (p.Cout / ocw) + col0 / ocw) * p.y_Lp + rr) * (size_t)(ocw >> 3) +
+                               (size_t)((cc >> 3) ^ f16_swz(ocw, rr));
+            reinterpret_cast<uint4*>(p.y16)[i16] = pk;
+          }
+        }
+      }
+      if (!waited) {
+        mbar_wait(&acc_full[acc_stage], acc_phase);
+        tc_fence_after();
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc_stage]);
@@ -355,30 +403,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
   }
 }
 
-// fp32 slabs [K][Cin][Cout] -> fp16 images [K][n_cchunks][kc/8][Cout][8]
+// fp32 slabs [K][Cin][Cout] -> fp16 images [K][n_cchunks][Cout][cw], rows swizzled like the operand planes
 __global__ void pack_w16_kernel(const float* __restrict__ w32, __half* __restrict__ dst, int K, int Cin, int Cout,
-                                int kc) {
+                                int cw) {
   const size_t n = (size_t)K * Cin * Cout;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  // destination-linear index -> (k, chunk, j, co, e)
-  const int e = (int)(i & 7);
-  size_t r = i >> 3;
-  const int co = (int)(r % Cout);
-  r /= Cout;
-  const int c8 = kc >> 3;
-  const int j = (int)(r % c8);
-  r /= c8;
-  const int nch = Cin / kc;
-  const int c = (int)(r % nch);
-  const int k = (int)(r / nch);
-  const int ci = c * kc + j * 8 + e;
-  dst[i] = __float2half_rn(w32[((size_t)k * Cin + ci) * Cout + co]);
+  // source-linear index -> (k, ci, co)
+  const int co = (int)(i % Cout);
+  const int ci = (int)((i / Cout) % Cin);
+  const int k = (int)(i / ((size_t)Cout * Cin));
+  const int nch = Cin / cw;
+  const int c = ci / cw, cc = ci - c * cw;
+  const size_t img = ((size_t)k * nch + c) * (size_t)Cout * cw;
+  const size_t off = (size_t)co * cw + (size_t)((((cc >> 3) ^ f16_swz(cw, co)) << 3) + (cc & 7));
+  dst[img + off] = __float2half_rn(w32[i]);
 }
 
 int pick_kc(int Cin) {
   if (Cin % 64 == 0) return 64;
-  if (Cin <= 64 && Cin % 16 == 0) return Cin;
+  if (Cin == 32) return 32;
   return 0;
 }
 
@@ -404,21 +448,23 @@ bool plan_smem(const TapConv& t, const TcLayer& tc, int total_slabs, SmemPlan* s
       omax = std::max(omax, t.off[r][i]);
     }
   if (-omin > kPadRows || omax > kPadRows) return false;
+  const int row_bytes = tc.kc * 2;
   sp->omin = omin;
-  sp->W = tc.mt * 128 + (omax - omin);
-  sp->a_stage_bytes = (uint32_t)align_up((size_t)(tc.kc / 8) * sp->W * 16, 128);
+  sp->W = (tc.mt * 128 + (omax - omin) + 7 + 7) & ~7;  // + up to 7 rows of start rounding, multiple of 8
+  sp->a_stage_bytes = (uint32_t)align_up((size_t)sp->W * row_bytes, 1024);
   sp->a_off = 0;
   sp->w_off = sp->a_off + kAStages * sp->a_stage_bytes;
   const uint32_t tail = (uint32_t)align_up((size_t)t.Cout * 4, 128) + 1024;
-  if (sp->w_off + tail + 2 * tc.slab_bytes > kSmemMax) return false;
-  int ws = (int)((kSmemMax - sp->w_off - tail) / tc.slab_bytes);
+  const uint32_t usable = kSmemMax - 1024;  // the kernel aligns its base to 1024 B
+  if (sp->w_off + tail + 2 * tc.slab_bytes > usable) return false;
+  int ws = (int)((usable - sp->w_off - tail) / tc.slab_bytes);
   ws = std::min(ws, kMaxWStages);
   sp->resident = (total_slabs <= ws) ? 1 : 0;
   sp->wstages = sp->resident ? total_slabs : ws;
   sp->bias_off = sp->w_off + (uint32_t)sp->wstages * (uint32_t)tc.slab_bytes;
   sp->bar_off = sp->bias_off + (uint32_t)align_up((size_t)t.Cout * 4, 128);
   sp->total = sp->bar_off + 1024;
-  return sp->total <= kSmemMax;
+  return sp->total <= usable;
 }
 
 int kernel_count(const TapConv& t) {
@@ -428,15 +474,23 @@ int kernel_count(const TapConv& t) {
   return k;
 }
 
-struct Plane {
-  TRef ref;  // current geometry
-};
+// how the A descriptor encodes a start address that is not 1024-byte aligned (row-shifted taps):
+// 1 (default) = matrix base offset field = address bits 7..9; 0 = leave the field zero.
+// MB_TC_BASEOFF overrides for experiments.
+int tc_baseoff_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("MB_TC_BASEOFF");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
+}
 
 size_t f16_plane_bytes(size_t B, size_t T, size_t cr) {
-  // worst case pads: C = 512 channels -> 64 runs per utterance
-  return align_up(2 * B * T * cr + B * 64 * (2 * kPadRows) * 16 + kPlaneSlack, 256);
+  // rows are padded to Lp = ceil8(L + 2*kPadRows) <= L + 2*kPadRows + 7 for at most 512 channels
+  return align_up(2 * B * T * cr + 2 * B * 512 * (2 * kPadRows + 7) + kPlaneSlack, 1024);
 }
-size_t f32_plane_bytes(size_t B, size_t T, size_t cr) { return align_up(4 * B * T * cr + 256, 256); }
+size_t f32_plane_bytes(size_t B, size_t T, size_t cr) { return align_up(4 * B * T * cr + 256, 1024); }
 
 int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef& res32, const TRef& y32,
               const TRef& y16, float out_slope, const int32_t* lengths, int B, int Lin, cudaStream_t st) {
@@ -458,7 +512,10 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.omin = sp.omin;
   p.W = sp.W;
   p.MT = op.tc.mt;
-  p.c8_per_chunk = op.tc.kc / 8;
+  p.cw = op.tc.kc;
+  p.row_bytes = op.tc.kc * 2;
+  p.layout_type = (op.tc.kc == 64) ? 2 : 4;
+  p.baseoff_mode = tc_baseoff_mode();
   p.nk16 = op.tc.kc / 16;
   p.n_cchunks = op.tc.n_cchunks;
   p.slab_bytes = (int)op.tc.slab_bytes;
@@ -472,13 +529,13 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.bias_off = sp.bias_off;
   p.bar_off = sp.bar_off;
   p.x16 = reinterpret_cast<const __half*>(x16.p);
-  p.x_Lp = x16.L + 2 * kPadRows;
+  p.x_Lp = f16_lp(x16.L);
   p.w16 = reinterpret_cast<const __half*>(tc_arena + op.tc.w16_off);
   p.bias = op.b32;
   p.res32 = reinterpret_cast<const float*>(res32.p);
   p.y32 = reinterpret_cast<float*>(y32.p);
   p.y16 = reinterpret_cast<__half*>(y16.p);
-  p.y_Lp = y16.L + 2 * kPadRows;
+  p.y_Lp = f16_lp(y16.L);
   p.out_slope = out_slope;
   p.mode = t.mode;
   p.div = t.div;
@@ -549,7 +606,7 @@ int tc_pack_weights(const TcLayer& tc, const TapConv& taps, const float* w32_sla
 size_t tc_workspace_bytes(const std::vector<TcBufReq>& bufs, int B, int T, int num_mels, int hop) {
   (void)num_mels;
   (void)hop;
-  size_t total = 512;
+  size_t total = 2048;
   for (const TcBufReq& b : bufs) total += f16_plane_bytes(B, T, b.cr) + f32_plane_bytes(B, T, b.cr);
   return total;
 }
@@ -563,7 +620,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
   // carve planes
   std::vector<char*> p16(nb), p32(nb);
   std::vector<TRef> cur16(nb), cur32(nb);  // geometry each plane currently holds
-  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
   for (int i = 0; i < nb; ++i) {
     p16[i] = ws;
     ws += f16_plane_bytes(B, T, bufs[i].cr);
@@ -706,10 +763,10 @@ int tc_debug_layer(const TcOp& op, const char* tc_arena, const float* x, const f
     return MB_OK;
   }
   // planes: x16 (activated), res32, y32
-  const size_t b_x16 = align_up((size_t)B * (t.Cin / 8) * (Lin + 2 * kPadRows) * 16 + kPlaneSlack, 256);
-  const size_t b_r32 = align_up((size_t)B * t.Cout * Lout * 4, 256);
-  if (workspace_bytes < b_x16 + 2 * b_r32 + 512) return fail(MB_ERR_WORKSPACE, "tc_debug_layer: workspace too small");
-  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const size_t b_x16 = align_up((size_t)B * t.Cin * f16_lp(Lin) * 2 + kPlaneSlack, 1024);
+  const size_t b_r32 = align_up((size_t)B * t.Cout * Lout * 4, 1024);
+  if (workspace_bytes < b_x16 + 2 * b_r32 + 2048) return fail(MB_ERR_WORKSPACE, "tc_debug_layer: workspace too small");
+  char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
   TRef x16 = make_ref(ws, LAYOUT_F16B, t.Cin, Lin);
   TRef r32 = residual ? make_ref(ws + b_x16, LAYOUT_F32B, t.Cout, Lout) : TRef{};
   TRef y32 = make_ref(ws + b_x16 + b_r32, LAYOUT_F32B, t.Cout, Lout);

@@ -231,7 +231,7 @@ class GanGenerator:
         cout = int(info.split("cout=")[1].split()[0])
         y = torch.zeros(B, cout, out_rows, dtype=torch.float32, device=x.device)
         cin = x.shape[1]
-        need = B * (cin // 8 + 1) * (L + 96) * 16 + 2 * B * cout * out_rows * 4 + (1 << 20)
+        need = B * cin * (L + 96) * 2 + 2 * B * cout * out_rows * 4 + (1 << 20)
         ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         rp = C.c_void_p(residual.contiguous().data_ptr()) if residual is not None else None

@@ -173,3 +173,21 @@ def build_wavernn(seed: int = 0):
                 sample_rate=hp.sample_rate, mode=hp.voc_mode)
     m.eval()
     return m
+
+
+def build_tacotron(seed: int = 0):
+    """Reference Tacotron as synthesizer/inference.py:52-65 builds it."""
+    install()
+    import torch
+    from models.synthesizer.hparams import hparams
+    from models.synthesizer.models.tacotron import Tacotron
+    from models.synthesizer.utils.symbols import symbols
+
+    torch.manual_seed(seed)
+    m = Tacotron(embed_dims=hparams.tts_embed_dims, num_chars=len(symbols), encoder_dims=hparams.tts_encoder_dims,
+                 decoder_dims=hparams.tts_decoder_dims, n_mels=hparams.num_mels, fft_bins=hparams.num_mels,
+                 postnet_dims=hparams.tts_postnet_dims, encoder_K=hparams.tts_encoder_K, lstm_dims=hparams.tts_lstm_dims,
+                 postnet_K=hparams.tts_postnet_K, num_highways=hparams.tts_num_highways, dropout=hparams.tts_dropout,
+                 stop_threshold=hparams.tts_stop_threshold, speaker_embedding_size=hparams.speaker_embedding_size)
+    m.eval()
+    return m

@@ -235,3 +235,118 @@ def wavernn_noise(seed: int, B: int, steps: int) -> torch.Tensor:
     for i in range(steps):
         out[i] = torch.empty(B, 512).exponential_(1)
     return out
+
+
+# ---- Tacotron (models/synthesizer/models/tacotron.py:140-162; hparams models/synthesizer/hparams.py) ----
+TACOTRON_HP = dict(embed_dims=512, num_chars=75, encoder_dims=256, decoder_dims=128, n_mels=80, fft_bins=80,
+                   postnet_dims=512, encoder_K=5, lstm_dims=1024, postnet_K=5, num_highways=4, dropout=0.5,
+                   stop_threshold=-3.4, speaker_embedding_size=256, gst_E=512, gst_token_num=10, gst_heads=8,
+                   gst_ref_filters=(32, 32, 64, 64, 128, 128), gst_n_mels=256, max_r=20)
+
+
+def _cbhg_modules(sd, prefix, K, in_channels, channels, proj_channels, num_highways):
+    """CBHG.__init__ construction order (sublayer/cbhg.py:7-41)"""
+    nn = torch.nn
+
+    def bnconv(name, cin, cout, k):
+        sd[f"{name}.conv.weight"] = nn.Conv1d(cin, cout, k, bias=False).weight.detach()
+        bn = nn.BatchNorm1d(cout)
+        for leaf in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+            sd[f"{name}.bnorm.{leaf}"] = getattr(bn, leaf).detach().clone()
+
+    for i, k in enumerate(range(1, K + 1)):
+        bnconv(f"{prefix}.conv1d_bank.{i}", in_channels, channels, k)
+    bnconv(f"{prefix}.conv_project1", K * channels, proj_channels[0], 3)
+    bnconv(f"{prefix}.conv_project2", proj_channels[0], proj_channels[1], 3)
+    if proj_channels[-1] != channels:
+        sd[f"{prefix}.pre_highway.weight"] = nn.Linear(proj_channels[-1], channels, bias=False).weight.detach()
+    for i in range(num_highways):
+        w1, w2 = nn.Linear(channels, channels), nn.Linear(channels, channels)
+        sd[f"{prefix}.highways.{i}.W1.weight"], sd[f"{prefix}.highways.{i}.W1.bias"] = w1.weight.detach(), torch.zeros(channels)
+        sd[f"{prefix}.highways.{i}.W2.weight"], sd[f"{prefix}.highways.{i}.W2.bias"] = w2.weight.detach(), w2.bias.detach()
+    g = nn.GRU(channels, channels // 2, batch_first=True, bidirectional=True)
+    for n, p in g.named_parameters():
+        sd[f"{prefix}.rnn.{n}"] = p.detach()
+
+
+def tacotron_state_dict(seed: int = 0, r: int = 2, randomize_bn: bool = True) -> Dict[str, torch.Tensor]:
+    """``torch.manual_seed(seed); Tacotron(**hparams)`` state_dict rebuilt from stock torch layers in the
+    reference's construction order; ``decoder.r`` (a loaded buffer, tacotron.py:53) set to ``r``."""
+    nn = torch.nn
+    hp = TACOTRON_HP
+    torch.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, i, o, bias=True):
+        m = nn.Linear(i, o, bias=bias)
+        sd[name + ".weight"] = m.weight.detach()
+        if bias:
+            sd[name + ".bias"] = m.bias.detach()
+
+    # Encoder (tacotron.py:11-29)
+    sd["encoder.embedding.weight"] = nn.Embedding(hp["num_chars"], hp["embed_dims"]).weight.detach()
+    lin("encoder.pre_net.fc1", hp["embed_dims"], hp["encoder_dims"])
+    lin("encoder.pre_net.fc2", hp["encoder_dims"], hp["encoder_dims"])
+    _cbhg_modules(sd, "encoder.cbhg", hp["encoder_K"], hp["encoder_dims"], hp["encoder_dims"],
+                  [hp["encoder_dims"], hp["encoder_dims"]], hp["num_highways"])
+    project_dims = hp["encoder_dims"] + hp["speaker_embedding_size"] + hp["gst_E"]
+    lin("encoder_proj", project_dims, hp["decoder_dims"], bias=False)
+    # GlobalStyleToken (sublayer/global_style_token.py:9-96)
+    filters = [1] + list(hp["gst_ref_filters"])
+    convs = [nn.Conv2d(filters[i], filters[i + 1], (3, 3), (2, 2), (1, 1)) for i in range(len(filters) - 1)]
+    for i, c in enumerate(convs):
+        sd[f"gst.encoder.convs.{i}.weight"], sd[f"gst.encoder.convs.{i}.bias"] = c.weight.detach(), c.bias.detach()
+    for i, f in enumerate(hp["gst_ref_filters"]):
+        bn = nn.BatchNorm2d(f)
+        for leaf in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+            sd[f"gst.encoder.bns.{i}.{leaf}"] = getattr(bn, leaf).detach().clone()
+    L = hp["gst_n_mels"]
+    for _ in convs:
+        L = (L - 3 + 2) // 2 + 1
+    g = nn.GRU(hp["gst_ref_filters"][-1] * L, hp["gst_E"] // 2, batch_first=True)
+    for n, p in g.named_parameters():
+        sd[f"gst.encoder.gru.{n}"] = p.detach()
+    d_q = hp["gst_E"] // 2 + hp["speaker_embedding_size"]
+    d_k = hp["gst_E"] // hp["gst_heads"]
+    lin("gst.stl.attention.W_query", d_q, hp["gst_E"], bias=False)
+    lin("gst.stl.attention.W_key", d_k, hp["gst_E"], bias=False)
+    lin("gst.stl.attention.W_value", d_k, hp["gst_E"], bias=False)
+    sd["gst.stl.embed"] = torch.empty(hp["gst_token_num"], d_k).normal_(0, 0.5)
+    # Decoder (tacotron.py:50-65)
+    lin("decoder.prenet.fc1", hp["n_mels"], hp["decoder_dims"] * 2)
+    lin("decoder.prenet.fc2", hp["decoder_dims"] * 2, hp["decoder_dims"] * 2)
+    c = nn.Conv1d(1, 32, 31, padding=15)
+    sd["decoder.attn_net.conv.weight"], sd["decoder.attn_net.conv.bias"] = c.weight.detach(), c.bias.detach()
+    lin("decoder.attn_net.L", 32, hp["decoder_dims"], bias=False)
+    lin("decoder.attn_net.W", hp["decoder_dims"], hp["decoder_dims"])
+    lin("decoder.attn_net.v", hp["decoder_dims"], 1, bias=False)
+    cell = nn.GRUCell(project_dims + hp["decoder_dims"] * 2, hp["decoder_dims"])
+    for n, p in cell.named_parameters():
+        sd[f"decoder.attn_rnn.{n}"] = p.detach()
+    lin("decoder.rnn_input", project_dims + hp["decoder_dims"], hp["lstm_dims"])
+    for name in ("res_rnn1", "res_rnn2"):
+        cell = nn.LSTMCell(hp["lstm_dims"], hp["lstm_dims"])
+        for n, p in cell.named_parameters():
+            sd[f"decoder.{name}.{n}"] = p.detach()
+    lin("decoder.mel_proj", hp["lstm_dims"], hp["n_mels"] * hp["max_r"], bias=False)
+    lin("decoder.stop_proj", project_dims + hp["lstm_dims"], 1)
+    sd["decoder.r"] = torch.tensor(r, dtype=torch.int)
+    # postnet (tacotron.py:160-162)
+    _cbhg_modules(sd, "postnet", hp["postnet_K"], hp["n_mels"], hp["postnet_dims"], [hp["postnet_dims"], hp["fft_bins"]],
+                  hp["num_highways"])
+    lin("post_proj", hp["postnet_dims"], hp["fft_bins"], bias=False)
+    sd["step"] = torch.zeros(1, dtype=torch.long)
+    sd["stop_threshold"] = torch.tensor(hp["stop_threshold"], dtype=torch.float32)
+    if randomize_bn:
+        g2 = torch.Generator().manual_seed(20_000 + seed)
+        for k in sorted(sd):
+            if ".bnorm." in k or ".bns." in k:
+                if k.endswith(".running_var"):
+                    sd[k] = torch.rand(sd[k].shape, generator=g2) * 1.5 + 0.25
+                elif k.endswith(".running_mean"):
+                    sd[k] = torch.randn(sd[k].shape, generator=g2) * 0.3
+                elif k.endswith(".weight"):
+                    sd[k] = torch.rand(sd[k].shape, generator=g2) + 0.5
+                elif k.endswith(".bias"):
+                    sd[k] = torch.randn(sd[k].shape, generator=g2) * 0.2
+    return sd
