@@ -11,14 +11,14 @@
 //     a row that is a multiple of 8 and lands 1024-byte aligned, it arrives in shared memory already
 //     in the canonical K-major swizzled operand layout (SBO = 1024 B) - no tensor map, no repack.
 //     The operand of tap t is the SAME buffer with the descriptor start address advanced by off_t
-//     rows (matrix base offset = address bits 7..9): every tap, every dilation and every phase of a
+//     rows (the swizzle is a function of absolute smem address bits, so no base-offset fix-up is needed): every tap, every dilation and every phase of a
 //     transposed conv reuse one window; zero padding comes from the zero pad rows of the plane.
 //     (A first version used the SWIZZLE_NONE 8x16 B core-matrix layout: correct, but the tensor core
 //     fetches such operands at 32 B/clk - 128 cycles per 128x16 A tile, profiles/r01_*swizzle_none*.)
 //   * weights: per (kernel index, 64-channel chunk) an fp16 image [Cout][64] with the same swizzle,
 //     streamed through a ring of shared-memory stages by bulk copies, or kept resident when the
 //     layer's whole weight set fits (all C<=64 layers).
-//   * warp roles: warp 0 = copy producer, warp 1 = MMA issuer (one thread) + TMEM allocator,
+//   * warp roles: warp 0 = copy producer, warp 1 = MMA issuer (warp-uniform loop, one elected lane issues) + TMEM allocator,
 //     warps 2-9 = epilogue (TMEM -> registers -> bias/residual/MRF/leaky-relu -> fp32 F32B plane
 //     and/or fp16 F16B plane, fully coalesced 16 B per thread per 8 channels).
 //   * accumulators double-buffered in TMEM (2 x MT x Cout columns <= 512) so the epilogue of work
@@ -148,6 +148,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 struct WorkItem {
@@ -162,6 +174,10 @@ __device__ __forceinline__ WorkItem decode_work(const TcParams& p, int work) {
   return w;
 }
 
+// N = Cout, MT = row tiles per work item, CW = channels per operand row (64: SWIZZLE_128B, 32: SWIZZLE_64B).
+// They are compile-time so that every MMA's descriptor is "base + immediate" (the single issuing
+// thread is otherwise the bottleneck: ~190 cycles per MMA with run-time address arithmetic).
+template <int N, int MT, int CW>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024 B alignment
@@ -245,21 +261,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // The whole warp runs this loop in lock-step; one elected lane issues the tcgen05 instructions.
+    // Descriptors differ only in their low word (start address >> 4) and all per-MMA offsets are
+    // immediates.
+    {
+      constexpr uint32_t ROWB = CW * 2;
+      constexpr int NK16 = CW / 16;
+      constexpr uint32_t MT_STEP = (128u * ROWB) >> 4;
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int a_stage = 0, a_phase = 0, w_stage = 0, w_phase = 0, acc_stage = 0, acc_phase = 0;
-      const uint32_t sbo = 8u * (uint32_t)p.row_bytes;
+      const uint64_t desc_hi = make_desc(0, 8u * ROWB, CW == 64 ? 2u : 4u, 0);  // everything but the address
+      const bool leader = elect_one();
       for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
         const WorkItem wi = decode_work(p, work);
         mbar_wait(&acc_empty[acc_stage], acc_phase ^ 1);
         tc_fence_after();
-        uint32_t accumulate = 0;
         const int delta = (kPadRows + wi.m0 + p.omin) & 7;  // rows the window start was rounded down by
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc_stage * MT * N);
+        const int nt = p.ntaps[wi.r];
+        bool first = true;
         for (int c = 0; c < p.n_cchunks; ++c) {
           mbar_wait(&a_full[a_stage], a_phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_base + (size_t)a_stage * p.a_stage_bytes);
-          for (int t = 0; t < p.ntaps[wi.r]; ++t) {
+          for (int t = 0; t < nt; ++t) {
             uint32_t w_addr;
             if (p.resident) {
               const int sid = p.slab[wi.r][t] * p.n_cchunks + c;
@@ -270,25 +295,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
               w_addr = smem_u32(w_base + (size_t)w_stage * p.slab_bytes);
             }
             tc_fence_after();
-            const int row_shift = delta + p.off[wi.r][t] - p.omin;
-            for (int s = 0; s < p.nk16; ++s) {
-              const uint64_t bdesc = make_desc(w_addr + (uint32_t)s * 32u, sbo, (uint32_t)p.layout_type, 0);
-              for (int mt = 0; mt < p.MT; ++mt) {
-                const uint32_t aa = a_addr + (uint32_t)(mt * 128 + row_shift) * (uint32_t)p.row_bytes + (uint32_t)s * 32u;
-                const uint64_t adesc = make_desc(aa, sbo, (uint32_t)p.layout_type, p.baseoff_mode ? ((aa >> 7) & (p.layout_type == 2 ? 7u : 3u)) : 0u);
-                tc_mma_f16(tmem_base + (uint32_t)((acc_stage * p.MT + mt) * p.Cout), adesc, bdesc, idesc, accumulate);
+            const uint64_t a0 = desc_hi + (uint64_t)((a_addr + (uint32_t)(delta + p.off[wi.r][t] - p.omin) * ROWB) >> 4);
+            const uint64_t b0 = desc_hi + (uint64_t)(w_addr >> 4);
+            if (leader) {
+              if (first) {
+#pragma unroll
+                for (int s = 0; s < NK16; ++s)
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt)
+                    tc_mma_f16(d_tmem + (uint32_t)(mt * N), a0 + (uint64_t)(2 * s + mt * MT_STEP), b0 + (uint64_t)(2 * s),
+                               idesc, s > 0 ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int s = 0; s < NK16; ++s)
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt)
+                    tc_mma_f16(d_tmem + (uint32_t)(mt * N), a0 + (uint64_t)(2 * s + mt * MT_STEP), b0 + (uint64_t)(2 * s),
+                               idesc, 1u);
               }
-              accumulate = 1;
+              if (!p.resident) tc_commit(&w_empty[w_stage]);
             }
+            first = false;
             if (!p.resident) {
-              tc_commit(&w_empty[w_stage]);
               if (++w_stage == p.wstages) { w_stage = 0; w_phase ^= 1; }
             }
           }
-          tc_commit(&a_empty[a_stage]);
+          if (leader) tc_commit(&a_empty[a_stage]);
           if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1; }
         }
-        tc_commit(&acc_full[acc_stage]);
+        if (leader) tc_commit(&acc_full[acc_stage]);
         if (++acc_stage == kAccStages) { acc_stage = 0; acc_phase ^= 1; }
       }
     }
@@ -427,7 +462,8 @@ int pick_kc(int Cin) {
 }
 
 bool tc_capable(const TapConv& t) {
-  if (t.Cout < 32 || t.Cout > 256 || (t.Cout % 32) != 0) return false;
+  if (t.Cout != 32 && t.Cout != 64 && t.Cout != 128 && t.Cout != 256) return false;  // kernel instances
+  if (t.Cout != 32 && pick_kc(t.Cin) != 64) return false;
   if (pick_kc(t.Cin) == 0) return false;
   if (t.act_tanh) return false;
   return true;
@@ -474,14 +510,15 @@ int kernel_count(const TapConv& t) {
   return k;
 }
 
-// how the A descriptor encodes a start address that is not 1024-byte aligned (row-shifted taps):
-// 1 (default) = matrix base offset field = address bits 7..9; 0 = leave the field zero.
-// MB_TC_BASEOFF overrides for experiments.
+// how the A descriptor encodes a start address that is not 1024-byte aligned (row-shifted taps).
+// Measured on B200 (tests/test_gan_tc_layers.py under MB_TC_BASEOFF=0/1): the operand fetch applies the
+// swizzle XOR on absolute shared-memory address bits, so the matrix-base-offset field must stay 0
+// (mode 0, default); mode 1 (field = address bits 7..9) double-counts the phase and is wrong.
 int tc_baseoff_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("MB_TC_BASEOFF");
-    mode = e ? atoi(e) : 1;
+    mode = e ? atoi(e) : 0;
   }
   return mode;
 }
@@ -542,18 +579,21 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.lengths = lengths;
   p.len_mul_out = t.len_mul_out;
   if (p.mode != EPI_STORE && !p.y32) return fail(MB_ERR_INVALID, "tc_conv(%s): accumulate mode without fp32 plane", op.name);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MB_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    attr_set = true;
-  }
+  void (*kern)(const TcParams) = nullptr;
+  if (p.Cout == 256 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<256, 1, 64>;
+  else if (p.Cout == 128 && p.MT == 2 && p.cw == 64) kern = tc_conv_kernel<128, 2, 64>;
+  else if (p.Cout == 64 && p.MT == 2 && p.cw == 64) kern = tc_conv_kernel<64, 2, 64>;
+  else if (p.Cout == 32 && p.MT == 4 && p.cw == 64) kern = tc_conv_kernel<32, 4, 64>;
+  else if (p.Cout == 32 && p.MT == 4 && p.cw == 32) kern = tc_conv_kernel<32, 4, 32>;
+  else return fail(MB_ERR_INVALID, "tc_conv(%s): no kernel instance for Cout=%d MT=%d cw=%d", op.name, p.Cout, p.MT, p.cw);
+  MB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(p.n_work, sms);
   if (grid <= 0) return MB_OK;
   // always claim the whole shared memory: one CTA per SM, so the 512-column TMEM allocation never contends
-  tc_conv_kernel<<<grid, kTcThreads, kSmemMax, st>>>(p);
+  kern<<<grid, kTcThreads, kSmemMax, st>>>(p);
   MB_LAUNCH_CHECK("tc_conv_kernel");
   return MB_OK;
 }
