@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) tapconv_f32_kernel(TapConv p, TapConvIO i
   }
 }
 
-// Cout == 1: one thread per output row, weights [taps][Cin] in shared memory
+// Cout == 1 (conv_post): weights [taps][Cin] in shared memory; a thread produces 4 consecutive output
+// rows so that every input row it loads is reused by up to 4 outputs.
 __global__ void __launch_bounds__(256) tapconv_cout1_kernel(TapConv p, TapConvIO io, const float* __restrict__ w,
                                                             const float* __restrict__ bias) {
   extern __shared__ float wsm[];  // [ntaps][Cin]
@@ -141,36 +142,48 @@ __global__ void __launch_bounds__(256) tapconv_cout1_kernel(TapConv p, TapConvIO
     wsm[i] = w[((size_t)p.slab[0][t] * p.Cin + ci) * p.Cout];
   }
   __syncthreads();
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= p.Lin) return;
+  const int l0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (l0 >= p.Lin) return;
   const int valid_in = p.lengths ? min(p.Lin, p.lengths[b] * p.len_mul_in) : p.Lin;
   const int valid_out = p.lengths ? min(p.Lout, p.lengths[b] * p.len_mul_out) : p.Lout;
   const float in_slope = (io.x.layout == LAYOUT_F16B) ? 1.f : p.in_slope;
-  float acc = 0.f;
-  if (io.x.layout == LAYOUT_F32B) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // contiguous tap offsets off[t] = t - pad (dilation 1) let us walk input rows once
+  const int o0 = p.off[0][0];
+  bool contiguous = true;
+  for (int t = 1; t < nt; ++t) contiguous = contiguous && (p.off[0][t] == o0 + t);
+  if (io.x.layout == LAYOUT_F32B && contiguous) {
     const float4* xp = reinterpret_cast<const float4*>(io.x.p);
     for (int c4 = 0; c4 < (p.Cin >> 2); ++c4) {
       const float4* run = xp + ((size_t)b * (p.Cin >> 2) + c4) * p.Lin;
-      for (int t = 0; t < nt; ++t) {
-        const int li = l + p.off[0][t];
+      for (int j = 0; j < nt + 3; ++j) {   // input row l0 + o0 + j feeds output i with tap t = j - i
+        const int li = l0 + o0 + j;
         if (li < 0 || li >= valid_in) continue;
-        const float4 v = run[li];
-        const float* wt = &wsm[t * p.Cin + c4 * 4];
-        acc = fmaf(wt[0], lrelu(v.x, in_slope), acc);
-        acc = fmaf(wt[1], lrelu(v.y, in_slope), acc);
-        acc = fmaf(wt[2], lrelu(v.z, in_slope), acc);
-        acc = fmaf(wt[3], lrelu(v.w, in_slope), acc);
+        float4 v = run[li];
+        v.x = lrelu(v.x, in_slope); v.y = lrelu(v.y, in_slope); v.z = lrelu(v.z, in_slope); v.w = lrelu(v.w, in_slope);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = j - i;
+          if (t < 0 || t >= nt) continue;
+          const float* wt = &wsm[t * p.Cin + c4 * 4];
+          acc[i] = fmaf(wt[0], v.x, acc[i]);
+          acc[i] = fmaf(wt[1], v.y, acc[i]);
+          acc[i] = fmaf(wt[2], v.z, acc[i]);
+          acc[i] = fmaf(wt[3], v.w, acc[i]);
+        }
       }
     }
   } else {
     for (int ci = 0; ci < p.Cin; ++ci)
-      for (int t = 0; t < nt; ++t) {
-        const int li = l + p.off[0][t];
-        if (li < 0 || li >= valid_in) continue;
-        acc = fmaf(wsm[t * p.Cin + ci], lrelu(tload(io.x, b, ci, li), in_slope), acc);
-      }
+      for (int t = 0; t < nt; ++t)
+        for (int i = 0; i < 4; ++i) {
+          const int li = l0 + i + p.off[0][t];
+          if (li < 0 || li >= valid_in) continue;
+          acc[i] = fmaf(wsm[t * p.Cin + ci], lrelu(tload(io.x, b, ci, li), in_slope), acc[i]);
+        }
   }
-  epilogue_store(p, io, b, 0, l, valid_out, acc + (bias ? bias[0] : 0.f));
+  for (int i = 0; i < 4; ++i)
+    if (l0 + i < p.Lin) epilogue_store(p, io, b, 0, l0 + i, valid_out, acc[i] + (bias ? bias[0] : 0.f));
 }
 
 __global__ void add_inplace_kernel(TRef dst32, TRef src32, TRef dst16, float slope, int B) {
@@ -255,7 +268,7 @@ cudaError_t launch_tapconv_f32(const TapConv& p, const TapConvIO& io, const floa
 cudaError_t launch_tapconv_cout1_f32(const TapConv& p, const TapConvIO& io, const float* w, const float* bias,
                                      cudaStream_t stream) {
   if (p.Cout != 1 || p.stride != 1) return cudaErrorInvalidValue;
-  dim3 grid((p.Lin + 255) / 256, p.B);
+  dim3 grid((p.Lin + 1023) / 1024, p.B);
   const size_t smem = sizeof(float) * p.ntaps[0] * p.Cin;
   tapconv_cout1_kernel<<<grid, 256, smem, stream>>>(p, io, w, bias);
   return cudaGetLastError();

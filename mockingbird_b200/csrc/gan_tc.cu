@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
       int a_stage = 0, a_phase = 0, w_stage = 0, w_phase = 0, acc_stage = 0, acc_phase = 0;
       const uint64_t desc_hi = make_desc(0, 8u * ROWB, CW == 64 ? 2u : 4u, 0);  // everything but the address
       const bool leader = elect_one();
+      uint32_t resident_seen = 0;  // resident weight images whose arrival has already been observed
       for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
         const WorkItem wi = decode_work(p, work);
         mbar_wait(&acc_empty[acc_stage], acc_phase ^ 1);
@@ -288,13 +289,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             uint32_t w_addr;
             if (p.resident) {
               const int sid = p.slab[wi.r][t] * p.n_cchunks + c;
-              mbar_wait(&w_full[sid], 0);
+              if (!(resident_seen & (1u << sid))) {
+                mbar_wait(&w_full[sid], 0);
+                tc_fence_after();
+                resident_seen |= 1u << sid;
+              }
               w_addr = smem_u32(w_base + (size_t)sid * p.slab_bytes);
             } else {
               mbar_wait(&w_full[w_stage], w_phase);
+              tc_fence_after();
               w_addr = smem_u32(w_base + (size_t)w_stage * p.slab_bytes);
             }
-            tc_fence_after();
             const uint64_t a0 = desc_hi + (uint64_t)((a_addr + (uint32_t)(delta + p.off[wi.r][t] - p.omin) * ROWB) >> 4);
             const uint64_t b0 = desc_hi + (uint64_t)(w_addr >> 4);
             if (leader) {
@@ -469,7 +474,8 @@ bool tc_capable(const TapConv& t) {
   return true;
 }
 
-int pick_mt(int Cout) { return Cout >= 256 ? 1 : (Cout >= 64 ? 2 : 4); }
+// row tiles per work item: as many as TMEM (2 x MT x Cout <= 512 columns) and shared memory allow
+int pick_mt_max(int Cout) { return Cout >= 256 ? 1 : (Cout >= 128 ? 2 : (Cout >= 64 ? 4 : 8)); }
 
 struct SmemPlan {
   uint32_t a_stage_bytes, a_off, w_off, bias_off, bar_off, total;
@@ -582,7 +588,12 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   void (*kern)(const TcParams) = nullptr;
   if (p.Cout == 256 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<256, 1, 64>;
   else if (p.Cout == 128 && p.MT == 2 && p.cw == 64) kern = tc_conv_kernel<128, 2, 64>;
+  else if (p.Cout == 128 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<128, 1, 64>;
+  else if (p.Cout == 64 && p.MT == 4 && p.cw == 64) kern = tc_conv_kernel<64, 4, 64>;
   else if (p.Cout == 64 && p.MT == 2 && p.cw == 64) kern = tc_conv_kernel<64, 2, 64>;
+  else if (p.Cout == 64 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<64, 1, 64>;
+  else if (p.Cout == 32 && p.MT == 8 && p.cw == 32) kern = tc_conv_kernel<32, 8, 32>;
+  else if (p.Cout == 32 && p.MT == 2 && p.cw == 64) kern = tc_conv_kernel<32, 2, 64>;
   else if (p.Cout == 32 && p.MT == 4 && p.cw == 64) kern = tc_conv_kernel<32, 4, 64>;
   else if (p.Cout == 32 && p.MT == 4 && p.cw == 32) kern = tc_conv_kernel<32, 4, 32>;
   else return fail(MB_ERR_INVALID, "tc_conv(%s): no kernel instance for Cout=%d MT=%d cw=%d", op.name, p.Cout, p.MT, p.cw);
@@ -619,10 +630,23 @@ int tc_plan_layers(std::vector<TcLayerDesc>& layers, size_t* tc_arena_bytes) {
     if (d.force_f32 || !tc_capable(t)) continue;
     tc.kc = pick_kc(t.Cin);
     tc.n_cchunks = t.Cin / tc.kc;
-    tc.mt = pick_mt(t.Cout);
     tc.slab_bytes = (size_t)tc.kc * t.Cout * 2;
     SmemPlan sp;
-    if (!plan_smem(t, tc, d.k * tc.n_cchunks, &sp)) continue;  // falls back to the FP32 kernel
+    bool ok = false;
+    for (tc.mt = pick_mt_max(t.Cout); tc.mt >= 1; tc.mt >>= 1) {
+      // keep the weights resident if a smaller tile count allows it; otherwise take the largest that fits
+      if (plan_smem(t, tc, d.k * tc.n_cchunks, &sp)) {
+        ok = true;
+        TcLayer half = tc;
+        half.mt = tc.mt >> 1;
+        SmemPlan sp2;
+        if (!sp.resident && half.mt >= 1 && plan_smem(t, half, d.k * tc.n_cchunks, &sp2) && sp2.resident) tc.mt = half.mt;
+        break;
+      }
+    }
+    if (!ok) continue;  // falls back to the FP32 kernel
+    if (t.Cout == 32 && tc.kc == 64 && tc.mt > 4) tc.mt = 4;  // instance list below
+    plan_smem(t, tc, d.k * tc.n_cchunks, &sp);
     if (sp.resident && d.k * tc.n_cchunks > 32) continue;
     tc.use_tc = 1;
     tc.w16_off = off;
