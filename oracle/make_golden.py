@@ -71,6 +71,12 @@ def main():
         make_golden_wavernn.main(GOLDEN, meta)
     except ImportError:
         pass
+    try:
+        import make_golden_tacotron
+
+        make_golden_tacotron.main(GOLDEN, meta)
+    except ImportError:
+        pass
     for p in sorted(GOLDEN.glob("*.npz")):
         print(p.name, p.stat().st_size)
 

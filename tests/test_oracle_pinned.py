@@ -89,3 +89,38 @@ def test_gan_oracles_bit_identical_to_reference_forward():
     with torch.no_grad():
         assert torch.equal(go.hifigan_forward(dict(g.state_dict()), rh.hifigan_config(), x), g(x))
         assert torch.equal(go.fregan_forward(dict(f.state_dict()), rh.fregan_config(), x), f(x))
+
+
+def _unpack_masks(z, name, B, Tc):
+    enc = np.unpackbits(z[f"{name}_enc_masks"], axis=-1).astype(bool)
+    dec = np.unpackbits(z[f"{name}_dec_masks"], axis=-1).astype(bool)
+    return [torch.from_numpy(m) for m in enc] + [torch.from_numpy(m) for m in dec]
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_tacotron_oracle_matches_golden(golden_dir, name):
+    """Tacotron.generate restatement with the captured PreNet dropout masks injected"""
+    import tacotron_oracle as to
+
+    z = np.load(golden_dir / "tacotron_seed0.npz")
+    sd = ri.tacotron_state_dict(0, r=2, randomize_bn=True)
+    chars, emb = torch.from_numpy(z[f"{name}_chars"]), torch.from_numpy(z[f"{name}_emb"])
+    steps, style, mst, r = [int(v) for v in z[f"{name}_cfg"]]
+    masks = _unpack_masks(z, name, *chars.shape)
+    mel, linear, attn = to.generate(sd, chars, emb, steps, style, mst, masks, r=r)
+    for got, key in ((mel, "mel"), (linear, "linear"), (attn, "attn")):
+        ref = torch.from_numpy(z[f"{name}_{key}"])
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5, key
+
+
+@needs_ref
+@pytest.mark.reference
+def test_ref_init_tacotron_bit_identical():
+    rh.install()
+    rh.hide_cuda()
+    m = rh.build_tacotron(seed=2)
+    sd = ri.tacotron_state_dict(2, r=1, randomize_bn=False)
+    ref = m.state_dict()
+    assert set(sd) == set(ref)
+    assert all(torch.equal(sd[k].float(), ref[k].float()) for k in sd)
