@@ -177,6 +177,59 @@ int mb_wavernn_generate(mb_wavernn* h, const int32_t* fold_starts_host, int32_t 
 /* debug/test hook: logits [folds, 512] fp32 of the LAST step executed by mb_wavernn_generate */
 int mb_wavernn_last_logits(mb_wavernn* h, float* logits, int32_t folds, void* workspace, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tacotron mel synthesizer
+ *   replaces  models/synthesizer/models/tacotron.py:140-298 (Tacotron.forward / generate: Encoder + CBHG,
+ *             global style token, attention decoder loop, postnet CBHG + post_proj),
+ *             driven by models/synthesizer/inference.py:75-142 (Synthesizer.synthesize_spectrograms)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mb_tacotron_config {
+  int32_t num_chars;              /* len(symbols) = 75 */
+  int32_t embed_dims;             /* 512 tts_embed_dims */
+  int32_t encoder_dims;           /* 256 */
+  int32_t decoder_dims;           /* 128 */
+  int32_t n_mels;                 /* 80  */
+  int32_t postnet_dims;           /* 512 */
+  int32_t encoder_K;              /* 5   */
+  int32_t lstm_dims;              /* 1024 */
+  int32_t postnet_K;              /* 5   */
+  int32_t num_highways;           /* 4   */
+  int32_t speaker_embedding_size; /* 256 */
+  int32_t gst_E;                  /* 512 gst_hyperparameters.E */
+  int32_t gst_tokens;             /* 10  */
+  int32_t gst_heads;              /* 8   */
+  int32_t max_r;                  /* 20  Decoder.max_r */
+} mb_tacotron_config;
+
+typedef struct mb_tacotron mb_tacotron;
+
+int mb_tacotron_create(const mb_tacotron_config* cfg, mb_tacotron** out);
+void mb_tacotron_destroy(mb_tacotron* h);
+size_t mb_tacotron_arena_bytes(const mb_tacotron* h);
+int mb_tacotron_set_arena(mb_tacotron* h, void* arena, size_t bytes);
+/* tensors of ckpt['model_state'] under their reference names, fp32, plus one
+ * derived tensor "gst.const_enc" [gst_E/2]: the GST ReferenceEncoder applied to the all-zero input of
+ * tacotron.py:251 - input independent, folded at load time by the host layer */
+int mb_tacotron_set_weight(mb_tacotron* h, const char* name, const float* w, const int64_t* dims, int32_t ndim,
+                           void* stream);
+int mb_tacotron_finalize(mb_tacotron* h, void* stream);
+size_t mb_tacotron_workspace_bytes(const mb_tacotron* h, int32_t batch, int32_t chars, int32_t steps, int32_t r);
+
+/* Tacotron.generate (tacotron.py:295-298) for one padded batch:
+ *   chars  int32 [B][Tc] (pad id 0), spk fp32 [B][speaker_embedding_size]
+ *   steps / r / style_idx / min_stop_token as the reference's arguments (r = decoder.r)
+ *   enc_masks uint8 [2][B*Tc][encoder_dims], dec_masks uint8 [ceil(steps/r)][2][B][2*decoder_dims]:
+ *     PreNet dropout keep-flags (pre_net.py:23,26 hard-wires training=True) to inject; NULL -> drawn
+ *     on the device from `seed`
+ *   mel / linear fp32 [B][n_mels][ceil(steps/r)*r] (first *frames_out_host frames valid, caller strides
+ *     by *frames_out_host: the arrays are written densely as [B][n_mels][frames]), attn fp32
+ *     [B][frames/r][Tc] or NULL.
+ * Synchronises the stream (the early-stop rule of tacotron.py:275 is polled every 16 decoder steps). */
+int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk, int32_t batch, int32_t n_chars,
+                         int32_t steps, int32_t r, int32_t style_idx, float min_stop_token, const uint8_t* enc_masks,
+                         const uint8_t* dec_masks, uint64_t seed, float* mel, float* linear, float* attn,
+                         int32_t* frames_out_host, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,12 @@ class WaveRNNConfig(C.Structure):
     ]
 
 
+class TacotronConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "num_chars", "embed_dims", "encoder_dims", "decoder_dims", "n_mels", "postnet_dims", "encoder_K", "lstm_dims",
+        "postnet_K", "num_highways", "speaker_embedding_size", "gst_E", "gst_tokens", "gst_heads", "max_r")]
+
+
 # name -> (restype, argtypes); every symbol include/mockingbird_b200.h declares
 SIGNATURES = {
     "mb_last_error": (C.c_char_p, []),
@@ -94,6 +100,17 @@ SIGNATURES = {
                                       C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
     "mb_wavernn_last_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mb_tacotron_create": (C.c_int, [C.POINTER(TacotronConfig), C.POINTER(C.c_void_p)]),
+    "mb_tacotron_destroy": (None, [C.c_void_p]),
+    "mb_tacotron_arena_bytes": (C.c_size_t, [C.c_void_p]),
+    "mb_tacotron_set_arena": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mb_tacotron_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32,
+                                         C.c_void_p]),
+    "mb_tacotron_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mb_tacotron_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "mb_tacotron_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -1,0 +1,870 @@
+// Tacotron inference on B200 (mb_tacotron_*): encoder (embedding, PreNet, CBHG), global style token,
+// attention decoder loop and postnet CBHG, lowered onto the FP32 kernels of tacotron_kernels.cu plus
+// the location-sensitive-attention step kernel below.
+//
+// reference: models/synthesizer/models/tacotron.py:199-298 (forward/generate), :71-138 (Decoder.forward),
+//            sublayer/cbhg.py:42-79, sublayer/lsa.py:21-42, sublayer/pre_net.py:11-27,
+//            sublayer/global_style_token.py:9-145
+// Activations are channels-last [rows][features]; Conv1d over time = shifted-row GEMM segments.
+#include "tacotron_kernels.cuh"
+
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mb_wavernn_math.h"
+#include "mb_common.h"
+
+namespace mb {
+namespace taco {
+
+namespace {
+
+// ---- location sensitive attention step: one CTA per batch row ---------------------------------------
+//   pq[d]   = W q + b                       (precomputed, [B][128])
+//   loc[f]  = conv1d(cumulative, k=31)[t]   (32 filters)
+//   u[t]    = v . tanh(pq + proj[b,t] + L loc) * (chars[b,t] != 0)
+//   scores  = softmax_t(u); cumulative += scores; ctx = scores @ seq[b]
+constexpr int ATT_D = 128, ATT_F = 32, ATT_K = 31;
+
+__global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__ pq, const float* __restrict__ proj,
+                                                       const float* __restrict__ seq, int seq_dim,
+                                                       const int32_t* __restrict__ chars, float* cum,
+                                                       const float* __restrict__ conv_w, const float* __restrict__ conv_b,
+                                                       const float* __restrict__ Lw, const float* __restrict__ vw,
+                                                       float* __restrict__ scores_out, int scores_ld, float* ctx, int Tc) {
+  extern __shared__ float sm[];
+  float* s_cw = sm;                         // [32][31]
+  float* s_L = s_cw + ATT_F * ATT_K;        // [128][32]
+  float* s_v = s_L + ATT_D * ATT_F;         // [128]
+  float* s_pq = s_v + ATT_D;                // [128]
+  float* s_cb = s_pq + ATT_D;               // [32]
+  float* s_cum = s_cb + ATT_F;              // [Tc + 30] zero padded
+  float* s_u = s_cum + Tc + 2 * 15;         // [Tc]
+  float* s_red = s_u + Tc;                  // [32]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < ATT_F * ATT_K; i += blockDim.x) s_cw[i] = conv_w[i];
+  for (int i = tid; i < ATT_D * ATT_F; i += blockDim.x) s_L[i] = Lw[i];
+  for (int i = tid; i < ATT_D; i += blockDim.x) {
+    s_v[i] = vw[i];
+    s_pq[i] = pq[(size_t)b * ATT_D + i];
+  }
+  for (int i = tid; i < ATT_F; i += blockDim.x) s_cb[i] = conv_b[i];
+  for (int i = tid; i < Tc + 30; i += blockDim.x) {
+    const int t = i - 15;
+    s_cum[i] = (t >= 0 && t < Tc) ? cum[(size_t)b * Tc + t] : 0.f;
+  }
+  __syncthreads();
+  for (int t = tid; t < Tc; t += blockDim.x) {
+    float loc[ATT_F];
+#pragma unroll 4
+    for (int f = 0; f < ATT_F; ++f) {
+      float a = 0.f;
+      for (int j = 0; j < ATT_K; ++j) a = fmaf(s_cw[f * ATT_K + j], s_cum[t + j], a);
+      loc[f] = a + s_cb[f];
+    }
+    const float* pr = proj + ((size_t)b * Tc + t) * ATT_D;
+    float u = 0.f;
+    for (int d = 0; d < ATT_D; ++d) {
+      float pl = 0.f;
+#pragma unroll
+      for (int f = 0; f < ATT_F; ++f) pl = fmaf(s_L[d * ATT_F + f], loc[f], pl);
+      u = fmaf(s_v[d], tanhf(s_pq[d] + pr[d] + pl), u);
+    }
+    s_u[t] = chars[(size_t)b * Tc + t] != 0 ? u : 0.f;  // u * (chars != 0): padded positions score exp(0)
+  }
+  __syncthreads();
+  // softmax over t
+  float mx = -3.0e38f;
+  for (int t = tid; t < Tc; t += blockDim.x) mx = fmaxf(mx, s_u[t]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+  __syncthreads();
+  mx = s_red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, s_red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int t = tid; t < Tc; t += blockDim.x) {
+    const float e = expf(s_u[t] - mx);
+    s_u[t] = e;
+    sum += e;
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += s_red[w];
+  for (int t = tid; t < Tc; t += blockDim.x) {
+    const float sc = s_u[t] / sum;
+    s_u[t] = sc;
+    scores_out[(size_t)b * scores_ld + t] = sc;
+    cum[(size_t)b * Tc + t] = s_cum[t + 15] + sc;
+  }
+  __syncthreads();
+  for (int f = tid; f < seq_dim; f += blockDim.x) {
+    float a = 0.f;
+    const float* sp = seq + (size_t)b * Tc * seq_dim + f;
+    for (int t = 0; t < Tc; ++t) a = fmaf(s_u[t], sp[(size_t)t * seq_dim], a);
+    ctx[(size_t)b * seq_dim + f] = a;
+  }
+}
+
+// global style token attention for one batch row: q [512] -> 8 heads over `ntok` tokens (K,V [ntok][512])
+__global__ void gst_attention_kernel(const float* __restrict__ q, const float* __restrict__ Kt, const float* __restrict__ Vt,
+                                     int ntok, float* __restrict__ out, int E, int heads, float inv_sqrt_dk) {
+  __shared__ float sc[8][16];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int hd = E / heads;
+  if (tid < heads * ntok) {
+    const int h = tid / ntok, k = tid - h * ntok;
+    float a = 0.f;
+    for (int d = 0; d < hd; ++d) a = fmaf(q[(size_t)b * E + h * hd + d], Kt[(size_t)k * E + h * hd + d], a);
+    sc[h][k] = a * inv_sqrt_dk;
+  }
+  __syncthreads();
+  if (tid < heads) {
+    float mx = -3.0e38f;
+    for (int k = 0; k < ntok; ++k) mx = fmaxf(mx, sc[tid][k]);
+    float s = 0.f;
+    for (int k = 0; k < ntok; ++k) {
+      sc[tid][k] = expf(sc[tid][k] - mx);
+      s += sc[tid][k];
+    }
+    for (int k = 0; k < ntok; ++k) sc[tid][k] /= s;
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += blockDim.x) {
+    const int h = e / hd;
+    float a = 0.f;
+    for (int k = 0; k < ntok; ++k) a = fmaf(sc[h][k], Vt[(size_t)k * E + e], a);
+    out[(size_t)b * E + e] = a;
+  }
+}
+
+__global__ void bn_fold_kernel(const float* g, const float* b, const float* mean, const float* var, float* scale,
+                               float* shift, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = g[i] * (1.0f / sqrtf(var[i] + 1e-5f));
+  scale[i] = s;
+  shift[i] = b[i] - mean[i] * s;
+}
+
+__global__ void tanh_kernel(const float* x, float* y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = tanhf(x[i]);
+}
+
+// compact mel projection rows: dst[(j*80 + m)][:] = W[(m*max_r + j)][:]
+__global__ void pack_melproj_kernel(const float* __restrict__ W, float* __restrict__ dst, int n_mels, int max_r, int r,
+                                    int K) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)r * n_mels * K) return;
+  const int k = (int)(i % K);
+  const int row = (int)(i / K);
+  const int j = row / n_mels, m = row - j * n_mels;
+  dst[i] = W[((size_t)m * max_r + j) * K + k];
+}
+
+__global__ void fill_masks_kernel(uint8_t* m, size_t n, uint64_t seed, uint32_t stream_id) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t o[4];
+  mb_philox4x32((uint32_t)(i >> 2), (uint32_t)(i >> 34), stream_id, 0x7461636fu, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  m[i] = (uint8_t)((o[i & 3] >> 16) & 1u);  // Bernoulli(0.5) keep flag
+}
+
+__global__ void stop_flag_kernel(const float* stopv, int B, float min_stop_token, int t, int* flag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    bool all = true;
+    for (int b = 0; b < B; ++b) all = all && (stopv[b] * 10.f > min_stop_token);
+    *flag = (all && t > 10) ? 1 : 0;
+  }
+}
+
+// [B][T][C] (first `frames` of `steps` rows) -> [B][C][frames]
+__global__ void to_ncl_kernel(const float* __restrict__ x, int steps, float* __restrict__ y, int B, int C, int frames) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * C * frames) return;
+  const int t = (int)(i % frames);
+  const int c = (int)((i / frames) % C);
+  const int b = (int)(i / ((size_t)frames * C));
+  y[i] = x[((size_t)b * steps + t) * C + c];
+}
+
+}  // namespace
+}  // namespace taco
+}  // namespace mb
+
+// =================================================================================================
+using namespace mb;
+using namespace mb::taco;
+
+struct mb_tacotron {
+  mb_tacotron_config cfg{};
+  struct Slot {
+    size_t off;
+    size_t n;
+    bool set;
+  };
+  std::map<std::string, Slot> slots;
+  size_t total = 0;
+  float* arena = nullptr;
+  bool finalized = false;
+  int packed_r = 0;
+};
+
+namespace {
+
+void slot(mb_tacotron* h, const std::string& name, size_t n) {
+  h->slots[name] = {h->total, n, false};
+  h->total += align_up(n, 64);
+}
+
+float* P(const mb_tacotron* h, const std::string& name) {
+  auto it = h->slots.find(name);
+  return it == h->slots.end() ? nullptr : h->arena + it->second.off;
+}
+
+void cbhg_slots(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p0, int p1, int nh) {
+  auto bnconv = [&](const std::string& n, int ci, int co, int k) {
+    slot(h, n + ".conv.weight", (size_t)co * ci * k);
+    for (const char* leaf : {".bnorm.weight", ".bnorm.bias", ".bnorm.running_mean", ".bnorm.running_var"}) slot(h, n + leaf, co);
+    slot(h, n + ".bn_scale", co);  // derived at finalize
+    slot(h, n + ".bn_shift", co);
+  };
+  for (int i = 0; i < K; ++i) bnconv(p + ".conv1d_bank." + std::to_string(i), cin, ch, i + 1);
+  bnconv(p + ".conv_project1", K * ch, p0, 3);
+  bnconv(p + ".conv_project2", p0, p1, 3);
+  if (p1 != ch) slot(h, p + ".pre_highway.weight", (size_t)ch * p1);
+  for (int i = 0; i < nh; ++i) {
+    const std::string q = p + ".highways." + std::to_string(i);
+    slot(h, q + ".W1.weight", (size_t)ch * ch);
+    slot(h, q + ".W1.bias", ch);
+    slot(h, q + ".W2.weight", (size_t)ch * ch);
+    slot(h, q + ".W2.bias", ch);
+    slot(h, q + ".W12", (size_t)2 * ch * ch);  // derived: [W1; W2] stacked
+    slot(h, q + ".b12", (size_t)2 * ch);
+  }
+  for (const char* sfx : {"", "_reverse"}) {
+    slot(h, p + ".rnn.weight_ih_l0" + sfx, (size_t)3 * (ch / 2) * ch);
+    slot(h, p + ".rnn.weight_hh_l0" + sfx, (size_t)3 * (ch / 2) * (ch / 2));
+    slot(h, p + ".rnn.bias_ih_l0" + sfx, (size_t)3 * (ch / 2));
+    slot(h, p + ".rnn.bias_hh_l0" + sfx, (size_t)3 * (ch / 2));
+  }
+}
+
+struct Ws {
+  // encoder
+  size_t ids, emb, m_enc, p1, x0, bank, pool, pj1, y, hw12, gi_f, gi_b, gh, hst, seq, proj, style_q, style;
+  // decoder
+  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, stopv, flags, dmask;
+  // outputs / postnet
+  size_t mel_all, scores_all, pbank, ppool, ppj1, ppj2, py, phw12, pgi_f, pgi_b, pgh, phst, pout, lin;
+  size_t total;
+};
+
+Ws ws_layout(const mb_tacotron_config& c, int B, int Tc, int steps, int r) {
+  Ws L{};
+  size_t o = 0;
+  auto take = [&](size_t n) {
+    size_t q = o;
+    o += align_up(n, 64);
+    return q;
+  };
+  const size_t Me = (size_t)B * Tc, Mp = (size_t)B * steps;
+  const int E = c.encoder_dims, PD = c.postnet_dims, proj_dims = E + c.speaker_embedding_size + c.gst_E;
+  L.ids = take(Me);
+  L.emb = take(Me * c.embed_dims);
+  L.m_enc = take((2 * Me * E + 3) / 4 + 64);  // uint8 masks
+  L.p1 = take(Me * E);
+  L.x0 = take(Me * E);
+  L.bank = take(Me * c.encoder_K * E);
+  L.pool = take(Me * c.encoder_K * E);
+  L.pj1 = take(Me * E);
+  L.y = take(Me * E);
+  L.hw12 = take(Me * 2 * E);
+  L.gi_f = take(Me * 3 * (E / 2));
+  L.gi_b = take(Me * 3 * (E / 2));
+  L.gh = take((size_t)2 * B * 3 * (PD / 2));
+  L.hst = take((size_t)2 * B * (PD / 2));
+  L.seq = take(Me * proj_dims);
+  L.proj = take(Me * c.decoder_dims);
+  L.style_q = take((size_t)B * c.gst_E);
+  L.style = take((size_t)B * c.gst_E);
+  L.attn_h = take((size_t)B * c.decoder_dims);
+  L.h1 = take((size_t)B * c.lstm_dims);
+  L.c1 = take((size_t)B * c.lstm_dims);
+  L.h2 = take((size_t)B * c.lstm_dims);
+  L.c2 = take((size_t)B * c.lstm_dims);
+  L.ctx = take((size_t)B * proj_dims);
+  L.cum = take(Me);
+  L.dp1 = take((size_t)B * 2 * c.decoder_dims);
+  L.dp2 = take((size_t)B * 2 * c.decoder_dims);
+  L.dgi = take((size_t)B * 3 * c.decoder_dims);
+  L.dgh = take((size_t)B * 3 * c.decoder_dims);
+  L.pq = take((size_t)B * c.decoder_dims);
+  L.x = take((size_t)B * c.lstm_dims);
+  L.gates = take((size_t)B * 4 * c.lstm_dims);
+  L.stopv = take(B);
+  const int nst = (steps + r - 1) / r;
+  L.flags = take(nst);
+  L.dmask = take(((size_t)2 * B * 2 * c.decoder_dims + 3) / 4 + 64);
+  L.mel_all = take(Mp * c.n_mels + (size_t)r * c.n_mels);
+  L.scores_all = take((size_t)B * nst * Tc);
+  L.pbank = take(Mp * c.postnet_K * PD);
+  L.ppool = take(Mp * c.postnet_K * PD);
+  L.ppj1 = take(Mp * PD);
+  L.ppj2 = take(Mp * c.n_mels);
+  L.py = take(Mp * PD);
+  L.phw12 = take(Mp * 2 * PD);
+  L.pgi_f = take(Mp * 3 * (PD / 2));
+  L.pgi_b = take(Mp * 3 * (PD / 2));
+  L.pgh = take((size_t)2 * B * 3 * (PD / 2));
+  L.phst = take((size_t)2 * B * (PD / 2));
+  L.pout = take(Mp * PD);
+  L.lin = take(Mp * c.n_mels);
+  L.total = o;
+  return L;
+}
+
+#define TK(expr)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) return fail(MB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    count_launch();                                                                                       \
+  } while (0)
+
+GemmArgs gemm1(const float* x, int K, int ld, const float* W, int ldw, const float* bias, int M, int N, float* Y, int ldy,
+               int act = ACT_NONE) {
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nseg = 1;
+  a.seg[0] = {x, K, ld, 0, 0, 1};
+  a.W = W;
+  a.ldw = ldw;
+  a.bias = bias;
+  a.M = M;
+  a.N = N;
+  a.T = 1;
+  a.act = act;
+  a.Y = Y;
+  a.ldy = ldy;
+  return a;
+}
+
+// CBHG (sublayer/cbhg.py:42-79) on x [B*T][cin] channels-last -> out [B*T][ch] written at out (ld ldout)
+int run_cbhg(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p0, int p1, int nh, const float* x, int B,
+             int T, float* bank, float* pool, float* pj1, float* y, float* hw12, float* gi_f, float* gi_b, float* gh,
+             float* hst, float* out, int ldout, cudaStream_t st) {
+  const int M = B * T;
+  // convolution bank: k = 1..K, "same" padding k//2 cropped to T, ReLU then BatchNorm
+  for (int i = 0; i < K; ++i) {
+    const int k = i + 1;
+    const std::string n = p + ".conv1d_bank." + std::to_string(i);
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nseg = k;
+    for (int tap = 0; tap < k; ++tap) a.seg[tap] = {x, cin, cin, tap - k / 2, tap, k};
+    a.W = P(h, n + ".conv.weight");
+    a.ldw = cin * k;
+    a.M = M;
+    a.N = ch;
+    a.T = T;
+    a.act = ACT_RELU;
+    a.bn_scale = P(h, n + ".bn_scale");
+    a.bn_shift = P(h, n + ".bn_shift");
+    a.Y = bank + (size_t)i * ch;
+    a.ldy = K * ch;
+    TK(launch_gemm(a, st));
+  }
+  TK(launch_maxpool2(bank, pool, B, T, K * ch, st));
+  {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nseg = 3;
+    for (int tap = 0; tap < 3; ++tap) a.seg[tap] = {pool, K * ch, K * ch, tap - 1, tap, 3};
+    a.W = P(h, p + ".conv_project1.conv.weight");
+    a.ldw = K * ch * 3;
+    a.M = M;
+    a.N = p0;
+    a.T = T;
+    a.act = ACT_RELU;
+    a.bn_scale = P(h, p + ".conv_project1.bn_scale");
+    a.bn_shift = P(h, p + ".conv_project1.bn_shift");
+    a.Y = pj1;
+    a.ldy = p0;
+    TK(launch_gemm(a, st));
+  }
+  float* cur = y;  // [M][ch] highway stream
+  {
+    // conv_project2 (no ReLU) + BN + residual x
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nseg = 3;
+    for (int tap = 0; tap < 3; ++tap) a.seg[tap] = {pj1, p0, p0, tap - 1, tap, 3};
+    a.W = P(h, p + ".conv_project2.conv.weight");
+    a.ldw = p0 * 3;
+    a.M = M;
+    a.N = p1;
+    a.T = T;
+    a.act = ACT_NONE;
+    a.bn_scale = P(h, p + ".conv_project2.bn_scale");
+    a.bn_shift = P(h, p + ".conv_project2.bn_shift");
+    a.res = x;
+    a.ldres = cin;
+    if (p1 != ch) {
+      a.Y = hw12;  // scratch: [M][p1] before the pre_highway projection
+      a.ldy = p1;
+      TK(launch_gemm(a, st));
+      GemmArgs b = gemm1(hw12, p1, p1, P(h, p + ".pre_highway.weight"), p1, nullptr, M, ch, cur, ch);
+      TK(launch_gemm(b, st));
+    } else {
+      a.Y = cur;
+      a.ldy = ch;
+      TK(launch_gemm(a, st));
+    }
+  }
+  for (int i = 0; i < nh; ++i) {
+    const std::string q = p + ".highways." + std::to_string(i);
+    GemmArgs a = gemm1(cur, ch, ch, P(h, q + ".W12"), ch, P(h, q + ".b12"), M, 2 * ch, hw12, 2 * ch);
+    TK(launch_gemm(a, st));
+    TK(launch_highway(hw12, cur, M, ch, st));
+  }
+  // bidirectional GRU: input projections for all t, then the two recurrences
+  const int H = ch / 2;
+  {
+    GemmArgs a = gemm1(cur, ch, ch, P(h, p + ".rnn.weight_ih_l0"), ch, P(h, p + ".rnn.bias_ih_l0"), M, 3 * H, gi_f, 3 * H);
+    TK(launch_gemm(a, st));
+    GemmArgs b = gemm1(cur, ch, ch, P(h, p + ".rnn.weight_ih_l0_reverse"), ch, P(h, p + ".rnn.bias_ih_l0_reverse"), M, 3 * H,
+                       gi_b, 3 * H);
+    TK(launch_gemm(b, st));
+  }
+  MB_CUDA_CHECK(cudaMemsetAsync(hst, 0, sizeof(float) * 2 * B * H, st));
+  float* hf = hst;
+  float* hb = hst + (size_t)B * H;
+  float* ghf = gh;
+  float* ghb = gh + (size_t)B * 3 * H;
+  for (int s = 0; s < T; ++s) {
+    {  // forward direction, time s
+      GemmArgs a = gemm1(hf, H, H, P(h, p + ".rnn.weight_hh_l0"), H, P(h, p + ".rnn.bias_hh_l0"), B, 3 * H, ghf, 3 * H);
+      TK(launch_gemm(a, st));
+      TK(launch_gru_cell(gi_f + (size_t)s * 3 * H, T * 3 * H, ghf, hf, H, out + (size_t)s * ldout, T * ldout, B, H, st));
+    }
+    {  // reverse direction, time T-1-s
+      const int t = T - 1 - s;
+      GemmArgs a = gemm1(hb, H, H, P(h, p + ".rnn.weight_hh_l0_reverse"), H, P(h, p + ".rnn.bias_hh_l0_reverse"), B, 3 * H,
+                         ghb, 3 * H);
+      TK(launch_gemm(a, st));
+      TK(launch_gru_cell(gi_b + (size_t)t * 3 * H, T * 3 * H, ghb, hb, H, out + (size_t)t * ldout + H, T * ldout, B, H, st));
+    }
+  }
+  return MB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb_tacotron_create(const mb_tacotron_config* cfg, mb_tacotron** out) {
+  if (!cfg || !out) return fail(MB_ERR_INVALID, "mb_tacotron_create: null argument");
+  const mb_tacotron_config& c = *cfg;
+  if (c.decoder_dims != ATT_D || c.encoder_dims % 2 || c.postnet_dims % 2 || c.gst_heads > 8 || c.gst_tokens > 16 ||
+      c.encoder_K > kMaxSeg || c.postnet_K > kMaxSeg)
+    return fail(MB_ERR_INVALID, "mb_tacotron_create: unsupported hyper-parameters");
+  mb_tacotron* h = new mb_tacotron();
+  h->cfg = c;
+  const int E = c.encoder_dims, D = c.decoder_dims, proj_dims = E + c.speaker_embedding_size + c.gst_E;
+  slot(h, "encoder.embedding.weight", (size_t)c.num_chars * c.embed_dims);
+  slot(h, "encoder.pre_net.fc1.weight", (size_t)E * c.embed_dims);
+  slot(h, "encoder.pre_net.fc1.bias", E);
+  slot(h, "encoder.pre_net.fc2.weight", (size_t)E * E);
+  slot(h, "encoder.pre_net.fc2.bias", E);
+  cbhg_slots(h, "encoder.cbhg", c.encoder_K, E, E, E, E, c.num_highways);
+  slot(h, "encoder_proj.weight", (size_t)D * proj_dims);
+  slot(h, "gst.const_enc", c.gst_E / 2);  // ReferenceEncoder(zeros): input independent, folded by the host
+  slot(h, "gst.stl.embed", (size_t)c.gst_tokens * (c.gst_E / c.gst_heads));
+  slot(h, "gst.stl.attention.W_query.weight", (size_t)c.gst_E * (c.gst_E / 2 + c.speaker_embedding_size));
+  slot(h, "gst.stl.attention.W_key.weight", (size_t)c.gst_E * (c.gst_E / c.gst_heads));
+  slot(h, "gst.stl.attention.W_value.weight", (size_t)c.gst_E * (c.gst_E / c.gst_heads));
+  slot(h, "gst.tanh_embed", (size_t)c.gst_tokens * (c.gst_E / c.gst_heads));  // derived
+  slot(h, "gst.keys", (size_t)c.gst_tokens * c.gst_E);
+  slot(h, "gst.values", (size_t)c.gst_tokens * c.gst_E);
+  slot(h, "decoder.prenet.fc1.weight", (size_t)2 * D * c.n_mels);
+  slot(h, "decoder.prenet.fc1.bias", 2 * D);
+  slot(h, "decoder.prenet.fc2.weight", (size_t)2 * D * 2 * D);
+  slot(h, "decoder.prenet.fc2.bias", 2 * D);
+  slot(h, "decoder.attn_net.conv.weight", ATT_F * ATT_K);
+  slot(h, "decoder.attn_net.conv.bias", ATT_F);
+  slot(h, "decoder.attn_net.L.weight", ATT_D * ATT_F);
+  slot(h, "decoder.attn_net.W.weight", ATT_D * ATT_D);
+  slot(h, "decoder.attn_net.W.bias", ATT_D);
+  slot(h, "decoder.attn_net.v.weight", ATT_D);
+  slot(h, "decoder.attn_rnn.weight_ih", (size_t)3 * D * (proj_dims + 2 * D));
+  slot(h, "decoder.attn_rnn.weight_hh", (size_t)3 * D * D);
+  slot(h, "decoder.attn_rnn.bias_ih", 3 * D);
+  slot(h, "decoder.attn_rnn.bias_hh", 3 * D);
+  slot(h, "decoder.rnn_input.weight", (size_t)c.lstm_dims * (proj_dims + D));
+  slot(h, "decoder.rnn_input.bias", c.lstm_dims);
+  for (const char* n : {"decoder.res_rnn1", "decoder.res_rnn2"}) {
+    slot(h, std::string(n) + ".weight_ih", (size_t)4 * c.lstm_dims * c.lstm_dims);
+    slot(h, std::string(n) + ".weight_hh", (size_t)4 * c.lstm_dims * c.lstm_dims);
+    slot(h, std::string(n) + ".bias_ih", 4 * c.lstm_dims);
+    slot(h, std::string(n) + ".bias_hh", 4 * c.lstm_dims);
+    slot(h, std::string(n) + ".bias_sum", 4 * c.lstm_dims);  // derived: b_hh + b_ih
+  }
+  slot(h, "decoder.mel_proj.weight", (size_t)c.n_mels * c.max_r * c.lstm_dims);
+  slot(h, "decoder.mel_proj.packed", (size_t)c.n_mels * c.max_r * c.lstm_dims);  // derived for the current r
+  slot(h, "decoder.stop_proj.weight", (size_t)(proj_dims + c.lstm_dims));
+  slot(h, "decoder.stop_proj.bias", 1);
+  cbhg_slots(h, "postnet", c.postnet_K, c.n_mels, c.postnet_dims, c.postnet_dims, c.n_mels, c.num_highways);
+  slot(h, "post_proj.weight", (size_t)c.n_mels * c.postnet_dims);
+  *out = h;
+  return MB_OK;
+}
+
+void mb_tacotron_destroy(mb_tacotron* h) { delete h; }
+
+size_t mb_tacotron_arena_bytes(const mb_tacotron* h) { return h ? h->total * sizeof(float) : 0; }
+
+int mb_tacotron_set_arena(mb_tacotron* h, void* arena, size_t bytes) {
+  if (!h || !arena) return fail(MB_ERR_INVALID, "mb_tacotron_set_arena: null argument");
+  if (bytes < mb_tacotron_arena_bytes(h)) return fail(MB_ERR_WORKSPACE, "mb_tacotron_set_arena: arena too small");
+  if (((uintptr_t)arena & 255) != 0) return fail(MB_ERR_INVALID, "mb_tacotron_set_arena: arena must be 256-byte aligned");
+  h->arena = (float*)arena;
+  return MB_OK;
+}
+
+int mb_tacotron_set_weight(mb_tacotron* h, const char* name, const float* w, const int64_t* dims, int32_t ndim,
+                           void* stream) {
+  if (!h || !name || !w) return fail(MB_ERR_INVALID, "mb_tacotron_set_weight: null argument");
+  if (!h->arena) return fail(MB_ERR_STATE, "mb_tacotron_set_weight: call mb_tacotron_set_arena first");
+  auto it = h->slots.find(name);
+  if (it == h->slots.end()) return fail(MB_ERR_INVALID, "mb_tacotron_set_weight: unknown tensor '%s'", name);
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= (size_t)dims[i];
+  if (n != it->second.n)
+    return fail(MB_ERR_INVALID, "mb_tacotron_set_weight: %s has %zu elements, expected %zu", name, n, it->second.n);
+  MB_CUDA_CHECK(cudaMemcpyAsync(h->arena + it->second.off, w, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  it->second.set = true;
+  h->finalized = false;
+  return MB_OK;
+}
+
+int mb_tacotron_finalize(mb_tacotron* h, void* stream) {
+  if (!h) return fail(MB_ERR_INVALID, "mb_tacotron_finalize: null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mb_tacotron_config& c = h->cfg;
+  auto derived = [](const std::string& n) {
+    return n.find(".bn_scale") != std::string::npos || n.find(".bn_shift") != std::string::npos ||
+           n.find(".W12") != std::string::npos || n.find(".b12") != std::string::npos || n == "gst.tanh_embed" ||
+           n == "gst.keys" || n == "gst.values" || n.find(".bias_sum") != std::string::npos ||
+           n == "decoder.mel_proj.packed";
+  };
+  for (auto& kv : h->slots)
+    if (!kv.second.set && !derived(kv.first))
+      return fail(MB_ERR_STATE, "mb_tacotron_finalize: tensor %s was never set", kv.first.c_str());
+  // fold eval BatchNorm into scale/shift
+  for (auto& kv : h->slots) {
+    const std::string& n = kv.first;
+    const size_t pos = n.find(".bnorm.weight");
+    if (pos == std::string::npos) continue;
+    const std::string base = n.substr(0, pos);
+    const int co = (int)kv.second.n;
+    bn_fold_kernel<<<(co + 255) / 256, 256, 0, st>>>(P(h, base + ".bnorm.weight"), P(h, base + ".bnorm.bias"),
+                                                     P(h, base + ".bnorm.running_mean"), P(h, base + ".bnorm.running_var"),
+                                                     P(h, base + ".bn_scale"), P(h, base + ".bn_shift"), co);
+    MB_LAUNCH_CHECK("bn_fold_kernel");
+  }
+  // stacked highway weights [W1; W2]
+  for (auto& kv : h->slots) {
+    const std::string& n = kv.first;
+    const size_t pos = n.find(".W1.weight");
+    if (pos == std::string::npos) continue;
+    const std::string base = n.substr(0, pos);
+    const size_t nn = kv.second.n;
+    const size_t ch = h->slots[base + ".W1.bias"].n;
+    MB_CUDA_CHECK(cudaMemcpyAsync(P(h, base + ".W12"), P(h, base + ".W1.weight"), nn * 4, cudaMemcpyDeviceToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(P(h, base + ".W12") + nn, P(h, base + ".W2.weight"), nn * 4, cudaMemcpyDeviceToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(P(h, base + ".b12"), P(h, base + ".W1.bias"), ch * 4, cudaMemcpyDeviceToDevice, st));
+    MB_CUDA_CHECK(cudaMemcpyAsync(P(h, base + ".b12") + ch, P(h, base + ".W2.bias"), ch * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  // GST constants: keys/values of the tanh'd tokens
+  {
+    const int dk = c.gst_E / c.gst_heads, nt = c.gst_tokens;
+    tanh_kernel<<<(nt * dk + 255) / 256, 256, 0, st>>>(P(h, "gst.stl.embed"), P(h, "gst.tanh_embed"), nt * dk);
+    MB_LAUNCH_CHECK("tanh_kernel");
+    GemmArgs a = gemm1(P(h, "gst.tanh_embed"), dk, dk, P(h, "gst.stl.attention.W_key.weight"), dk, nullptr, nt, c.gst_E,
+                       P(h, "gst.keys"), c.gst_E);
+    TK(launch_gemm(a, st));
+    GemmArgs b = gemm1(P(h, "gst.tanh_embed"), dk, dk, P(h, "gst.stl.attention.W_value.weight"), dk, nullptr, nt, c.gst_E,
+                       P(h, "gst.values"), c.gst_E);
+    TK(launch_gemm(b, st));
+  }
+  h->packed_r = 0;
+  h->finalized = true;
+  return MB_OK;
+}
+
+size_t mb_tacotron_workspace_bytes(const mb_tacotron* h, int32_t B, int32_t Tc, int32_t steps, int32_t r) {
+  if (!h || B <= 0 || Tc <= 0 || steps <= 0 || r <= 0) return 0;
+  const int nst = (steps + r - 1) / r;
+  return ws_layout(h->cfg, B, Tc, nst * r, r).total * sizeof(float) + 256;
+}
+
+int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk, int32_t B, int32_t Tc, int32_t steps,
+                         int32_t r, int32_t style_idx, float min_stop_token, const uint8_t* enc_masks,
+                         const uint8_t* dec_masks, uint64_t seed, float* mel_out, float* linear_out, float* attn_out,
+                         int32_t* frames_out_host, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !chars || !spk || !mel_out || !linear_out || !frames_out_host || !workspace)
+    return fail(MB_ERR_INVALID, "mb_tacotron_generate: null argument");
+  if (!h->finalized) return fail(MB_ERR_STATE, "mb_tacotron_generate: weights not finalized");
+  const mb_tacotron_config& c = h->cfg;
+  if (B <= 0 || Tc <= 0 || steps <= 0 || r <= 0 || r > c.max_r) return fail(MB_ERR_INVALID, "mb_tacotron_generate: bad shape");
+  const int nst = (steps + r - 1) / r;
+  const int steps_alloc = nst * r;  // the reference emits r frames per decoder step (tacotron.py:264-272)
+  const Ws L = ws_layout(c, B, Tc, steps_alloc, r);
+  if (workspace_bytes < L.total * sizeof(float) + 256) return fail(MB_ERR_WORKSPACE, "mb_tacotron_generate: workspace too small");
+  float* ws = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int E = c.encoder_dims, D = c.decoder_dims, LD = c.lstm_dims, PD = c.postnet_dims, NM = c.n_mels;
+  const int SE = c.speaker_embedding_size, proj_dims = E + SE + c.gst_E;
+  const int Me = B * Tc;
+
+  if (h->packed_r != r) {
+    const size_t n = (size_t)r * NM * LD;
+    pack_melproj_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P(h, "decoder.mel_proj.weight"),
+                                                                     P(h, "decoder.mel_proj.packed"), NM, c.max_r, r, LD);
+    MB_LAUNCH_CHECK("pack_melproj_kernel");
+    h->packed_r = r;
+  }
+
+  // ------------------------------------------------------------------ encoder (tacotron.py:31-44)
+  TK(launch_embedding(chars, P(h, "encoder.embedding.weight"), ws + L.emb, Me, c.embed_dims, st));
+  uint8_t* em = reinterpret_cast<uint8_t*>(ws + L.m_enc);
+  const size_t enc_mask_n = (size_t)Me * E;
+  if (enc_masks) {
+    MB_CUDA_CHECK(cudaMemcpyAsync(em, enc_masks, 2 * enc_mask_n, cudaMemcpyDeviceToDevice, st));
+  } else {
+    fill_masks_kernel<<<(unsigned)((2 * enc_mask_n + 255) / 256), 256, 0, st>>>(em, 2 * enc_mask_n, seed, 0xffffffffu);
+    MB_LAUNCH_CHECK("fill_masks_kernel");
+  }
+  {
+    GemmArgs a = gemm1(ws + L.emb, c.embed_dims, c.embed_dims, P(h, "encoder.pre_net.fc1.weight"), c.embed_dims,
+                       P(h, "encoder.pre_net.fc1.bias"), Me, E, ws + L.p1, E, ACT_RELU);
+    a.mask = em;
+    TK(launch_gemm(a, st));
+    GemmArgs b = gemm1(ws + L.p1, E, E, P(h, "encoder.pre_net.fc2.weight"), E, P(h, "encoder.pre_net.fc2.bias"), Me, E,
+                       ws + L.x0, E, ACT_RELU);
+    b.mask = em + enc_mask_n;
+    TK(launch_gemm(b, st));
+  }
+  float* seq = ws + L.seq;
+  int rc = run_cbhg(h, "encoder.cbhg", c.encoder_K, E, E, E, E, c.num_highways, ws + L.x0, B, Tc, ws + L.bank, ws + L.pool,
+                    ws + L.pj1, ws + L.y, ws + L.hw12, ws + L.gi_f, ws + L.gi_b, ws + L.gh, ws + L.hst, seq, proj_dims, st);
+  if (rc != MB_OK) return rc;
+  // speaker embedding per char (tacotron.py:236), style embedding (tacotron.py:238-253)
+  TK(launch_copy_cols(spk, SE, Tc, seq, proj_dims, E, Me, SE, st));
+  if (style_idx >= 0 && style_idx < c.gst_tokens) {
+    // zero query over a single token: softmax over one key == 1  ->  style = W_value tanh(embed[idx])
+    TK(launch_copy_cols(P(h, "gst.values") + (size_t)style_idx * c.gst_E, c.gst_E, Me, seq, proj_dims, E + SE, Me, c.gst_E, st));
+  } else {
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nseg = 2;
+    a.seg[0] = {P(h, "gst.const_enc"), c.gst_E / 2, 0, 0, 0, 1};  // ld 0: the same row for every batch element
+    a.seg[1] = {spk, SE, SE, 0, c.gst_E / 2, 1};
+    a.W = P(h, "gst.stl.attention.W_query.weight");
+    a.ldw = c.gst_E / 2 + SE;
+    a.M = B;
+    a.N = c.gst_E;
+    a.T = 1;
+    a.Y = ws + L.style_q;
+    a.ldy = c.gst_E;
+    TK(launch_gemm(a, st));
+    const int dk = c.gst_E / c.gst_heads;
+    gst_attention_kernel<<<B, 256, 0, st>>>(ws + L.style_q, P(h, "gst.keys"), P(h, "gst.values"), c.gst_tokens,
+                                            ws + L.style, c.gst_E, c.gst_heads, 1.0f / sqrtf((float)dk));
+    MB_LAUNCH_CHECK("gst_attention_kernel");
+    TK(launch_copy_cols(ws + L.style, c.gst_E, Tc, seq, proj_dims, E + SE, Me, c.gst_E, st));
+  }
+  {
+    GemmArgs a = gemm1(seq, proj_dims, proj_dims, P(h, "encoder_proj.weight"), proj_dims, nullptr, Me, D, ws + L.proj, D);
+    TK(launch_gemm(a, st));
+  }
+
+  // ------------------------------------------------------------------ decoder loop (tacotron.py:264-275)
+  MB_CUDA_CHECK(cudaMemsetAsync(ws + L.attn_h, 0, sizeof(float) * (L.dp1 - L.attn_h), st));  // states, ctx, cum
+  float* mel_all = ws + L.mel_all;
+  MB_CUDA_CHECK(cudaMemsetAsync(mel_all, 0, sizeof(float) * ((size_t)B * steps_alloc * NM + (size_t)r * NM), st));
+  int* flags = reinterpret_cast<int*>(ws + L.flags);
+  MB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * nst, st));
+  uint8_t* dm = reinterpret_cast<uint8_t*>(ws + L.dmask);
+  const size_t dmask_n = (size_t)B * 2 * D;
+  const size_t lsa_smem = sizeof(float) * (ATT_F * ATT_K + ATT_D * ATT_F + 2 * ATT_D + ATT_F + (Tc + 30) + Tc + 32);
+  if (lsa_smem > 48 * 1024) MB_CUDA_CHECK(cudaFuncSetAttribute(lsa_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsa_smem));
+  int done_step = -1;
+  std::vector<int> hflags(nst, 0);
+  int checked = 0;
+  for (int si = 0; si < nst; ++si) {
+    const int t = si * r;
+    // PreNet on the last frame of the previous step (go frame = zeros)
+    const float* prenet_in = (si == 0) ? mel_all + (size_t)B * steps_alloc * NM  // zero tail row block
+                                       : mel_all + (size_t)(t - 1) * NM;
+    const int prenet_ld = (si == 0) ? 0 : steps_alloc * NM;
+    const uint8_t* m1;
+    const uint8_t* m2;
+    if (dec_masks) {
+      m1 = dec_masks + (size_t)si * 2 * dmask_n;
+      m2 = m1 + dmask_n;
+    } else {
+      fill_masks_kernel<<<(unsigned)((2 * dmask_n + 255) / 256), 256, 0, st>>>(dm, 2 * dmask_n, seed, (uint32_t)si);
+      MB_LAUNCH_CHECK("fill_masks_kernel");
+      m1 = dm;
+      m2 = dm + dmask_n;
+    }
+    {
+      GemmArgs a = gemm1(prenet_in, NM, prenet_ld, P(h, "decoder.prenet.fc1.weight"), NM, P(h, "decoder.prenet.fc1.bias"), B,
+                         2 * D, ws + L.dp1, 2 * D, ACT_RELU);
+      a.mask = m1;
+      TK(launch_gemm(a, st));
+      GemmArgs b = gemm1(ws + L.dp1, 2 * D, 2 * D, P(h, "decoder.prenet.fc2.weight"), 2 * D, P(h, "decoder.prenet.fc2.bias"),
+                         B, 2 * D, ws + L.dp2, 2 * D, ACT_RELU);
+      b.mask = m2;
+      TK(launch_gemm(b, st));
+    }
+    {  // attention GRU on [context, prenet]
+      GemmArgs a;
+      memset(&a, 0, sizeof(a));
+      a.nseg = 2;
+      a.seg[0] = {ws + L.ctx, proj_dims, proj_dims, 0, 0, 1};
+      a.seg[1] = {ws + L.dp2, 2 * D, 2 * D, 0, proj_dims, 1};
+      a.W = P(h, "decoder.attn_rnn.weight_ih");
+      a.ldw = proj_dims + 2 * D;
+      a.bias = P(h, "decoder.attn_rnn.bias_ih");
+      a.M = B;
+      a.N = 3 * D;
+      a.T = 1;
+      a.Y = ws + L.dgi;
+      a.ldy = 3 * D;
+      TK(launch_gemm(a, st));
+      GemmArgs b = gemm1(ws + L.attn_h, D, D, P(h, "decoder.attn_rnn.weight_hh"), D, P(h, "decoder.attn_rnn.bias_hh"), B, 3 * D,
+                         ws + L.dgh, 3 * D);
+      TK(launch_gemm(b, st));
+      TK(launch_gru_cell(ws + L.dgi, 3 * D, ws + L.dgh, ws + L.attn_h, D, nullptr, 0, B, D, st));
+    }
+    {  // location sensitive attention + context
+      GemmArgs a = gemm1(ws + L.attn_h, D, D, P(h, "decoder.attn_net.W.weight"), D, P(h, "decoder.attn_net.W.bias"), B, D,
+                         ws + L.pq, D);
+      TK(launch_gemm(a, st));
+      lsa_step_kernel<<<B, 256, lsa_smem, st>>>(ws + L.pq, ws + L.proj, seq, proj_dims, chars, ws + L.cum,
+                                                P(h, "decoder.attn_net.conv.weight"), P(h, "decoder.attn_net.conv.bias"),
+                                                P(h, "decoder.attn_net.L.weight"), P(h, "decoder.attn_net.v.weight"),
+                                                ws + L.scores_all + (size_t)si * Tc, nst * Tc, ws + L.ctx, Tc);
+      MB_LAUNCH_CHECK("lsa_step_kernel");
+    }
+    {  // rnn_input on [context, attn_hidden]
+      GemmArgs a;
+      memset(&a, 0, sizeof(a));
+      a.nseg = 2;
+      a.seg[0] = {ws + L.ctx, proj_dims, proj_dims, 0, 0, 1};
+      a.seg[1] = {ws + L.attn_h, D, D, 0, proj_dims, 1};
+      a.W = P(h, "decoder.rnn_input.weight");
+      a.ldw = proj_dims + D;
+      a.bias = P(h, "decoder.rnn_input.bias");
+      a.M = B;
+      a.N = LD;
+      a.T = 1;
+      a.Y = ws + L.x;
+      a.ldy = LD;
+      TK(launch_gemm(a, st));
+    }
+    for (int l = 0; l < 2; ++l) {  // residual LSTMs
+      const std::string n = l == 0 ? "decoder.res_rnn1" : "decoder.res_rnn2";
+      float* hh = ws + (l == 0 ? L.h1 : L.h2);
+      float* cc = ws + (l == 0 ? L.c1 : L.c2);
+      GemmArgs a;
+      memset(&a, 0, sizeof(a));
+      // gates = linear_hh(h) + linear_ih(x): two GEMMs chained through the residual input of the second
+      GemmArgs g1 = gemm1(hh, LD, LD, P(h, n + ".weight_hh"), LD, P(h, n + ".bias_hh"), B, 4 * LD, ws + L.gates, 4 * LD);
+      TK(launch_gemm(g1, st));
+      GemmArgs g2 = gemm1(ws + L.x, LD, LD, P(h, n + ".weight_ih"), LD, P(h, n + ".bias_ih"), B, 4 * LD, ws + L.gates, 4 * LD);
+      g2.res = ws + L.gates;
+      g2.ldres = 4 * LD;
+      TK(launch_gemm(g2, st));
+      TK(launch_lstm_cell(ws + L.gates, cc, hh, ws + L.x, B, LD, st));
+    }
+    {  // mel frames of this step, written straight into mel_all[b][t..t+r)[:]
+      GemmArgs a = gemm1(ws + L.x, LD, LD, P(h, "decoder.mel_proj.packed"), LD, nullptr, B, r * NM, mel_all + (size_t)t * NM,
+                         steps_alloc * NM);
+      TK(launch_gemm(a, st));
+      GemmArgs s;
+      memset(&s, 0, sizeof(s));
+      s.nseg = 2;
+      s.seg[0] = {ws + L.x, LD, LD, 0, 0, 1};
+      s.seg[1] = {ws + L.ctx, proj_dims, proj_dims, 0, LD, 1};
+      s.W = P(h, "decoder.stop_proj.weight");
+      s.ldw = LD + proj_dims;
+      s.bias = P(h, "decoder.stop_proj.bias");
+      s.M = B;
+      s.N = 1;
+      s.T = 1;
+      s.act = ACT_SIGMOID;
+      s.Y = ws + L.stopv;
+      s.ldy = 1;
+      TK(launch_gemm(s, st));
+      stop_flag_kernel<<<1, 32, 0, st>>>(ws + L.stopv, B, min_stop_token, t, flags + si);
+      MB_LAUNCH_CHECK("stop_flag_kernel");
+    }
+    // early-stop rule (tacotron.py:275) polled every 16 steps
+    if ((si % 16) == 15 || si == nst - 1) {
+      MB_CUDA_CHECK(cudaMemcpyAsync(hflags.data() + checked, flags + checked, sizeof(int) * (si + 1 - checked),
+                                    cudaMemcpyDeviceToHost, st));
+      MB_CUDA_CHECK(cudaStreamSynchronize(st));
+      for (int j = checked; j <= si && done_step < 0; ++j)
+        if (hflags[j]) done_step = j;
+      checked = si + 1;
+      if (done_step >= 0) break;
+    }
+  }
+  const int nsteps_done = (done_step >= 0 ? done_step : nst - 1) + 1;
+  int frames = nsteps_done * r;
+  if (frames > steps_alloc) frames = steps_alloc;
+  *frames_out_host = frames;
+
+  // ------------------------------------------------------------------ postnet (tacotron.py:281-283)
+  // the postnet sees exactly `frames` frames per utterance: compact mel_all to [B][frames][80] first
+  float* melc = ws + L.lin;  // reuse the output buffer as the compact input, then overwrite
+  if (frames != steps_alloc) {
+    for (int b = 0; b < B; ++b)
+      MB_CUDA_CHECK(cudaMemcpyAsync(ws + L.ppj2 + (size_t)b * frames * NM, mel_all + (size_t)b * steps_alloc * NM,
+                                    sizeof(float) * frames * NM, cudaMemcpyDeviceToDevice, st));
+    melc = ws + L.ppj2;
+    // ppj2 is also run_cbhg's conv_project2 scratch only when p1 != ch (it uses hw12), so it is free here
+  } else {
+    melc = mel_all;
+  }
+  rc = run_cbhg(h, "postnet", c.postnet_K, NM, PD, PD, NM, c.num_highways, melc, B, frames, ws + L.pbank, ws + L.ppool,
+                ws + L.ppj1, ws + L.py, ws + L.phw12, ws + L.pgi_f, ws + L.pgi_b, ws + L.pgh, ws + L.phst, ws + L.pout, PD, st);
+  if (rc != MB_OK) return rc;
+  {
+    GemmArgs a = gemm1(ws + L.pout, PD, PD, P(h, "post_proj.weight"), PD, nullptr, B * frames, NM, ws + L.lin, NM);
+    TK(launch_gemm(a, st));
+  }
+  // outputs in the reference's layouts: mel [B][80][frames], linear [B][80][frames], attn [B][nsteps][Tc]
+  {
+    const size_t n = (size_t)B * NM * frames;
+    to_ncl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mel_all, steps_alloc, mel_out, B, NM, frames);
+    MB_LAUNCH_CHECK("to_ncl_kernel");
+    to_ncl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws + L.lin, frames, linear_out, B, NM, frames);
+    MB_LAUNCH_CHECK("to_ncl_kernel");
+    if (attn_out)
+      for (int b = 0; b < B; ++b)
+        MB_CUDA_CHECK(cudaMemcpyAsync(attn_out + (size_t)b * nsteps_done * Tc, ws + L.scores_all + (size_t)b * nst * Tc,
+                                      sizeof(float) * nsteps_done * Tc, cudaMemcpyDeviceToDevice, st));
+  }
+  return MB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// FP32 building blocks of the Tacotron path (csrc/tacotron.cu).  Activations are row-major
+// [rows][features] ("channels last"), so Linear layers, Conv1d over time (as shifted-row segments),
+// GRU/LSTM gate projections and the CBHG convolution bank are all ONE kernel shape:
+//
+//   Y[m][n] = epi( sum_j sum_kk  X_j[row_j(m)][kk] * W[n*ldw + w_off_j + kk*w_stride_j] )
+//
+// row_j(m) = m + shift_j inside the same length-T sequence (zero outside) - a tap of a "same" conv -
+// and epi = bias, activation, eval-BatchNorm affine (applied AFTER the ReLU like
+// common/batch_norm_conv.py:11-14), PreNet dropout mask, residual.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace mb {
+namespace taco {
+
+constexpr int kMaxSeg = 5;
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_TANH = 3 };
+
+struct Seg {
+  const float* x;   // [M][ld]
+  int K;            // features taken from this segment
+  int ld;           // row stride of x
+  int shift;        // time shift (conv tap) - 0 for plain Linear inputs
+  int w_off;        // first weight column of this segment
+  int w_stride;     // weight column stride (Conv1d weight [co][ci][k]: stride k)
+};
+
+struct GemmArgs {
+  Seg seg[kMaxSeg];
+  int nseg;
+  const float* W;
+  int ldw;
+  const float* bias;       // [N] or nullptr
+  int M, N, T;             // T: rows per sequence (shift bounds); T <= 1: no sequence structure
+  int act;
+  const float* bn_scale;   // [N] or nullptr: y = act(.) * scale + shift
+  const float* bn_shift;
+  const uint8_t* mask;     // [M][N] keep flags (PreNet dropout, p = 0.5 -> x2) or nullptr
+  const float* res;        // residual [M][ldres] or nullptr
+  int ldres;
+  float* Y;
+  int ldy;
+};
+
+cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st);
+
+// h' = GRU cell (ATen gru_cell): gi, gh [M][3H] pre-activations incl. biases; h in/out [M][ldh]
+cudaError_t launch_gru_cell(const float* gi, int ldgi, const float* gh, float* h, int ldh, float* out2, int ldout2,
+                            int M, int H, cudaStream_t st);
+// LSTM cell (ATen lstm_cell): g = gates [M][4H] (ih + hh + biases); c in/out; h out; xres: x += h (residual)
+cudaError_t launch_lstm_cell(const float* g, float* c, float* h, float* x, int M, int H, cudaStream_t st);
+// y = g*relu(x1) + (1-g)*y, g = sigmoid(x2); x12 = [M][2C] (x1 | x2)
+cudaError_t launch_highway(const float* x12, float* y, int M, int C, cudaStream_t st);
+// out[b][t][c] = max(x[b][t-1][c], x[b][t][c])   (MaxPool1d(2,1,1)[:T])
+cudaError_t launch_maxpool2(const float* x, float* y, int B, int T, int C, cudaStream_t st);
+// embedding rows
+cudaError_t launch_embedding(const int32_t* ids, const float* table, float* y, int M, int D, cudaStream_t st);
+// dst[m][off + j] = src[(m / rows_per_src)][j]  (broadcast a per-sequence vector along time) or row copy
+cudaError_t launch_copy_cols(const float* src, int ldsrc, int rows_per_src, float* dst, int lddst, int off, int M,
+                             int n, cudaStream_t st);
+
+}  // namespace taco
+}  // namespace mb

@@ -106,3 +106,31 @@ def test_generator_without_cuda_fails_loudly():
         g.cuda()
     with pytest.raises(_lib.MbError):
         g.to("cpu")
+
+
+def test_text_front_end_matches_reference_ids():
+    """symbols table (utils/symbols.py:18) and basic_cleaners text_to_sequence (utils/text.py:13-40)"""
+    from mockingbird_b200.synthesizer.utils.symbols import symbols
+    from mockingbird_b200.synthesizer.utils.text import text_to_sequence
+
+    assert len(symbols) == 75 and symbols[0] == "_" and symbols[1] == "~"
+    assert text_to_sequence("Hello  World 1", ["basic_cleaners"]) == [35, 32, 39, 39, 42, 74, 50, 42, 45, 39, 31, 74, 54, 1]
+    try:
+        import ref_harness as rh
+    except ImportError:
+        return
+    if rh.reference_available():
+        rh.install()
+        from models.synthesizer.utils.text import text_to_sequence as ref_tts
+
+        for t in ["ni3 hao3 shi4 jie4", "Mixed CASE,  spaces!", "~_skip~"]:
+            assert text_to_sequence(t, ["basic_cleaners"]) == ref_tts(t, ["basic_cleaners"])
+
+
+def test_tacotron_handle_and_missing_weight_errors():
+    from mockingbird_b200.synthesizer.models.tacotron import Tacotron
+
+    t = Tacotron(512, 75, 256, 128, 80, 80, 512, 5, 1024, 5, 4, 0.5, -3.4, 256)
+    assert _lib.lib().mb_tacotron_arena_bytes(t._handle) > 32_000_000 * 4
+    assert _lib.lib().mb_tacotron_workspace_bytes(t._handle, 2, 10, 20, 2) > 0
+    assert _lib.lib().mb_tacotron_finalize(t._handle, None) == 2  # weights never set
