@@ -1,0 +1,68 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: utterance sharding, weight-arena
+broadcast, host gather - the N>1 path of bench.py / the serving recipe in INTEGRATION.md."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mockingbird_b200 import distributed as mbd
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, lengths, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        arena = torch.arange(4096, dtype=torch.int64).to(torch.uint8) if rank == 0 else torch.zeros(4096, dtype=torch.uint8)
+        mbd.broadcast_weights([arena], src=0)
+        ok_arena = bool(torch.equal(arena, torch.arange(4096, dtype=torch.int64).to(torch.uint8)))
+        mine = mbd.shard_utterances(lengths, rank, world)
+        local = [("utt", i, lengths[i] * 200) for i in mine]  # stand-in for vocoded waveforms
+        gathered = mbd.gather_object_lists(local, dst=0)
+        if rank == 0:
+            shards = [mbd.shard_utterances(lengths, r, world) for r in range(world)]
+            merged = mbd.merge_sharded(gathered, shards, len(lengths))
+            q.put((ok_arena, merged, [len(s) for s in shards], [sum(lengths[i] for i in s) for s in shards]))
+        else:
+            q.put((ok_arena,))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_shard_broadcast_gather():
+    lengths = [120, 33, 75, 20, 99, 64, 101, 47, 58]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, lengths, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = [o for o in outs if len(o) == 4][0]
+    assert all(o[0] for o in outs)                      # both ranks hold rank 0's arena bytes
+    ok, merged, counts, work = full
+    assert [m[1] for m in merged] == list(range(len(lengths)))   # every utterance exactly once, in order
+    assert [m[2] for m in merged] == [l * 200 for l in lengths]
+    assert abs(counts[0] - counts[1]) <= 1
+    assert abs(work[0] - work[1]) <= max(lengths)        # length-sorted dealing balances padded work
+
+
+def test_shard_is_a_partition_single_process():
+    lengths = list(range(1, 38))
+    for ws in (1, 2, 4, 8):
+        shards = [mbd.shard_utterances(lengths, r, ws) for r in range(ws)]
+        assert sorted(i for s in shards for i in s) == list(range(len(lengths)))
+        assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
