@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hifigan_cfg2", choices=["hifigan_cfg2", "wavernn_cfg3"])
+    ap.add_argument("--workload", default="hifigan_cfg2", choices=["hifigan_cfg2", "wavernn_cfg3", "tacotron_cfg4"])
     ap.add_argument("--precision", default=os.environ.get("MOCKINGBIRD_B200_GAN_PRECISION", "f16tc"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-child", nargs=3, default=None, help=argparse.SUPPRESS)
@@ -169,10 +169,14 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_threads()
-    if args.workload != "hifigan_cfg2":
+    if args.workload == "wavernn_cfg3":
         import bench_wavernn
 
         return bench_wavernn.run_reference(args, threads)
+    if args.workload == "tacotron_cfg4":
+        import bench_tacotron
+
+        return bench_tacotron.run_reference(args, threads)
     per_step = []
     total = 0
     for s in range(args.warmup + args.steps):
@@ -363,6 +367,10 @@ def main():
         workload, amount, threads = args.cpu_child[0], int(args.cpu_child[1]), int(args.cpu_child[2])
         if workload == "hifigan_cfg2":
             v, dt, n = cpu_hifigan(32, amount, threads)
+        elif workload == "tacotron_cfg4":
+            import bench_tacotron
+
+            v, dt = bench_tacotron.cpu_oracle(amount, threads)
         else:
             import bench_wavernn
 
@@ -373,6 +381,10 @@ def main():
         return run_reference(args)
     if args.workload == "hifigan_cfg2":
         return run_ours_hifigan(args)
+    if args.workload == "tacotron_cfg4":
+        import bench_tacotron
+
+        return bench_tacotron.run_ours(args)
     import bench_wavernn
 
     return bench_wavernn.run_ours(args)
