@@ -97,6 +97,244 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
   }
 }
 
+// ---- large-M kernel: 128 x 128 tile, 8 x 8 per thread, k-major shared tiles ----------------------
+constexpr int LBM = 128, LBN = 128, LBK = 8;
+
+__global__ void __launch_bounds__(256) gemm_big_kernel(const GemmArgs a) {
+  __shared__ __align__(16) float As[2][LBK][LBM + 4];
+  __shared__ __align__(16) float Bs[2][LBK][LBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads, each 8 rows x 8 cols (two 4-wide halves)
+  const int m0 = blockIdx.y * LBM, n0 = blockIdx.x * LBN;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  // loader mapping: 128 rows x 8 k = 1024 elements per operand -> 4 per thread
+  const int lk = tid & 7;        // k within the chunk
+  const int lr = tid >> 3;       // 0..31, rows lr + 32*i
+  float ra[4], rb[4];
+
+  // flat list of (segment, k0) chunks
+  int nchunks = 0;
+  for (int s = 0; s < a.nseg; ++s) nchunks += (a.seg[s].K + LBK - 1) / LBK;
+
+  auto load = [&](int chunk) {
+    int s = 0, c = chunk;
+    while (c >= (a.seg[s].K + LBK - 1) / LBK) {
+      c -= (a.seg[s].K + LBK - 1) / LBK;
+      ++s;
+    }
+    const Seg sg = a.seg[s];
+    const int k = c * LBK + lk;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + lr + 32 * i;
+      float v = 0.f;
+      if (m < a.M && k < sg.K) {
+        bool ok = true;
+        int row = m;
+        if (sg.shift != 0) {
+          const int t = m % a.T + sg.shift;
+          ok = (t >= 0 && t < a.T);
+          row = m + sg.shift;
+        }
+        if (ok) v = sg.x[(size_t)row * sg.ld + k];
+      }
+      ra[i] = v;
+      const int n = n0 + lr + 32 * i;
+      float w = 0.f;
+      if (n < a.N && k < sg.K) w = a.W[(size_t)n * a.ldw + sg.w_off + (size_t)k * sg.w_stride];
+      rb[i] = w;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      As[buf][lk][lr + 32 * i] = ra[i];
+      Bs[buf][lk][lr + 32 * i] = rb[i];
+    }
+  };
+
+  load(0);
+  stash(0);
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunks) load(c + 1);
+#pragma unroll
+    for (int kk = 0; kk < LBK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    if (c + 1 < nchunks) stash(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= a.N) continue;
+      float v = acc[i][j];
+      if (a.bias) v += a.bias[n];
+      v = act_fn(v, a.act);
+      if (a.bn_scale) v = fmaf(v, a.bn_scale[n], a.bn_shift[n]);
+      if (a.mask) v = a.mask[(size_t)m * a.N + n] ? v * 2.f : 0.f;
+      if (a.res) v += a.res[(size_t)m * a.ldres + n];
+      a.Y[(size_t)m * a.ldy + n] = v;
+    }
+  }
+}
+
+// ---- skinny kernel (M <= 64: decoder step, recurrent h projections): one CTA = all rows x 8 output
+// columns, the 8 warps split K and reduce through shared memory -> N/8 CTAs keep every SM busy.
+constexpr int SKK = 16;
+
+// CG = column groups of 8 per CTA (1 -> 8 columns, 4 -> 32 columns: fewer re-reads of X for wide N)
+template <int CG>
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmArgs a) {
+  constexpr int SKN = 8 * CG;
+  // Xs [8 warps][SKK][64+4] | Ws [8][SKK][SKN]; the cross-warp reduction buffer aliases Xs afterwards
+  extern __shared__ __align__(16) float sm[];
+  float (*Xs)[SKK][68] = reinterpret_cast<float (*)[SKK][68]>(sm);
+  float (*Ws)[SKK][SKN] = reinterpret_cast<float (*)[SKK][SKN]>(sm + 8 * SKK * 68);
+  float (*red)[64][9] = reinterpret_cast<float (*)[64][9]>(sm);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rt = lane & 15, ct = lane >> 4;  // rows 4*rt.., cols 4*ct.. within a column group
+  const int n0 = blockIdx.x * SKN;
+  float acc[CG][4][4];
+#pragma unroll
+  for (int g = 0; g < CG; ++g)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[g][i][j] = 0.f;
+
+  const int lq = lane & 3, lr = lane >> 2;  // staging: 4 lanes x float4 cover 16 k of a row, 8 rows per pass
+  int chunk = 0;
+  for (int s = 0; s < a.nseg; ++s) {
+    const Seg sg = a.seg[s];
+    const bool vec = ((sg.ld & 3) == 0) && ((sg.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.x) & 15) == 0);
+    const bool wvec = (sg.w_stride == 1) && ((a.ldw & 3) == 0) && ((sg.w_off & 3) == 0) && ((sg.K & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.W) & 15) == 0);
+    for (int k0 = 0; k0 < sg.K; k0 += SKK, ++chunk) {
+      if ((chunk & 7) != warp) continue;
+      const int k = k0 + 4 * lq;
+#pragma unroll
+      for (int pass = 0; pass < 8; ++pass) {
+        const int m = pass * 8 + lr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < a.M) {
+          const float* src = sg.x + (size_t)m * sg.ld + k;
+          if (vec && k + 3 < sg.K) v = *reinterpret_cast<const float4*>(src);
+          else {
+            if (k < sg.K) v.x = src[0];
+            if (k + 1 < sg.K) v.y = src[1];
+            if (k + 2 < sg.K) v.z = src[2];
+            if (k + 3 < sg.K) v.w = src[3];
+          }
+        }
+        Xs[warp][4 * lq + 0][m] = v.x;
+        Xs[warp][4 * lq + 1][m] = v.y;
+        Xs[warp][4 * lq + 2][m] = v.z;
+        Xs[warp][4 * lq + 3][m] = v.w;
+      }
+#pragma unroll
+      for (int pass = 0; pass < CG; ++pass) {
+        const int j = pass * 8 + lr;
+        const int n = n0 + j;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < a.N) {
+          const float* src = a.W + (size_t)n * a.ldw + sg.w_off + (size_t)k * sg.w_stride;
+          if (wvec && k + 3 < sg.K) v = *reinterpret_cast<const float4*>(src);
+          else {
+            if (k < sg.K) v.x = src[0];
+            if (k + 1 < sg.K) v.y = src[(size_t)sg.w_stride];
+            if (k + 2 < sg.K) v.z = src[(size_t)2 * sg.w_stride];
+            if (k + 3 < sg.K) v.w = src[(size_t)3 * sg.w_stride];
+          }
+        }
+        Ws[warp][4 * lq + 0][j] = v.x;
+        Ws[warp][4 * lq + 1][j] = v.y;
+        Ws[warp][4 * lq + 2][j] = v.z;
+        Ws[warp][4 * lq + 3][j] = v.w;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int kk = 0; kk < SKK; ++kk) {
+        const float4 xv = *reinterpret_cast<const float4*>(&Xs[warp][kk][rt * 4]);
+        const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+          const float4 wv = *reinterpret_cast<const float4*>(&Ws[warp][kk][g * 8 + ct * 4]);
+          const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[g][i][j] = fmaf(xr[i], wr[j], acc[g][i][j]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < CG; ++g) {
+    __syncthreads();  // Xs (first pass) / the previous group's partials are no longer needed
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[warp][rt * 4 + i][ct * 4 + j] = acc[g][i][j];
+    __syncthreads();
+    for (int o = tid; o < 64 * 8; o += 256) {
+      const int m = o >> 3, j = o & 7;
+      const int n = n0 + g * 8 + j;
+      if (m >= a.M || n >= a.N) continue;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += red[w][m][j];
+      if (a.bias) v += a.bias[n];
+      v = act_fn(v, a.act);
+      if (a.bn_scale) v = fmaf(v, a.bn_scale[n], a.bn_shift[n]);
+      if (a.mask) v = a.mask[(size_t)m * a.N + n] ? v * 2.f : 0.f;
+      if (a.res) v += a.res[(size_t)m * a.ldres + n];
+      a.Y[(size_t)m * a.ldy + n] = v;
+    }
+  }
+}
+
+// y[m] = act(bias + sum_j x_j[m] . w[off_j : off_j + K_j])  for N == 1 (stop projection): one CTA per row
+__global__ void __launch_bounds__(256) rowdot_kernel(const GemmArgs a) {
+  __shared__ float red[8];
+  const int m = blockIdx.x, tid = threadIdx.x;
+  float s = 0.f;
+  for (int sgi = 0; sgi < a.nseg; ++sgi) {
+    const Seg sg = a.seg[sgi];
+    for (int k = tid; k < sg.K; k += 256) s = fmaf(sg.x[(size_t)m * sg.ld + k], a.W[sg.w_off + (size_t)k * sg.w_stride], s);
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    if (a.bias) v += a.bias[0];
+    a.Y[(size_t)m * a.ldy] = act_fn(v, a.act);
+  }
+}
+
 __global__ void gru_cell_kernel(const float* __restrict__ gi, int ldgi, const float* __restrict__ gh, float* h, int ldh,
                                 float* out2, int ldout2, int M, int H) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,6 +405,32 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int ldsrc, int r
 
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return cudaSuccess;
+  bool shifted = false;
+  for (int s = 0; s < a.nseg; ++s) shifted = shifted || a.seg[s].shift != 0;
+  if (a.N == 1 && !shifted && !a.mask && !a.res && !a.bn_scale) {
+    rowdot_kernel<<<a.M, 256, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  if (a.M <= 64 && !shifted) {
+    if (a.N >= 2048) {
+      constexpr size_t smem = sizeof(float) * (8 * SKK * 68 + 8 * SKK * 32);
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(gemm_skinny_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+      }
+      gemm_skinny_kernel<4><<<(a.N + 31) / 32, 256, smem, st>>>(a);
+    } else {
+      constexpr size_t smem = sizeof(float) * (8 * SKK * 68 + 8 * SKK * 8);
+      gemm_skinny_kernel<1><<<(a.N + 7) / 8, 256, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+  }
+  if (a.M >= 1024 && a.N >= 128) {
+    dim3 grid((a.N + LBN - 1) / LBN, (a.M + LBM - 1) / LBM);
+    gemm_big_kernel<<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+  }
   // small-M (decoder step) problems: narrower N tiles -> more CTAs
   if (a.M <= 128 && a.N >= 512) {
     dim3 grid((a.N + 31) / 32, (a.M + BM - 1) / BM);
