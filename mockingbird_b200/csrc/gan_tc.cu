@@ -33,6 +33,7 @@
 #include <cstring>
 #include <map>
 
+#include "gan_tc_dev.cuh"
 #include "mb_common.h"
 
 namespace mb {
@@ -75,92 +76,7 @@ struct TcParams {
   int len_mul_out;
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "MB_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MB_DONE_%=;\n"
-      "bra MB_WAIT_%=;\n"
-      "MB_DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-// start address, LBO = 1 (unused for swizzled K-major), SBO = 8 rows, base offset, layout type
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type,
-                                              uint32_t base_offset) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(base_offset & 7) << 49;
-  d |= (uint64_t)(layout_type & 7) << 61;
-  return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+using namespace tcdev;
 
 struct WorkItem {
   int b, m0, r;
@@ -217,11 +133,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.Cout; i += kTcThreads) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.Cout; i += kTcThreads) bias_s[i] = p.bias ? p.bias[i] : 0.f;  // weights: never written by a kernel
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, bias) overlapped the
+  // tail of the previous layer's kernel; activations written by it may only be touched after this wait.
+  // Dependents of THIS kernel may begin their own prologue as soon as SMs free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
 
   if (warp == 0) {
@@ -516,6 +437,16 @@ int kernel_count(const TapConv& t) {
   return k;
 }
 
+// MB_TC_FUSE=0 disables the fused resblock-pair kernel (gan_tc_pair.cu) for A/B measurements
+bool tc_fuse_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB_TC_FUSE");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
+}
+
 // how the A descriptor encodes a start address that is not 1024-byte aligned (row-shifted taps).
 // Measured on B200 (tests/test_gan_tc_layers.py under MB_TC_BASEOFF=0/1): the operand fetch applies the
 // swizzle XOR on absolute shared-memory address bits, so the matrix-base-offset field must stay 0
@@ -604,7 +535,18 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   const int grid = std::min(p.n_work, sms);
   if (grid <= 0) return MB_OK;
   // always claim the whole shared memory: one CTA per SM, so the 512-column TMEM allocation never contends
-  kern<<<grid, kTcThreads, kSmemMax, st>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = kSmemMax;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
   MB_LAUNCH_CHECK("tc_conv_kernel");
   return MB_OK;
 }
@@ -691,6 +633,11 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
     p32[i] = ws;
     ws += f32_plane_bytes(B, T, bufs[i].cr);
   }
+  // buffer -> fp16 plane storage.  The fused pair kernel must not write the fp16 plane it is still reading
+  // halos from (other CTAs), so it ping-pongs between the buffer's storage and the unused storage of the
+  // pair's intermediate buffer; map16 tracks where each buffer's current fp16 plane lives.
+  std::vector<int> map16(nb);
+  for (int i = 0; i < nb; ++i) map16[i] = i;
   const int n = (int)ops.size();
   for (int i = 0; i < n; ++i) {
     const TcOp& op = ops[i];
@@ -707,18 +654,47 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       }
       TRef d32 = make_ref(p32[op.dst], LAYOUT_F32B, op.cout, Lout);
       TRef s32 = make_ref(p32[op.src], LAYOUT_F32B, op.cout, Lout);
-      TRef d16 = need16 ? make_ref(p16[op.dst], LAYOUT_F16B, op.cout, Lout) : TRef{};
+      TRef d16 = need16 ? make_ref(p16[map16[op.dst]], LAYOUT_F16B, op.cout, Lout) : TRef{};
       cudaError_t e = launch_add_inplace_f32(d32, s32, d16, slope16, B, st);
       if (e != cudaSuccess) return fail(MB_ERR_CUDA, "add kernel: %s", cudaGetErrorString(e));
       count_launch();
       continue;
     }
+    // ---- fuse a resblock pair (c1 -> T -> c2) into one kernel when the channel count allows it
+    TcPairParams pp;
+    memset(&pp, 0, sizeof(pp));
+    bool fuse = false;
+    if (tc_fuse_enabled() && i + 1 < n && op.tc.use_tc && ops[i + 1].is_conv && ops[i + 1].tc.use_tc) {
+      const TcOp& c2 = ops[i + 1];
+      const TapConv& t1 = op.taps;
+      const TapConv& t2 = c2.taps;
+      const int k = t1.ntaps[0];
+      const int d1 = k > 1 ? t1.off[0][1] - t1.off[0][0] : 1;
+      bool ok = op.cin == op.cout && c2.cin == c2.cout && op.cin == c2.cin && t1.stride == 1 && t2.stride == 1 &&
+                t2.ntaps[0] == k && (k & 1) && op.res < 0 && op.dst2 < 0 && c2.dst2 < 0 && t1.mode == EPI_STORE &&
+                op.dst == c2.src && op.dst >= 0 && op.dst < nb && op.src >= 0 && op.src < nb && c2.res != op.dst &&
+                op.rate_in == c2.rate_in;
+      for (int t = 0; ok && t < k; ++t)
+        ok = (t1.off[0][t] == t * d1 - d1 * (k - 1) / 2) && (t2.off[0][t] == t - (k - 1) / 2) && t1.slab[0][t] == t &&
+             t2.slab[0][t] == t;
+      // the intermediate buffer must not be read by anything but c2 before it is overwritten
+      for (int j = i + 2; ok && j < n; ++j) {
+        const TcOp& c = ops[j];
+        if (c.src == op.dst || (c.is_conv && (c.res == op.dst || c.dst2 == op.dst))) ok = false;
+        if (c.is_conv && c.dst == op.dst && c.taps.mode == EPI_STORE) break;
+      }
+      if (ok && tc_pair_plan(op.cin, k, d1, &pp)) fuse = true;
+    }
+    const TcOp& oop = fuse ? ops[i + 1] : op;  // the op whose outputs this launch produces
+    const char* fused_x16 = fuse ? p16[map16[op.src]] : nullptr;
+    if (fuse && oop.dst == op.src) std::swap(map16[oop.dst], map16[op.dst]);  // write the other storage
+    const int scan_from = fuse ? i + 2 : i + 1;
     // ---- which planes must this op produce? (scan the consumers of dst until it is overwritten)
     bool need16 = false, need32 = false;
     float slope16 = 1.f;
     bool have_slope = false;
     auto scan = [&](int buf, bool& n16, bool& n32, float& s16, bool& hs) -> int {
-      for (int j = i + 1; j < n; ++j) {
+      for (int j = scan_from; j < n; ++j) {
         const TcOp& c = ops[j];
         if (c.is_conv) {
           if (c.src == buf) {
@@ -745,36 +721,62 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
     };
     TRef y32, y16, y2_32, y2_16;
     float y2_slope = 1.f;
-    if (op.dst == BUF_OUT) {
-      y32 = make_ref(wav, LAYOUT_NCL, op.cout, Lout);
+    if (oop.dst == BUF_OUT) {
+      y32 = make_ref(wav, LAYOUT_NCL, oop.cout, Lout);
     } else {
-      if (op.dst < 0 || op.dst >= nb) return fail(MB_ERR_INVALID, "tc_forward: bad dst");
-      int rc = scan(op.dst, need16, need32, slope16, have_slope);
+      if (oop.dst < 0 || oop.dst >= nb) return fail(MB_ERR_INVALID, "tc_forward: bad dst");
+      int rc = scan(oop.dst, need16, need32, slope16, have_slope);
       if (rc != MB_OK) return rc;
-      if (op.taps.mode != EPI_STORE) need32 = true;
-      if (need32) y32 = make_ref(p32[op.dst], LAYOUT_F32B, op.cout, Lout);
+      if (oop.taps.mode != EPI_STORE) need32 = true;
+      if (need32) y32 = make_ref(p32[oop.dst], LAYOUT_F32B, oop.cout, Lout);
       if (need16) {
-        y16 = make_ref(p16[op.dst], LAYOUT_F16B, op.cout, Lout);
-        if (cur16[op.dst].C != op.cout || cur16[op.dst].L != Lout) {
+        y16 = make_ref(p16[map16[oop.dst]], LAYOUT_F16B, oop.cout, Lout);
+        if (cur16[map16[oop.dst]].C != oop.cout || cur16[map16[oop.dst]].L != Lout) {
           cudaError_t e = launch_zero_pads_f16(y16, B, st);
           if (e != cudaSuccess) return fail(MB_ERR_CUDA, "zero_pads: %s", cudaGetErrorString(e));
           count_launch();
-          cur16[op.dst] = y16;
+          cur16[map16[oop.dst]] = y16;
         }
       }
     }
-    if (op.dst2 >= 0) {
-      if (op.dst2 >= nb) return fail(MB_ERR_INVALID, "tc_forward: bad dst2");
+    if (oop.dst2 >= 0) {
+      if (oop.dst2 >= nb) return fail(MB_ERR_INVALID, "tc_forward: bad dst2");
       bool n16 = false, n32 = true, hs = false;
-      int rc = scan(op.dst2, n16, n32, y2_slope, hs);
+      int rc = scan(oop.dst2, n16, n32, y2_slope, hs);
       if (rc != MB_OK) return rc;
-      y2_32 = make_ref(p32[op.dst2], LAYOUT_F32B, op.cout, Lout);
-      if (n16) y2_16 = make_ref(p16[op.dst2], LAYOUT_F16B, op.cout, Lout);
+      y2_32 = make_ref(p32[oop.dst2], LAYOUT_F32B, oop.cout, Lout);
+      if (n16) y2_16 = make_ref(p16[map16[oop.dst2]], LAYOUT_F16B, oop.cout, Lout);
     }
-    TRef res32 = (op.res >= 0) ? make_ref(p32[op.res], LAYOUT_F32B, op.cout, Lout) : TRef{};
+    TRef res32 = (oop.res >= 0) ? make_ref(p32[oop.res], LAYOUT_F32B, oop.cout, Lout) : TRef{};
+    if (fuse) {
+      const TcOp& c2 = ops[i + 1];
+      pp.L = Lin;
+      pp.x16 = reinterpret_cast<const __half*>(fused_x16);
+      pp.x_Lp = f16_lp(Lin);
+      pp.w1 = reinterpret_cast<const __half*>(tc_arena + op.tc.w16_off);
+      pp.w2 = reinterpret_cast<const __half*>(tc_arena + c2.tc.w16_off);
+      pp.bias1 = op.b32;
+      pp.bias2 = c2.b32;
+      pp.slope_mid = c2.taps.in_slope;
+      pp.res32 = reinterpret_cast<const float*>(res32.p);
+      pp.y32 = reinterpret_cast<float*>(y32.p);
+      pp.y16 = reinterpret_cast<__half*>(y16.p);
+      pp.y_Lp = f16_lp(Lout);
+      pp.out_slope = slope16;
+      pp.mode = c2.taps.mode;
+      pp.div = c2.taps.div;
+      pp.lengths = lengths;
+      pp.len_mul = c2.taps.len_mul_out;
+      if (pp.mode != EPI_STORE && !pp.y32) return fail(MB_ERR_INVALID, "tc_pair(%s): accumulate mode without fp32 plane", c2.name);
+      int rc = launch_tc_pair(pp, B, st);
+      if (rc != MB_OK) return rc;
+      if (events) MB_CUDA_CHECK(cudaEventRecord(events[i + 1], st));
+      ++i;  // c2 is done as well
+      continue;
+    }
     if (op.tc.use_tc) {
       if (op.src < 0 || op.src >= nb) return fail(MB_ERR_INVALID, "tc_forward: tensor-core layer %s reads an external buffer", op.name);
-      TRef x16 = make_ref(p16[op.src], LAYOUT_F16B, op.cin, Lin);
+      TRef x16 = make_ref(p16[map16[op.src]], LAYOUT_F16B, op.cin, Lin);
       int rc = launch_tc(op, tc_arena, x16, res32, y32, y16, slope16, lengths, B, Lin, st);
       if (rc != MB_OK) return rc;
     } else {

@@ -55,6 +55,33 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
                const float* mel, const int32_t* lengths, int B, int T, int num_mels, int hop, float* wav,
                void* workspace, cudaStream_t stream, cudaEvent_t* events /* nullptr or [ops+1] */);
 
+// fused resblock pair (gan_tc_pair.cu): c1 (k taps, dilation d1) -> lrelu -> c2 (k taps, dilation 1)
+struct TcPairParams {
+  int L, C, k, d1, h1, h2;
+  int MT, M_out, W1, W2;
+  int a1_stages, a2_stages;
+  int tiles_per_utt, n_work;
+  uint32_t a1_stage_bytes, a2_bytes, a1_off, a2_off, w1_off, w2_off, bias_off, bar_off;
+  const __half* x16;
+  int x_Lp;
+  const __half* w1;
+  const __half* w2;
+  const float* bias1;
+  const float* bias2;
+  float slope_mid;
+  const float* res32;
+  float* y32;
+  __half* y16;
+  int y_Lp;
+  float out_slope;
+  int mode;
+  float div;
+  const int32_t* lengths;
+  int len_mul;
+};
+bool tc_pair_plan(int C, int k, int d1, TcPairParams* p);
+int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st);
+
 int tc_debug_layer(const TcOp& op, const char* tc_arena, const float* x, const float* residual, int B, int Lin,
                    float* y, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 

@@ -1,0 +1,419 @@
+// Fused resblock pair on tcgen05: one kernel computes   x_new = c2(lrelu(c1(a) + b1)) + b2 + x_old
+// (hifigan/models.py:36-41: xt = c1(lrelu(x)); xt = c2(lrelu(xt)); x = xt + x) for the layers whose
+// channel count is <= 64.  The intermediate activation xt never goes to HBM: the first accumulator is
+// read from TMEM by the epilogue warps, biased, leaky-relu'd, rounded to fp16 and written straight into
+// a swizzled shared-memory operand buffer that the second convolution's MMAs consume.
+//
+//   work item  = (utterance, M_out = MT*128 - (k-1) output rows)
+//   MMA1(i)    : acc1[i&1] = c1 over xt rows [m0 - h2, m0 - h2 + MT*128)        (A1 = bulk-TMA window)
+//   E1(i)      : acc1 -> +b1 -> lrelu -> 0 outside [0, valid) -> fp16 -> A2[i]   (smem, SWIZZLE_128B/64B)
+//   MMA2(i)    : acc2[i&1] = c2 over output rows [m0, m0 + MT*128)              (A2 rows i + t)
+//   E2(i)      : acc2 -> +b2 + residual (fp32) -> fp32 plane / MRF sum and fp16 (activated) plane
+// issue order MMA1(i+1), MMA2(i) and E1(i+1), E2(i): the tensor core always has the other phase's tile
+// to chew on while the epilogue warps drain one (all four accumulators live in TMEM: 4*MT*N <= 512).
+// Both weight sets are shared-memory resident for the whole kernel.
+#include <cstring>
+
+#include "gan_tc.h"
+#include "gan_tc_dev.cuh"
+#include "mb_common.h"
+
+namespace mb {
+
+namespace {
+
+using namespace tcdev;
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+
+template <int N, int MT, int CW>
+__global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_constant__ TcPairParams p) {
+  constexpr uint32_t ROWB = CW * 2;
+  constexpr int NK16 = CW / 16;
+  constexpr uint32_t MT_STEP = (128u * ROWB) >> 4;
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t SLAB = (uint32_t)N * ROWB;  // one tap's weight image [N][CW]
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a1_base = smem + p.a1_off;
+  uint8_t* a2_base = smem + p.a2_off;
+  uint8_t* w1_base = smem + p.w1_off;
+  uint8_t* w2_base = smem + p.w2_off;
+  float* bias1_s = reinterpret_cast<float*>(smem + p.bias_off);
+  float* bias2_s = bias1_s + N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* a1_full = bars;            // [2]
+  uint64_t* a1_empty = bars + 2;       // [2]
+  uint64_t* w_full = bars + 4;         // [2] : 0 = c1 weights, 1 = c2 weights
+  uint64_t* acc1_full = bars + 6;      // [2]
+  uint64_t* acc1_empty = bars + 8;     // [2]
+  uint64_t* a2_full = bars + 10;       // [2]
+  uint64_t* a2_empty = bars + 12;      // [2]
+  uint64_t* acc2_full = bars + 14;     // [2]
+  uint64_t* acc2_empty = bars + 16;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a1_full[i], 1);
+      mbar_init(&a1_empty[i], 1);
+      mbar_init(&w_full[i], 1);
+      mbar_init(&acc1_full[i], 1);
+      mbar_init(&acc1_empty[i], 32 * kEpiWarps);
+      mbar_init(&a2_full[i], 32 * kEpiWarps);
+      mbar_init(&a2_empty[i], 1);
+      mbar_init(&acc2_full[i], 1);
+      mbar_init(&acc2_empty[i], 32 * kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < N; i += kThreads) {
+    bias1_s[i] = p.bias1[i];
+    bias2_s[i] = p.bias2[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int n_items = (p.n_work > (int)blockIdx.x) ? (p.n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int halo = p.h1 + p.h2;
+
+  if (warp == 0) {
+    // ===================== copy producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(&w_full[0], (uint32_t)p.k * SLAB);
+      bulk_g2s(smem_u32(w1_base), p.w1, (uint32_t)p.k * SLAB, &w_full[0]);
+      mbar_expect_tx(&w_full[1], (uint32_t)p.k * SLAB);
+      bulk_g2s(smem_u32(w2_base), p.w2, (uint32_t)p.k * SLAB, &w_full[1]);
+      for (int it = 0; it < n_items; ++it) {
+        const int work = blockIdx.x + it * gridDim.x;
+        const int b = work / p.tiles_per_utt;
+        const int m0 = (work - b * p.tiles_per_utt) * p.M_out;
+        const int slot = it % p.a1_stages, ph = (it / p.a1_stages) & 1;
+        mbar_wait(&a1_empty[slot], ph ^ 1);
+        const uint32_t bytes = (uint32_t)p.W1 * ROWB;
+        mbar_expect_tx(&a1_full[slot], bytes);
+        const int row0 = (kPadRows + m0 - halo) & ~7;
+        const __half* src = p.x16 + ((size_t)b * p.x_Lp + (size_t)row0) * CW;
+        bulk_g2s(smem_u32(a1_base + (size_t)slot * p.a1_stage_bytes), src, bytes, &a1_full[slot]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint64_t desc_hi = make_desc(0, 8u * ROWB, CW == 64 ? 2u : 4u, 0);
+    const bool leader = elect_one();
+    bool w1_seen = false, w2_seen = false;
+    auto mma2 = [&](int j) {
+      const int aslot = j % p.a2_stages, aph = (j / p.a2_stages) & 1;
+      const int cslot = j & 1, cph = (j >> 1) & 1;
+      if (!w2_seen) {
+        mbar_wait(&w_full[1], 0);
+        w2_seen = true;
+      }
+      mbar_wait(&a2_full[aslot], aph);
+      mbar_wait(&acc2_empty[cslot], cph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)((2 + cslot) * MT * N);
+      const uint32_t a_addr = smem_u32(a2_base + (size_t)aslot * p.a2_bytes);
+      if (leader) {
+        for (int t = 0; t < p.k; ++t) {
+          const uint64_t a0 = desc_hi + (uint64_t)((a_addr + (uint32_t)t * ROWB) >> 4);
+          const uint64_t b0 = desc_hi + (uint64_t)((smem_u32(w2_base) + (uint32_t)t * SLAB) >> 4);
+#pragma unroll
+          for (int s = 0; s < NK16; ++s)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              tc_mma_f16(d_tmem + (uint32_t)(mt * N), a0 + (uint64_t)(2 * s + mt * MT_STEP), b0 + (uint64_t)(2 * s), idesc,
+                         (t | s) ? 1u : 0u);
+        }
+        tc_commit(&a2_empty[aslot]);
+        tc_commit(&acc2_full[cslot]);
+      }
+    };
+    for (int it = 0; it < n_items; ++it) {
+      const int work = blockIdx.x + it * gridDim.x;
+      const int b = work / p.tiles_per_utt;
+      const int m0 = (work - b * p.tiles_per_utt) * p.M_out;
+      const int slot = it % p.a1_stages, ph = (it / p.a1_stages) & 1;
+      const int cslot = it & 1, cph = (it >> 1) & 1;
+      if (!w1_seen) {
+        mbar_wait(&w_full[0], 0);
+        w1_seen = true;
+      }
+      mbar_wait(&a1_full[slot], ph);
+      mbar_wait(&acc1_empty[cslot], cph ^ 1);
+      tc_fence_after();
+      const int delta = (kPadRows + m0 - halo) & 7;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(cslot * MT * N);
+      const uint32_t a_addr = smem_u32(a1_base + (size_t)slot * p.a1_stage_bytes);
+      if (leader) {
+        for (int t = 0; t < p.k; ++t) {
+          const uint64_t a0 = desc_hi + (uint64_t)((a_addr + (uint32_t)(delta + t * p.d1) * ROWB) >> 4);
+          const uint64_t b0 = desc_hi + (uint64_t)((smem_u32(w1_base) + (uint32_t)t * SLAB) >> 4);
+#pragma unroll
+          for (int s = 0; s < NK16; ++s)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              tc_mma_f16(d_tmem + (uint32_t)(mt * N), a0 + (uint64_t)(2 * s + mt * MT_STEP), b0 + (uint64_t)(2 * s), idesc,
+                         (t | s) ? 1u : 0u);
+        }
+        tc_commit(&a1_empty[slot]);
+        tc_commit(&acc1_full[cslot]);
+      }
+      if (it > 0) mma2(it - 1);
+    }
+    if (n_items > 0) mma2(n_items - 1);
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int row_in_tile = quarter * 32 + lane;
+    constexpr int UPT = N / 32;          // 32-column units per row tile
+    constexpr int NUNITS = MT * UPT;
+    const int C4 = N >> 2;
+    constexpr int OCW = (N >= 64) ? 64 : N;  // output plane row chunk (f16_cw)
+
+    auto e1 = [&](int it) {
+      const int work = blockIdx.x + it * gridDim.x;
+      const int b = work / p.tiles_per_utt;
+      const int m0 = (work - b * p.tiles_per_utt) * p.M_out;
+      const int valid = p.lengths ? min(p.L, p.lengths[b] * p.len_mul) : p.L;
+      const int cslot = it & 1, cph = (it >> 1) & 1;
+      const int aslot = it % p.a2_stages, aph = (it / p.a2_stages) & 1;
+      mbar_wait(&acc1_full[cslot], cph);
+      mbar_wait(&a2_empty[aslot], aph ^ 1);
+      tc_fence_after();
+      uint8_t* a2 = a2_base + (size_t)aslot * p.a2_bytes;
+      for (int u = grp; u < NUNITS; u += 2) {
+        const int mt = u / UPT;
+        const int col0 = (u - mt * UPT) << 5;
+        const int j = mt * 128 + row_in_tile;   // xt row within the item
+        const int g = m0 - p.h2 + j;            // global xt row
+        const bool live = (g >= 0 && g < valid);
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((cslot * MT + mt) * N + col0), raw);
+        uint8_t* rowp = a2 + (size_t)j * ROWB;
+        const int sw = f16_swz(CW, j);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float x = __uint_as_float(raw[8 * c + e]) + bias1_s[col0 + 8 * c + e];
+            v[e] = live ? lrelu(x, p.slope_mid) : 0.f;
+          }
+          __half2 h0 = __floats2half2_rn(v[0], v[1]);
+          __half2 h1 = __floats2half2_rn(v[2], v[3]);
+          __half2 h2 = __floats2half2_rn(v[4], v[5]);
+          __half2 h3 = __floats2half2_rn(v[6], v[7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2);
+          pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          const int chunk = (col0 >> 3) + c;   // 16-byte chunk within the row (C <= 64: one row chunk)
+          *reinterpret_cast<uint4*>(rowp + ((chunk ^ sw) << 4)) = pk;
+        }
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.shared -> visible to the UMMA operand fetch
+      mbar_arrive(&a2_full[aslot]);
+      mbar_arrive(&acc1_empty[cslot]);
+    };
+
+    auto e2 = [&](int it) {
+      const int work = blockIdx.x + it * gridDim.x;
+      const int b = work / p.tiles_per_utt;
+      const int m0 = (work - b * p.tiles_per_utt) * p.M_out;
+      const int valid = p.lengths ? min(p.L, p.lengths[b] * p.len_mul) : p.L;
+      const int cslot = it & 1, cph = (it >> 1) & 1;
+      bool waited = false;
+      for (int u = grp; u < NUNITS; u += 2) {
+        const int mt = u / UPT;
+        const int col0 = (u - mt * UPT) << 5;
+        const int i = mt * 128 + row_in_tile;
+        const int lo = m0 + i;
+        const bool inb = (i < p.M_out) && (lo < p.L);
+        const bool live = inb && lo < valid;
+        const size_t i32 = ((size_t)b * C4 + (col0 >> 2)) * p.L + lo;
+        float4 rv[8], ov[8];
+        if (inb && p.res32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.L];
+        }
+        if (inb && p.mode != EPI_STORE) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) ov[g] = reinterpret_cast<const float4*>(p.y32)[i32 + (size_t)g * p.L];
+        }
+        if (!waited) {
+          mbar_wait(&acc2_full[cslot], cph);
+          tc_fence_after();
+          waited = true;
+        }
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(((2 + cslot) * MT + mt) * N + col0), raw);
+        if (!inb) continue;
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]) + bias2_s[col0 + e];
+        if (p.res32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            v[4 * g + 0] += rv[g].x; v[4 * g + 1] += rv[g].y; v[4 * g + 2] += rv[g].z; v[4 * g + 3] += rv[g].w;
+          }
+        }
+        if (p.mode != EPI_STORE) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            v[4 * g + 0] += ov[g].x; v[4 * g + 1] += ov[g].y; v[4 * g + 2] += ov[g].z; v[4 * g + 3] += ov[g].w;
+          }
+          if (p.mode == EPI_ADD_DIV) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] /= p.div;
+          }
+        }
+        if (!live) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0.f;
+        }
+        if (p.y32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            reinterpret_cast<float4*>(p.y32)[i32 + (size_t)g * p.L] =
+                make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        }
+        if (p.y16) {
+          const int rr = kPadRows + lo;
+          const int sw = f16_swz(OCW, rr);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            __half2 h0 = __floats2half2_rn(lrelu(v[8 * g + 0], p.out_slope), lrelu(v[8 * g + 1], p.out_slope));
+            __half2 h1 = __floats2half2_rn(lrelu(v[8 * g + 2], p.out_slope), lrelu(v[8 * g + 3], p.out_slope));
+            __half2 h2 = __floats2half2_rn(lrelu(v[8 * g + 4], p.out_slope), lrelu(v[8 * g + 5], p.out_slope));
+            __half2 h3 = __floats2half2_rn(lrelu(v[8 * g + 6], p.out_slope), lrelu(v[8 * g + 7], p.out_slope));
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            const int cc = (col0 >> 3) + g;
+            const size_t i16 = ((size_t)b * p.y_Lp + rr) * (size_t)(OCW >> 3) + (size_t)(cc ^ sw);
+            reinterpret_cast<uint4*>(p.y16)[i16] = pk;
+          }
+        }
+      }
+      if (!waited) {
+        mbar_wait(&acc2_full[cslot], cph);
+        tc_fence_after();
+      }
+      tc_fence_before();
+      mbar_arrive(&acc2_empty[cslot]);
+    };
+
+    for (int it = 0; it < n_items; ++it) {
+      e1(it);
+      if (it > 0) e2(it - 1);
+    }
+    if (n_items > 0) e2(n_items - 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+constexpr uint32_t kSmemMax = 227 * 1024;
+
+}  // namespace
+
+bool tc_pair_plan(int C, int k, int d1, TcPairParams* p) {
+  if (C != 64 && C != 32) return false;
+  const int row_bytes = C * 2;
+  const int h1 = d1 * (k - 1) / 2, h2 = (k - 1) / 2;
+  if (h1 + h2 > kPadRows) return false;
+  const uint32_t slab = (uint32_t)C * row_bytes;
+  const uint32_t wbytes = (uint32_t)align_up((size_t)k * slab, 1024);
+  const uint32_t usable = kSmemMax - 1024;
+  const int mt_max = (C == 64) ? 2 : 4;  // 4 accumulators of MT*N columns in 512 TMEM columns
+  for (int mt = mt_max; mt >= 1; mt >>= 1) {
+    for (int stages = 2; stages >= 1; --stages) {
+      const int W1 = (mt * 128 + 2 * h1 + 7 + 7) & ~7;
+      const int W2 = (mt * 128 + 16 + 7) & ~7;
+      const uint32_t a1b = (uint32_t)align_up((size_t)W1 * row_bytes, 1024);
+      const uint32_t a2b = (uint32_t)align_up((size_t)W2 * row_bytes, 1024);
+      const uint32_t total = stages * a1b + stages * a2b + 2 * wbytes + 1024 + 1024;
+      if (total > usable) continue;
+      p->C = C;
+      p->k = k;
+      p->d1 = d1;
+      p->h1 = h1;
+      p->h2 = h2;
+      p->MT = mt;
+      p->M_out = mt * 128 - 2 * h2;
+      p->W1 = W1;
+      p->W2 = W2;
+      p->a1_stages = stages;
+      p->a2_stages = stages;
+      p->a1_stage_bytes = a1b;
+      p->a2_bytes = a2b;
+      p->a1_off = 0;
+      p->a2_off = stages * a1b;
+      p->w1_off = p->a2_off + stages * a2b;
+      p->w2_off = p->w1_off + wbytes;
+      p->bias_off = p->w2_off + wbytes;
+      p->bar_off = p->bias_off + 1024;
+      return true;
+    }
+  }
+  return false;
+}
+
+int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
+  p.tiles_per_utt = (p.L + p.M_out - 1) / p.M_out;
+  p.n_work = B * p.tiles_per_utt;
+  void (*kern)(const TcPairParams) = nullptr;
+  if (p.C == 64 && p.MT == 2) kern = tc_pair_kernel<64, 2, 64>;
+  else if (p.C == 64 && p.MT == 1) kern = tc_pair_kernel<64, 1, 64>;
+  else if (p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32>;
+  else if (p.C == 32 && p.MT == 2) kern = tc_pair_kernel<32, 2, 32>;
+  else if (p.C == 32 && p.MT == 1) kern = tc_pair_kernel<32, 1, 32>;
+  else return fail(MB_ERR_INVALID, "tc_pair: no kernel instance for C=%d MT=%d", p.C, p.MT);
+  MB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.n_work < sms ? p.n_work : sms;
+  if (grid <= 0) return MB_OK;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemMax;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+  count_launch();
+  return MB_OK;
+}
+
+}  // namespace mb
