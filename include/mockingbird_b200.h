@@ -230,6 +230,40 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
                          const uint8_t* dec_masks, uint64_t seed, float* mel, float* linear, float* attn,
                          int32_t* frames_out_host, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Speaker encoder (cfg 5 front half)
+ *   replaces  models/encoder/model.py:41-61 (SpeakerEncoder.forward: 3 x LSTM(40 -> 256), last hidden of
+ *             the top layer -> Linear -> ReLU -> L2), driven by models/encoder/inference.py:51-64
+ *             (embed_frames_batch) and :157-166 (mean of the partial embeddings, L2 normalised)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mb_encoder_config {
+  int32_t mel_n_channels; /* 40  params_data.py mel_n_channels */
+  int32_t hidden_size;    /* 256 params_model.py model_hidden_size */
+  int32_t num_layers;     /* 3   model_num_layers */
+  int32_t embedding_size; /* 256 model_embedding_size */
+} mb_encoder_config;
+
+typedef struct mb_encoder mb_encoder;
+
+int mb_encoder_create(const mb_encoder_config* cfg, mb_encoder** out);
+void mb_encoder_destroy(mb_encoder* h);
+size_t mb_encoder_arena_bytes(const mb_encoder* h);
+int mb_encoder_set_arena(mb_encoder* h, void* arena, size_t bytes);
+/* tensors of ckpt['model_state'] under their reference names: lstm.weight_ih_l{0..}, lstm.weight_hh_l*,
+ * lstm.bias_ih_l*, lstm.bias_hh_l*, linear.weight, linear.bias (similarity_weight/bias are loss-only) */
+int mb_encoder_set_weight(mb_encoder* h, const char* name, const float* w, const int64_t* dims, int32_t ndim,
+                          void* stream);
+int mb_encoder_finalize(mb_encoder* h, void* stream);
+size_t mb_encoder_workspace_bytes(const mb_encoder* h, int32_t rows, int32_t n_frames);
+/* SpeakerEncoder.forward: frames fp32 [rows][n_frames][mel_n_channels] -> embeds fp32 [rows][embedding_size]
+ * (L2 normalised with the reference's +1e-5) */
+int mb_encoder_embed_frames(mb_encoder* h, const float* frames, int32_t rows, int32_t n_frames, float* embeds,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* embed_utterance's reduction (inference.py:164-166): utterance u owns partial rows
+ * [offsets[u], offsets[u+1]) (int32 device array [n_utterances+1]); out = L2(mean of those rows) */
+int mb_encoder_reduce_partials(mb_encoder* h, const float* partial_embeds, const int32_t* offsets,
+                               int32_t n_utterances, float* utterance_embeds, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

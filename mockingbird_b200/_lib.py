@@ -63,6 +63,10 @@ class TacotronConfig(C.Structure):
         "postnet_K", "num_highways", "speaker_embedding_size", "gst_E", "gst_tokens", "gst_heads", "max_r")]
 
 
+class EncoderConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("mel_n_channels", "hidden_size", "num_layers", "embedding_size")]
+
+
 # name -> (restype, argtypes); every symbol include/mockingbird_b200.h declares
 SIGNATURES = {
     "mb_last_error": (C.c_char_p, []),
@@ -111,6 +115,17 @@ SIGNATURES = {
     "mb_tacotron_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mb_encoder_create": (C.c_int, [C.POINTER(EncoderConfig), C.POINTER(C.c_void_p)]),
+    "mb_encoder_destroy": (None, [C.c_void_p]),
+    "mb_encoder_arena_bytes": (C.c_size_t, [C.c_void_p]),
+    "mb_encoder_set_arena": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mb_encoder_set_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32,
+                                        C.c_void_p]),
+    "mb_encoder_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mb_encoder_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
+    "mb_encoder_embed_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]),
+    "mb_encoder_reduce_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

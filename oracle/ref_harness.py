@@ -191,3 +191,15 @@ def build_tacotron(seed: int = 0):
                  stop_threshold=hparams.tts_stop_threshold, speaker_embedding_size=hparams.speaker_embedding_size)
     m.eval()
     return m
+
+
+def build_encoder(seed: int = 0):
+    """Reference SpeakerEncoder as encoder/inference.py:31-34 builds it (CPU)."""
+    install()
+    import torch
+    from models.encoder.model import SpeakerEncoder
+
+    torch.manual_seed(seed)
+    m = SpeakerEncoder(torch.device("cpu"), torch.device("cpu"))
+    m.eval()
+    return m

@@ -350,3 +350,20 @@ def tacotron_state_dict(seed: int = 0, r: int = 2, randomize_bn: bool = True) ->
                 elif k.endswith(".bias"):
                     sd[k] = torch.randn(sd[k].shape, generator=g2) * 0.2
     return sd
+
+
+def encoder_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """``torch.manual_seed(seed); SpeakerEncoder(cpu, cpu)`` state_dict rebuilt from stock torch layers in
+    the reference's construction order (models/encoder/model.py:17-28): nn.LSTM(40, 256, 3), nn.Linear(256, 256);
+    similarity_weight / similarity_bias are constants (10, -5) and consume no RNG."""
+    nn = torch.nn
+    torch.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    lstm = nn.LSTM(input_size=40, hidden_size=256, num_layers=3, batch_first=True)
+    for k, v in lstm.state_dict().items():
+        sd["lstm." + k] = v.detach()
+    lin = nn.Linear(256, 256)
+    sd["linear.weight"], sd["linear.bias"] = lin.weight.detach(), lin.bias.detach()
+    sd["similarity_weight"] = torch.tensor([10.0])
+    sd["similarity_bias"] = torch.tensor([-5.0])
+    return sd

@@ -124,3 +124,50 @@ def test_ref_init_tacotron_bit_identical():
     ref = m.state_dict()
     assert set(sd) == set(ref)
     assert all(torch.equal(sd[k].float(), ref[k].float()) for k in sd)
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_encoder_oracle_matches_golden(golden_dir, name):
+    """SpeakerEncoder.forward restatement vs the live-reference golden (model.py:41-61)"""
+    import encoder_oracle as eo
+
+    z = np.load(golden_dir / "encoder_seed0.npz")
+    sd = ri.encoder_state_dict(0)
+    got = eo.embed_frames(sd, torch.from_numpy(z[f"{name}_frames"])).numpy()
+    assert np.abs(got - z[f"{name}_embeds"]).max() < 1e-6
+    if name == "a":
+        utt = eo.embed_utterance_partials(sd, torch.from_numpy(z["a_frames"]))
+        assert np.abs(utt - z["a_utterance"]).max() < 1e-6
+        assert abs(float(np.linalg.norm(utt)) - 1.0) < 1e-6
+
+
+@needs_ref
+@pytest.mark.reference
+def test_ref_init_encoder_bit_identical():
+    rh.install()
+    rh.hide_cuda()
+    m = rh.build_encoder(seed=3)
+    sd = ri.encoder_state_dict(3)
+    ref = m.state_dict()
+    assert set(sd) == set(ref)
+    assert all(torch.equal(sd[k], ref[k]) for k in sd)
+
+
+def test_encoder_partial_slices_match_reference_rule():
+    """compute_partial_slices (encoder/inference.py:66-125): known cases incl. the coverage rule"""
+    from mockingbird_b200.encoder.inference import compute_partial_slices
+
+    w, m = compute_partial_slices(16000 * 3)  # 3 s: 301 frames, step 80
+    assert [s.start for s in m] == [0, 80, 160] and all(s.stop - s.start == 160 for s in m)
+    assert w[1] == slice(80 * 160, 240 * 160)
+    w, m = compute_partial_slices(1000)  # shorter than one partial: always one slice
+    assert len(m) == 1 and m[0] == slice(0, 160)
+    w, m = compute_partial_slices(16000 * 3, min_pad_coverage=1.0)
+    assert [s.start for s in m] == [0, 80]
+    if rh.reference_available():
+        rh.install()
+        from models.encoder import inference as ref_inf
+
+        for n in (1000, 25601, 48000, 51199, 160000):
+            for kw in ({}, {"overlap": 0.25}, {"rate": 1.3}, {"min_pad_coverage": 0.5}):
+                assert compute_partial_slices(n, **kw) == ref_inf.compute_partial_slices(n, **kw)
