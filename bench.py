@@ -2,7 +2,7 @@
 """bench.py - headline benchmark of the B200 vocoder hot path (contract: see DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload hifigan_cfg2|wavernn_cfg3] [--precision f16tc|fp32]
+                    [--workload hifigan_cfg2|wavernn_cfg3|tacotron_cfg4|e2e_cfg5] [--precision f16tc|fp32]
 
 Default workload = BASELINE.json configs[1]: HiFi-GAN Generator forward, batch 32 random mels of
 256 frames x 80 bins, per GPU.  A "step" is one forward over one batch.  Prints ONE JSON line
@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hifigan_cfg2", choices=["hifigan_cfg2", "wavernn_cfg3", "tacotron_cfg4"])
+    ap.add_argument("--workload", default="hifigan_cfg2", choices=["hifigan_cfg2", "wavernn_cfg3", "tacotron_cfg4", "e2e_cfg5"])
     ap.add_argument("--precision", default=os.environ.get("MOCKINGBIRD_B200_GAN_PRECISION", "f16tc"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-child", nargs=3, default=None, help=argparse.SUPPRESS)
@@ -177,6 +177,10 @@ def run_reference(args):
         import bench_tacotron
 
         return bench_tacotron.run_reference(args, threads)
+    if args.workload == "e2e_cfg5":
+        import bench_e2e
+
+        return bench_e2e.run_reference(args, threads)
     per_step = []
     total = 0
     for s in range(args.warmup + args.steps):
@@ -373,6 +377,10 @@ def main():
             import bench_tacotron
 
             v, dt = bench_tacotron.cpu_oracle(amount, threads)
+        elif workload == "e2e_cfg5":
+            import bench_e2e
+
+            v, dt = bench_e2e.cpu_oracle(amount, threads)
         else:
             import bench_wavernn
 
@@ -387,6 +395,10 @@ def main():
         import bench_tacotron
 
         return bench_tacotron.run_ours(args)
+    if args.workload == "e2e_cfg5":
+        import bench_e2e
+
+        return bench_e2e.run_ours(args)
     import bench_wavernn
 
     return bench_wavernn.run_ours(args)

@@ -1,0 +1,252 @@
+"""End-to-end workload of bench.py (--workload e2e_cfg5): BASELINE.json configs[4], speaker encoder ->
+Tacotron -> HiFi-GAN on synthetic utterances sharded across the GPUs, 128 utterances per GPU
+(1024 on 8 GPUs; weak scaling).
+
+Per utterance (SURVEY.md 8d cfg 5): 6 synthetic partial windows rand(6,160,40) -> speaker embedding;
+token sequence of random length 20..120; Tacotron steps=400, r=2, min_stop_token=10 (no early stop),
+style_idx=-1 -> 400-frame mel; HiFi-GAN -> 80 000 audio samples.  The global utterance list is
+length-sorted and dealt round-robin to ranks (distributed.shard_utterances); no collective on the data path.
+
+A "step" is the whole pipeline over the rank's 128 utterances.  `value`: device-resident (inputs in
+HBM, model-level calls).  `e2e`: through the drop-in module surfaces with host numpy in and out
+(encoder.inference.embed_utterances_frames -> Synthesizer.synthesize_from_sequences ->
+hifigan.inference.infer_waveforms), host<->device copies inside the timed region."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+UTT_PER_GPU, PARTIALS, PFRAMES, STEPS, R, TBATCH, VBATCH = 128, 6, 160, 400, 2, 64, 32
+
+
+def make_utterances(n_total: int):
+    """global synthetic utterance list: (token lengths, token ids, partial mel windows seed)"""
+    import torch
+
+    g = torch.Generator().manual_seed(6)
+    lens = torch.randint(20, 121, (n_total,), generator=g)
+    chars = torch.randint(2, 75, (n_total, 120), generator=g)
+    return lens, chars
+
+
+def cpu_oracle(n_utt: int, threads: int, frames: int = 200):
+    """CPU oracles chained the same way on `n_utt` utterances with `frames` decoder frames each"""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import torch
+    import encoder_oracle as eo
+    import gan_oracle as go
+    import ref_init as ri
+    import tacotron_oracle as to
+
+    torch.set_num_threads(threads)
+    lens, chars = make_utterances(n_utt)
+    tsd = ri.tacotron_state_dict(0, r=R, randomize_bn=True)
+    esd = ri.encoder_state_dict(0)
+    cfg = ri.HIFIGAN_CONFIG_16K
+    gsd = go.fold_weight_norm(ri.hifigan_state_dict(cfg, 0))
+    parts = torch.rand(n_utt * PARTIALS, PFRAMES, 40, generator=torch.Generator().manual_seed(7)) * 0.2
+    tc = int(lens.max())
+    ch = chars[:, :tc].clone()
+    for b in range(n_utt):
+        ch[b, lens[b]:] = 0
+    g = torch.Generator().manual_seed(9)
+    nst = frames // R
+    masks = [torch.rand(n_utt, tc, 256, generator=g) < 0.5 for _ in range(2)] + \
+            [torch.rand(n_utt, 256, generator=g) < 0.5 for _ in range(2 * nst)]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        pe = eo.embed_frames(esd, parts).view(n_utt, PARTIALS, -1).mean(1)
+        emb = pe / pe.norm(dim=1, keepdim=True)
+        mel, lin, _ = to.generate(tsd, ch, emb, frames, -1, 10, masks, r=R)
+        n = 0
+        for b in range(n_utt):  # batch-1 vocoder calls like hifigan/inference.py:66-70
+            n += go.hifigan_forward(gsd, cfg, lin[b:b + 1]).numel()
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def run_reference(args, threads):
+    per = []
+    n_utt, frames = 32, 200
+    for s in range(args.warmup + args.steps):
+        v, dt = cpu_oracle(n_utt, threads, frames)
+        if s >= args.warmup:
+            per.append(dt)
+    secs = sum(per)
+    v = n_utt * frames * 200 * args.steps / secs
+    print(json.dumps({
+        "impl": "reference", "metric": "vocoder audio samples/sec", "value": v, "unit": "samples/s",
+        "utterances_per_s": v / 80000.0, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "e2e_cfg5: encoder -> Tacotron -> HiFi-GAN (sample: 32 utterances x 200 frames per step)"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": "32 utterances x 200 of 400 decoder frames per step, torch-CPU oracles chained"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT / "oracle"))  # ref_init only: seeded random-init weights (no checkpoints exist)
+    import ref_init as ri
+    from bench import ClockSampler, cpu_child, host_threads, log
+    from mockingbird_b200 import _lib
+    from mockingbird_b200.distributed import shard_utterances
+    from mockingbird_b200.encoder import inference as enc_inf
+    from mockingbird_b200.encoder.model import SpeakerEncoder
+    from mockingbird_b200.synthesizer.hparams import hparams as shp
+    from mockingbird_b200.synthesizer.inference import Synthesizer
+    from mockingbird_b200.vocoder.hifigan import inference as gan_vocoder
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+
+    # models: every rank builds the objects, rank 0's packed weights are broadcast over NCCL
+    enc = SpeakerEncoder(dev)
+    enc.load_state_dict(ri.encoder_state_dict(0))
+    enc.eval()
+    enc_inf.set_model(enc, dev)
+    syn = Synthesizer("unused.pt", verbose=False)
+    taco = syn.load_state(ri.tacotron_state_dict(0, r=R, randomize_bn=True))
+    taco.to(dev)
+    cfg = ri.HIFIGAN_CONFIG_16K
+    gen = gan_vocoder.load_state(ri.hifigan_state_dict(cfg, 0), cfg)
+    if world > 1:
+        for m in (enc, taco, gen):
+            dist.broadcast(m.packed_arena(), src=0)
+    shp.synthesis_batch_size = TBATCH
+
+    n_total = UTT_PER_GPU * world
+    lens, chars = make_utterances(n_total)
+    mine = shard_utterances(lens.tolist(), rank, world)
+    assert len(mine) == UTT_PER_GPU
+    seqs = [chars[i, : int(lens[i])].tolist() for i in mine]  # sorted longest first -> little padding per batch
+    parts = [(torch.rand(PARTIALS, PFRAMES, 40, generator=torch.Generator().manual_seed(1000 + i)) * 0.2).numpy() for i in mine]
+    parts_dev = torch.from_numpy(np.concatenate(parts)).to(dev)
+    offsets = list(range(0, UTT_PER_GPU * PARTIALS + 1, PARTIALS))
+    chars_dev = []
+    for s in range(0, UTT_PER_GPU, TBATCH):
+        tc = max(len(q) for q in seqs[s:s + TBATCH])
+        c = torch.zeros(min(TBATCH, UTT_PER_GPU - s), tc, dtype=torch.int32)
+        for b, q in enumerate(seqs[s:s + TBATCH]):
+            c[b, : len(q)] = torch.tensor(q, dtype=torch.int32)
+        chars_dev.append(c.to(dev))
+    lib = _lib.lib()
+    produced = {"samples": 0}
+
+    def step_resident():
+        emb = enc.reduce_partials(enc.forward(parts_dev), offsets)
+        n = 0
+        for bi, c in enumerate(chars_dev):
+            _, lin, _ = taco.generate(c, emb[bi * TBATCH: bi * TBATCH + c.shape[0]], steps=STEPS, style_idx=-1, min_stop_token=10)
+            for v in range(0, lin.shape[0], VBATCH):
+                n += gen(lin[v:v + VBATCH].contiguous()).numel()
+        produced["samples"] = n
+
+    def step_e2e():
+        embeds = enc_inf.embed_utterances_frames(parts)
+        specs = syn.synthesize_from_sequences(seqs, list(embeds), False, -1, 10, STEPS)
+        wavs = gan_vocoder.infer_waveforms(specs, batch_size=VBATCH)
+        produced["samples"] = sum(len(w) for w in wavs)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    log("e2e_cfg5: warm-up")
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.mb_launch_count()
+    k = max(1, args.steps)
+    ms = timed(step_resident, k)
+    launches = int(lib.mb_launch_count() - l0)
+    clocks = sampler.stop()
+    n_res = produced["samples"]
+    # stage split of one resident step (events between stages)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    emb = enc.reduce_partials(enc.forward(parts_dev), offsets)
+    ev[1].record()
+    lins = [taco.generate(c, emb[bi * TBATCH: bi * TBATCH + c.shape[0]], steps=STEPS, style_idx=-1, min_stop_token=10)[1]
+            for bi, c in enumerate(chars_dev)]
+    ev[2].record()
+    for lin in lins:
+        for v in range(0, lin.shape[0], VBATCH):
+            gen(lin[v:v + VBATCH].contiguous())
+    ev[3].record()
+    torch.cuda.synchronize()
+    split = {"encoder_ms": ev[0].elapsed_time(ev[1]), "tacotron_ms": ev[1].elapsed_time(ev[2]),
+             "hifigan_ms": ev[2].elapsed_time(ev[3])}
+    log(f"resident {ms / k:.1f} ms/step {split}; e2e pass")
+    step_e2e()
+    ms_e2e = timed(step_e2e, k)
+    n_e2e = produced["samples"]
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = host_threads()
+            r = cpu_child("e2e_cfg5", 64, threads, 300.0)
+            if r:
+                cpu = {"value": r["value"], "unit": "samples/s", "cores": threads, "kind": "port",
+                       "sample": f"64 utterances x 200 of 400 decoder frames ({r['seconds']:.1f} s), torch-CPU oracles chained"}
+        value = world * n_res * k / (ms * 1e-3)
+        h2d = sum(p.nbytes for p in parts) + sum(len(q) for q in seqs) * 8 + UTT_PER_GPU * 256 * 4 + UTT_PER_GPU * 80 * STEPS * 4
+        d2h = UTT_PER_GPU * 256 * 4 + UTT_PER_GPU * 80 * STEPS * 4 + n_e2e * 4
+        # dominant stage = Tacotron (FP32 FFMA): its FLOPs over its share of the step
+        flops = 2.0 * UTT_PER_GPU * (20.99e6 * (STEPS // R) + 8.03e6 * STEPS + 3.2e6 * 70)
+        taco_s = split["tacotron_ms"] * 1e-3
+        print(json.dumps({
+            "metric": "vocoder audio samples/sec", "value": value, "unit": "samples/s",
+            "utterances_per_s": value / (STEPS * 200), "n_gpus": world, "steps": k, "warmup": max(1, min(args.warmup, 3)),
+            "ms_per_step": ms / k, "rtf": (ms / k * 1e-3) / (n_res / 16000.0), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (encoder, Tacotron) / f16 operands + f32 accumulate (HiFi-GAN)", "data": "synthetic",
+            "config": {"workload": "e2e_cfg5: encoder -> Tacotron(steps=400, r=2) -> HiFi-GAN, 128 utterances per GPU "
+                                   f"({n_total} total), length-sorted round-robin shards", "parallelism": f"dp{world}",
+                       "l2": "per-step working set (activations of 128 utterances) exceeds L2"},
+            "stage_split_ms": split,
+            "e2e": {"value": world * n_e2e * k / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / k},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "latency", "kernel": "Tacotron stage (FP32 FFMA GEMMs; 200 dependent decoder steps per batch of 64)",
+                         "achieved": flops / taco_s / 1e12, "peak": 72.0, "unit": "TFLOP/s",
+                         "frac": flops / taco_s / 1e12 / 72.0, "traffic": None,
+                         "note": "pipeline of three models; per-stage times in stage_split_ms; the HiFi-GAN stage has its own "
+                                 "roofline line under --workload hifigan_cfg2"},
+            "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()

@@ -66,6 +66,9 @@ struct TcParams {
   const __half* w16;
   const float* bias;
   const float* res32;
+  const __half* res16;                 // residual taken from an (activated) fp16 plane instead: x = y >= 0 ? y : y * res_inv
+  int res_Lp;
+  float res_inv;
   float* y32;
   __half* y16;
   int y_Lp;
@@ -281,9 +284,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         const bool live = inb && lo < valid_out;
         const size_t i32 = ((size_t)wi.b * C4 + (col0 >> 2)) * p.Lout + lo;  // + g * Lout per 4 channels
         float4 rv[8], ov[8];
+        uint4 rh[4];
         if (inb && p.res32) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.Lout];
+        }
+        if (inb && p.res16) {
+          const int rr = kPadRows + lo;
+          const size_t rbase = (((size_t)wi.b * (p.Cout / ocw) + col0 / ocw) * p.res_Lp + rr) * (size_t)(ocw >> 3);
+          const int c0 = (col0 & (ocw - 1)) >> 3, sw = f16_swz(ocw, rr);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rh[g] = reinterpret_cast<const uint4*>(p.res16)[rbase + (size_t)((c0 + g) ^ sw)];
         }
         if (inb && p.mode != EPI_STORE) {
 #pragma unroll
@@ -305,6 +316,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
           for (int g = 0; g < 8; ++g) {
             v[4 * g + 0] += rv[g].x; v[4 * g + 1] += rv[g].y; v[4 * g + 2] += rv[g].z; v[4 * g + 3] += rv[g].w;
           }
+        }
+        if (p.res16) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) add_res16(&v[8 * g], rh[g], p.res_inv);
         }
         if (p.mode != EPI_STORE) {
 #pragma unroll
@@ -447,6 +462,18 @@ bool tc_fuse_enabled() {
   return on != 0;
 }
 
+// MB_TC_RES16=0 keeps an fp32 residual plane in every stage (default: only in the full-rate stage; the
+// other stages carry the residual stream as ONE activated fp16 plane that is both the next conv's operand
+// and - through the exact inverse of the leaky-relu - the residual; error budget in DESIGN.md 3.4)
+bool tc_res16_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB_TC_RES16");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
+}
+
 // how the A descriptor encodes a start address that is not 1024-byte aligned (row-shifted taps).
 // Measured on B200 (tests/test_gan_tc_layers.py under MB_TC_BASEOFF=0/1): the operand fetch applies the
 // swizzle XOR on absolute shared-memory address bits, so the matrix-base-offset field must stay 0
@@ -466,8 +493,8 @@ size_t f16_plane_bytes(size_t B, size_t T, size_t cr) {
 }
 size_t f32_plane_bytes(size_t B, size_t T, size_t cr) { return align_up(4 * B * T * cr + 256, 1024); }
 
-int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef& res32, const TRef& y32,
-              const TRef& y16, float out_slope, const int32_t* lengths, int B, int Lin, cudaStream_t st) {
+int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef& res32, const TRef& res16, float res_slope,
+              const TRef& y32, const TRef& y16, float out_slope, const int32_t* lengths, int B, int Lin, cudaStream_t st) {
   const TapConv& t = op.taps;
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -507,6 +534,9 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.w16 = reinterpret_cast<const __half*>(tc_arena + op.tc.w16_off);
   p.bias = op.b32;
   p.res32 = reinterpret_cast<const float*>(res32.p);
+  p.res16 = reinterpret_cast<const __half*>(res16.p);
+  p.res_Lp = f16_lp(res16.L);
+  p.res_inv = 1.f / res_slope;
   p.y32 = reinterpret_cast<float*>(y32.p);
   p.y16 = reinterpret_cast<__half*>(y16.p);
   p.y_Lp = f16_lp(y16.L);
@@ -638,7 +668,15 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
   // pair's intermediate buffer; map16 tracks where each buffer's current fp16 plane lives.
   std::vector<int> map16(nb);
   for (int i = 0; i < nb; ++i) map16[i] = i;
+  std::vector<float> plane_slope(nb, 1.f);  // leaky-relu slope each fp16 storage was written with
   const int n = (int)ops.size();
+  int full_rate = 1;
+  for (const TcOp& o : ops) full_rate = std::max(full_rate, o.rate_out);
+  // residual taken from the activated fp16 plane (no fp32 residual plane) in every stage but the full-rate one
+  auto res16_ok = [&](const TcOp& c) {
+    return tc_res16_enabled() && c.is_conv && c.tc.use_tc && c.res >= 0 && c.res < nb && c.taps.stride == 1 &&
+           c.rate_out < full_rate;
+  };
   for (int i = 0; i < n; ++i) {
     const TcOp& op = ops[i];
     if (events) MB_CUDA_CHECK(cudaEventRecord(events[i], st));
@@ -655,6 +693,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       TRef d32 = make_ref(p32[op.dst], LAYOUT_F32B, op.cout, Lout);
       TRef s32 = make_ref(p32[op.src], LAYOUT_F32B, op.cout, Lout);
       TRef d16 = need16 ? make_ref(p16[map16[op.dst]], LAYOUT_F16B, op.cout, Lout) : TRef{};
+      if (need16) plane_slope[map16[op.dst]] = slope16;
       cudaError_t e = launch_add_inplace_f32(d32, s32, d16, slope16, B, st);
       if (e != cudaSuccess) return fail(MB_ERR_CUDA, "add kernel: %s", cudaGetErrorString(e));
       count_launch();
@@ -687,6 +726,9 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
     }
     const TcOp& oop = fuse ? ops[i + 1] : op;  // the op whose outputs this launch produces
     const char* fused_x16 = fuse ? p16[map16[op.src]] : nullptr;
+    const bool use_res16 = res16_ok(oop);
+    const TRef res16 = use_res16 ? make_ref(p16[map16[oop.res]], LAYOUT_F16B, oop.cout, Lout) : TRef{};
+    const float res_slope = use_res16 ? plane_slope[map16[oop.res]] : 1.f;
     if (fuse && oop.dst == op.src) std::swap(map16[oop.dst], map16[op.dst]);  // write the other storage
     const int scan_from = fuse ? i + 2 : i + 1;
     // ---- which planes must this op produce? (scan the consumers of dst until it is overwritten)
@@ -707,7 +749,10 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
               n32 = true;
             }
           }
-          if (c.res == buf) n32 = true;
+          if (c.res == buf) {
+            if (res16_ok(c)) n16 = true;
+            else n32 = true;
+          }
           if (c.dst2 == buf) n32 = true;
           if (c.dst == buf) {
             if (c.taps.mode != EPI_STORE) n32 = true;
@@ -737,6 +782,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
           count_launch();
           cur16[map16[oop.dst]] = y16;
         }
+        plane_slope[map16[oop.dst]] = slope16;
       }
     }
     if (oop.dst2 >= 0) {
@@ -745,9 +791,12 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       int rc = scan(oop.dst2, n16, n32, y2_slope, hs);
       if (rc != MB_OK) return rc;
       y2_32 = make_ref(p32[oop.dst2], LAYOUT_F32B, oop.cout, Lout);
-      if (n16) y2_16 = make_ref(p16[map16[oop.dst2]], LAYOUT_F16B, oop.cout, Lout);
+      if (n16) {
+        y2_16 = make_ref(p16[map16[oop.dst2]], LAYOUT_F16B, oop.cout, Lout);
+        plane_slope[map16[oop.dst2]] = y2_slope;
+      }
     }
-    TRef res32 = (oop.res >= 0) ? make_ref(p32[oop.res], LAYOUT_F32B, oop.cout, Lout) : TRef{};
+    TRef res32 = (oop.res >= 0 && !use_res16) ? make_ref(p32[oop.res], LAYOUT_F32B, oop.cout, Lout) : TRef{};
     if (fuse) {
       const TcOp& c2 = ops[i + 1];
       pp.L = Lin;
@@ -759,6 +808,9 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       pp.bias2 = c2.b32;
       pp.slope_mid = c2.taps.in_slope;
       pp.res32 = reinterpret_cast<const float*>(res32.p);
+      pp.res16 = reinterpret_cast<const __half*>(res16.p);
+      pp.res_Lp = f16_lp(Lout);
+      pp.res_inv = 1.f / res_slope;
       pp.y32 = reinterpret_cast<float*>(y32.p);
       pp.y16 = reinterpret_cast<__half*>(y16.p);
       pp.y_Lp = f16_lp(Lout);
@@ -777,7 +829,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
     if (op.tc.use_tc) {
       if (op.src < 0 || op.src >= nb) return fail(MB_ERR_INVALID, "tc_forward: tensor-core layer %s reads an external buffer", op.name);
       TRef x16 = make_ref(p16[map16[op.src]], LAYOUT_F16B, op.cin, Lin);
-      int rc = launch_tc(op, tc_arena, x16, res32, y32, y16, slope16, lengths, B, Lin, st);
+      int rc = launch_tc(op, tc_arena, x16, res32, res16, res_slope, y32, y16, slope16, lengths, B, Lin, st);
       if (rc != MB_OK) return rc;
     } else {
       TapConv p = op.taps;
@@ -843,7 +895,7 @@ int tc_debug_layer(const TcOp& op, const char* tc_arena, const float* x, const f
     e = launch_convert_layout(make_ref(const_cast<float*>(residual), LAYOUT_NCL, t.Cout, Lout), r32, B, 1.f, st);
     if (e != cudaSuccess) return fail(MB_ERR_CUDA, "convert: %s", cudaGetErrorString(e));
   }
-  int rc = launch_tc(op, tc_arena, x16, r32, y32, TRef{}, 1.f, nullptr, B, Lin, st);
+  int rc = launch_tc(op, tc_arena, x16, r32, TRef{}, 1.f, y32, TRef{}, 1.f, nullptr, B, Lin, st);
   if (rc != MB_OK) return rc;
   e = launch_convert_layout(y32, yn, B, 1.f, st);
   if (e != cudaSuccess) return fail(MB_ERR_CUDA, "convert: %s", cudaGetErrorString(e));

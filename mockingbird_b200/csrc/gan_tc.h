@@ -70,6 +70,9 @@ struct TcPairParams {
   const float* bias2;
   float slope_mid;
   const float* res32;
+  const __half* res16;  // residual from an activated fp16 plane: x = y >= 0 ? y : y * res_inv
+  int res_Lp;
+  float res_inv;
   float* y32;
   __half* y16;
   int y_Lp;

@@ -95,6 +95,17 @@ __device__ __forceinline__ bool elect_one() {
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+// v[0..8) += x, where the fp16 plane holds y = lrelu(x) (8 channels, 16 bytes) and inv = 1 / slope
+__device__ __forceinline__ void add_res16(float* v, const uint4& pk, float inv) {
+  const __half2* h = reinterpret_cast<const __half2*>(&pk);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(h[e]);
+    v[2 * e + 0] += f.x >= 0.f ? f.x : f.x * inv;
+    v[2 * e + 1] += f.y >= 0.f ? f.y : f.y * inv;
+  }
+}
+
 
 }  // namespace tcdev
 }  // namespace mb

@@ -250,9 +250,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_const
         const bool live = inb && lo < valid;
         const size_t i32 = ((size_t)b * C4 + (col0 >> 2)) * p.L + lo;
         float4 rv[8], ov[8];
+        uint4 rh[4];
         if (inb && p.res32) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.L];
+        }
+        if (inb && p.res16) {
+          const int rr = kPadRows + lo;
+          const size_t rbase = ((size_t)b * p.res_Lp + rr) * (size_t)(OCW >> 3);
+          const int sw = f16_swz(OCW, rr);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rh[g] = reinterpret_cast<const uint4*>(p.res16)[rbase + (size_t)(((col0 >> 3) + g) ^ sw)];
         }
         if (inb && p.mode != EPI_STORE) {
 #pragma unroll
@@ -274,6 +282,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_const
           for (int g = 0; g < 8; ++g) {
             v[4 * g + 0] += rv[g].x; v[4 * g + 1] += rv[g].y; v[4 * g + 2] += rv[g].z; v[4 * g + 3] += rv[g].w;
           }
+        }
+        if (p.res16) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) add_res16(&v[8 * g], rh[g], p.res_inv);
         }
         if (p.mode != EPI_STORE) {
 #pragma unroll
