@@ -72,6 +72,7 @@ struct TcParams {
   float* y32;
   __half* y16;
   int y_Lp;
+  int y_nchunks, y_chunk0;             // fp16 destination plane: row chunks per utterance / first chunk this launch writes
   float out_slope;
   int mode;
   float div;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             pk.w = *reinterpret_cast<uint32_t*>(&h3);
             const int rr = kPadRows + lo;
             const int cc = (col0 & (ocw - 1)) + 8 * g;  // channel within the row chunk
-            const size_t i16 = (((size_t)wi.b * (p.Cout / ocw) + col0 / ocw) * p.y_Lp + rr) * (size_t)(ocw >> 3) +
+            const size_t i16 = (((size_t)wi.b * p.y_nchunks + p.y_chunk0 + col0 / ocw) * p.y_Lp + rr) * (size_t)(ocw >> 3) +
                                (size_t)((cc >> 3) ^ f16_swz(ocw, rr));
             reinterpret_cast<uint4*>(p.y16)[i16] = pk;
           }
@@ -394,6 +395,64 @@ __global__ void pack_w16_kernel(const float* __restrict__ w32, __half* __restric
   const size_t img = ((size_t)k * nch + c) * (size_t)Cout * cw;
   const size_t off = (size_t)co * cw + (size_t)((((cc >> 3) ^ f16_swz(cw, co)) << 3) + (cc & 7));
   dst[img + off] = __float2half_rn(w32[i]);
+}
+
+// ---- 3-term split of an fp32 layer (conv_pre) --------------------------------------------------------
+// input plane channels: [hi(x) (Cin) | lo(x) (Cin) | hi(x) (Cin) | 0 ...] (256 channels, no activation),
+// weight images:        [hi(w)       | hi(w)       | lo(w)       | 0 ...]  -> sum = x*w up to ~2^-22 relative.
+__device__ __forceinline__ __half split_hi(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ __half split_lo(float v) { return __float2half_rn(v - __half2float(__float2half_rn(v))); }
+
+__global__ void split3_input_kernel(const float* __restrict__ x /* NCL [B][Cin][L] */, __half* __restrict__ dst, int B,
+                                    int Cin, int L, const int32_t* __restrict__ lengths) {
+  // one thread per (b, 16-byte chunk of the 256-channel row, l); l fastest -> coalesced reads of x
+  const size_t n = (size_t)B * 32 * L;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = (int)(i % L);
+  const int ch8 = (int)((i / L) % 32);
+  const int b = (int)(i / ((size_t)L * 32));
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = ch8 * 8 + e;
+    const int part = c / Cin, ci = c - part * Cin;
+    float v = 0.f;
+    if (part < 3 && (!lengths || l < lengths[b])) v = x[((size_t)b * Cin + ci) * L + l];  // frames past the length read as zero padding
+    h[e] = part == 1 ? split_lo(v) : (part < 3 ? split_hi(v) : __float2half_rn(0.f));
+  }
+  const int Lp = f16_lp(L);
+  const int r = kPadRows + l;
+  const int chunk = ch8 >> 3, cc8 = ch8 & 7;
+  const size_t o = (((size_t)b * 4 + chunk) * Lp + r) * 8 + (size_t)(cc8 ^ f16_swz(64, r));
+  reinterpret_cast<uint4*>(dst)[o] = *reinterpret_cast<const uint4*>(h);
+}
+
+// fp32 slabs [K][Cin][Cout] -> per 256-output half: images [K][4 chunks][256][64] (swizzled rows)
+__global__ void pack_w16_split3_kernel(const float* __restrict__ w32, __half* __restrict__ dst, int K, int Cin, int Cout) {
+  const size_t n = (size_t)K * 256 * Cout;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int co = (int)(i % Cout);
+  const int c = (int)((i / Cout) % 256);
+  const int k = (int)(i / ((size_t)Cout * 256));
+  const int part = c / Cin, ci = c - part * Cin;
+  __half v = __float2half_rn(0.f);
+  if (part < 3) {
+    const float w = w32[((size_t)k * Cin + ci) * Cout + co];
+    v = part == 2 ? split_lo(w) : split_hi(w);
+  }
+  const int half_idx = co >> 8, col = co & 255;
+  const int chunk = c >> 6, cc = c & 63;
+  const size_t img = (((size_t)half_idx * K + k) * 4 + chunk) * (size_t)(256 * 64);
+  const size_t off = (size_t)col * 64 + (size_t)((((cc >> 3) ^ f16_swz(64, col)) << 3) + (cc & 7));
+  dst[img + off] = v;
+}
+
+bool tc_split3_enabled();
+bool split3_capable(const TapConv& t) {
+  return tc_split3_enabled() && t.stride == 1 && !t.act_tanh && t.Cin * 3 <= 256 && t.Cout % 256 == 0 && t.Cout >= 256 &&
+         t.mode == EPI_STORE;
 }
 
 int pick_kc(int Cin) {
@@ -474,6 +533,26 @@ bool tc_res16_enabled() {
   return on != 0;
 }
 
+// MB_TC_PAIR32=0 disables the fp32-input pair kernel of the full-rate stage (falls back to the fp16-plane pair)
+bool tc_pair32_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB_TC_PAIR32");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
+}
+
+// MB_TC_SPLIT3=0 keeps conv_pre on the FP32 FFMA kernel
+bool tc_split3_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB_TC_SPLIT3");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
+}
+
 // how the A descriptor encodes a start address that is not 1024-byte aligned (row-shifted taps).
 // Measured on B200 (tests/test_gan_tc_layers.py under MB_TC_BASEOFF=0/1): the operand fetch applies the
 // swizzle XOR on absolute shared-memory address bits, so the matrix-base-offset field must stay 0
@@ -494,7 +573,8 @@ size_t f16_plane_bytes(size_t B, size_t T, size_t cr) {
 size_t f32_plane_bytes(size_t B, size_t T, size_t cr) { return align_up(4 * B * T * cr + 256, 1024); }
 
 int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef& res32, const TRef& res16, float res_slope,
-              const TRef& y32, const TRef& y16, float out_slope, const int32_t* lengths, int B, int Lin, cudaStream_t st) {
+              const TRef& y32, const TRef& y16, float out_slope, const int32_t* lengths, int B, int Lin, cudaStream_t st,
+              int y_c0 = 0, const float* bias_override = nullptr) {
   const TapConv& t = op.taps;
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -532,7 +612,7 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.x16 = reinterpret_cast<const __half*>(x16.p);
   p.x_Lp = f16_lp(x16.L);
   p.w16 = reinterpret_cast<const __half*>(tc_arena + op.tc.w16_off);
-  p.bias = op.b32;
+  p.bias = bias_override ? bias_override : op.b32;
   p.res32 = reinterpret_cast<const float*>(res32.p);
   p.res16 = reinterpret_cast<const __half*>(res16.p);
   p.res_Lp = f16_lp(res16.L);
@@ -540,11 +620,14 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.y32 = reinterpret_cast<float*>(y32.p);
   p.y16 = reinterpret_cast<__half*>(y16.p);
   p.y_Lp = f16_lp(y16.L);
+  p.y_nchunks = (y16.p ? y16.C : t.Cout) / f16_cw(t.Cout);
+  p.y_chunk0 = y_c0 / f16_cw(t.Cout);
   p.out_slope = out_slope;
   p.mode = t.mode;
   p.div = t.div;
   p.lengths = lengths;
   p.len_mul_out = t.len_mul_out;
+  if (y_c0 != 0 && (p.y32 || p.res32 || p.res16)) return fail(MB_ERR_INVALID, "tc_conv(%s): channel-offset launch supports the fp16 plane only", op.name);
   if (p.mode != EPI_STORE && !p.y32) return fail(MB_ERR_INVALID, "tc_conv(%s): accumulate mode without fp32 plane", op.name);
   void (*kern)(const TcParams) = nullptr;
   if (p.Cout == 256 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<256, 1, 64>;
@@ -599,6 +682,17 @@ int tc_plan_layers(std::vector<TcLayerDesc>& layers, size_t* tc_arena_bytes) {
     TcLayer& tc = *d.tc;
     const TapConv& t = *d.taps;
     tc = TcLayer{};
+    if (!d.force_f32 && !tc_capable(t) && split3_capable(t)) {
+      // conv_pre: runs as Cout/256 launches of the <256,1,64> instance over a 256-channel split plane
+      tc.split3 = 1;
+      tc.kc = 64;
+      tc.n_cchunks = 4;
+      tc.mt = 1;
+      tc.slab_bytes = (size_t)64 * 256 * 2;
+      tc.w16_off = off;
+      off += align_up((size_t)(t.Cout / 256) * d.k * 4 * tc.slab_bytes, 256);
+      continue;  // use_tc stays 0: every generic decision treats the layer as an FP32-input layer
+    }
     if (d.force_f32 || !tc_capable(t)) continue;
     tc.kc = pick_kc(t.Cin);
     tc.n_cchunks = t.Cin / tc.kc;
@@ -630,6 +724,14 @@ int tc_plan_layers(std::vector<TcLayerDesc>& layers, size_t* tc_arena_bytes) {
 
 int tc_pack_weights(const TcLayer& tc, const TapConv& taps, const float* w32_slabs, char* tc_arena,
                     cudaStream_t stream) {
+  if (tc.split3) {
+    const int K = kernel_count(taps);
+    const size_t n = (size_t)K * 256 * taps.Cout;
+    pack_w16_split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        w32_slabs, reinterpret_cast<__half*>(tc_arena + tc.w16_off), K, taps.Cin, taps.Cout);
+    MB_LAUNCH_CHECK("pack_w16_split3_kernel");
+    return MB_OK;
+  }
   if (!tc.use_tc) return MB_OK;
   const int K = kernel_count(taps);
   const size_t n = (size_t)K * taps.Cin * taps.Cout;
@@ -668,6 +770,8 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
   // pair's intermediate buffer; map16 tracks where each buffer's current fp16 plane lives.
   std::vector<int> map16(nb);
   for (int i = 0; i < nb; ++i) map16[i] = i;
+  std::vector<int> map32(nb);  // same indirection for the fp32 planes (fp32-input pair kernel, in-place pairs)
+  for (int i = 0; i < nb; ++i) map32[i] = i;
   std::vector<float> plane_slope(nb, 1.f);  // leaky-relu slope each fp16 storage was written with
   const int n = (int)ops.size();
   int full_rate = 1;
@@ -677,6 +781,39 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
     return tc_res16_enabled() && c.is_conv && c.tc.use_tc && c.res >= 0 && c.res < nb && c.taps.stride == 1 &&
            c.rate_out < full_rate;
   };
+  // ---- pre-pass: which (c1, c2) op pairs run as ONE fused kernel (gan_tc_pair.cu)?
+  //   kind 1: fp16-plane input;  kind 2: fp32-plane input (full-rate stage, residual = the pair's input)
+  std::vector<int> fuse_kind(n, 0);
+  std::vector<TcPairParams> pair_plan(n);
+  for (int i = 0; i + 1 < n; ++i) {
+    memset(&pair_plan[i], 0, sizeof(TcPairParams));
+    const TcOp& op = ops[i];
+    if (!tc_fuse_enabled() || !op.is_conv || !op.tc.use_tc || !ops[i + 1].is_conv || !ops[i + 1].tc.use_tc) continue;
+    const TcOp& c2 = ops[i + 1];
+    const TapConv& t1 = op.taps;
+    const TapConv& t2 = c2.taps;
+    const int k = t1.ntaps[0];
+    const int d1 = k > 1 ? t1.off[0][1] - t1.off[0][0] : 1;
+    bool ok = op.cin == op.cout && c2.cin == c2.cout && op.cin == c2.cin && t1.stride == 1 && t2.stride == 1 &&
+              t2.ntaps[0] == k && (k & 1) && op.res < 0 && op.dst2 < 0 && c2.dst2 < 0 && t1.mode == EPI_STORE &&
+              op.dst == c2.src && op.dst >= 0 && op.dst < nb && op.src >= 0 && op.src < nb && c2.res != op.dst &&
+              op.rate_in == c2.rate_in;
+    for (int t = 0; ok && t < k; ++t)
+      ok = (t1.off[0][t] == t * d1 - d1 * (k - 1) / 2) && (t2.off[0][t] == t - (k - 1) / 2) && t1.slab[0][t] == t &&
+           t2.slab[0][t] == t;
+    // the intermediate buffer must not be read by anything but c2 before it is overwritten
+    for (int j = i + 2; ok && j < n; ++j) {
+      const TcOp& c = ops[j];
+      if (c.src == op.dst || (c.is_conv && (c.res == op.dst || c.dst2 == op.dst))) ok = false;
+      if (c.is_conv && c.dst == op.dst && c.taps.mode == EPI_STORE) break;
+    }
+    if (!ok) continue;
+    const bool want32 = tc_pair32_enabled() && c2.res == op.src && !res16_ok(c2);
+    if (want32 && tc_pair_plan(op.cin, k, d1, true, &pair_plan[i])) fuse_kind[i] = 2;
+    else if (tc_pair_plan(op.cin, k, d1, false, &pair_plan[i])) fuse_kind[i] = 1;
+    if (fuse_kind[i]) ++i;  // c2 belongs to this pair
+  }
+  auto reads_f32 = [&](int j) { return fuse_kind[j] == 2; };  // op j (a c1) takes its operand from the fp32 plane
   for (int i = 0; i < n; ++i) {
     const TcOp& op = ops[i];
     if (events) MB_CUDA_CHECK(cudaEventRecord(events[i], st));
@@ -687,11 +824,11 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       bool need16 = false;
       float slope16 = 1.f;
       for (int j = i + 1; j < n; ++j) {
-        if (ops[j].is_conv && ops[j].src == op.dst && ops[j].tc.use_tc) { need16 = true; slope16 = ops[j].taps.in_slope; }
+        if (ops[j].is_conv && ops[j].src == op.dst && ops[j].tc.use_tc && !reads_f32(j)) { need16 = true; slope16 = ops[j].taps.in_slope; }
         if (ops[j].is_conv && ops[j].dst == op.dst) break;
       }
-      TRef d32 = make_ref(p32[op.dst], LAYOUT_F32B, op.cout, Lout);
-      TRef s32 = make_ref(p32[op.src], LAYOUT_F32B, op.cout, Lout);
+      TRef d32 = make_ref(p32[map32[op.dst]], LAYOUT_F32B, op.cout, Lout);
+      TRef s32 = make_ref(p32[map32[op.src]], LAYOUT_F32B, op.cout, Lout);
       TRef d16 = need16 ? make_ref(p16[map16[op.dst]], LAYOUT_F16B, op.cout, Lout) : TRef{};
       if (need16) plane_slope[map16[op.dst]] = slope16;
       cudaError_t e = launch_add_inplace_f32(d32, s32, d16, slope16, B, st);
@@ -699,36 +836,17 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       count_launch();
       continue;
     }
-    // ---- fuse a resblock pair (c1 -> T -> c2) into one kernel when the channel count allows it
-    TcPairParams pp;
-    memset(&pp, 0, sizeof(pp));
-    bool fuse = false;
-    if (tc_fuse_enabled() && i + 1 < n && op.tc.use_tc && ops[i + 1].is_conv && ops[i + 1].tc.use_tc) {
-      const TcOp& c2 = ops[i + 1];
-      const TapConv& t1 = op.taps;
-      const TapConv& t2 = c2.taps;
-      const int k = t1.ntaps[0];
-      const int d1 = k > 1 ? t1.off[0][1] - t1.off[0][0] : 1;
-      bool ok = op.cin == op.cout && c2.cin == c2.cout && op.cin == c2.cin && t1.stride == 1 && t2.stride == 1 &&
-                t2.ntaps[0] == k && (k & 1) && op.res < 0 && op.dst2 < 0 && c2.dst2 < 0 && t1.mode == EPI_STORE &&
-                op.dst == c2.src && op.dst >= 0 && op.dst < nb && op.src >= 0 && op.src < nb && c2.res != op.dst &&
-                op.rate_in == c2.rate_in;
-      for (int t = 0; ok && t < k; ++t)
-        ok = (t1.off[0][t] == t * d1 - d1 * (k - 1) / 2) && (t2.off[0][t] == t - (k - 1) / 2) && t1.slab[0][t] == t &&
-             t2.slab[0][t] == t;
-      // the intermediate buffer must not be read by anything but c2 before it is overwritten
-      for (int j = i + 2; ok && j < n; ++j) {
-        const TcOp& c = ops[j];
-        if (c.src == op.dst || (c.is_conv && (c.res == op.dst || c.dst2 == op.dst))) ok = false;
-        if (c.is_conv && c.dst == op.dst && c.taps.mode == EPI_STORE) break;
-      }
-      if (ok && tc_pair_plan(op.cin, k, d1, &pp)) fuse = true;
-    }
+    // ---- fused resblock pair (c1 -> T -> c2), decided in the pre-pass above
+    TcPairParams pp = pair_plan[i];
+    const bool fuse = fuse_kind[i] != 0;
     const TcOp& oop = fuse ? ops[i + 1] : op;  // the op whose outputs this launch produces
     const char* fused_x16 = fuse ? p16[map16[op.src]] : nullptr;
     const bool use_res16 = res16_ok(oop);
     const TRef res16 = use_res16 ? make_ref(p16[map16[oop.res]], LAYOUT_F16B, oop.cout, Lout) : TRef{};
     const float res_slope = use_res16 ? plane_slope[map16[oop.res]] : 1.f;
+    const TRef res32 = (oop.res >= 0 && !use_res16) ? make_ref(p32[map32[oop.res]], LAYOUT_F32B, oop.cout, Lout) : TRef{};
+    const char* fused_x32 = (fuse_kind[i] == 2) ? p32[map32[op.src]] : nullptr;
+    if (fuse_kind[i] == 2 && oop.dst == op.src) std::swap(map32[oop.dst], map32[op.dst]);  // write the other fp32 storage
     if (fuse && oop.dst == op.src) std::swap(map16[oop.dst], map16[op.dst]);  // write the other storage
     const int scan_from = fuse ? i + 2 : i + 1;
     // ---- which planes must this op produce? (scan the consumers of dst until it is overwritten)
@@ -740,7 +858,9 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
         const TcOp& c = ops[j];
         if (c.is_conv) {
           if (c.src == buf) {
-            if (c.tc.use_tc) {
+            if (reads_f32(j)) {
+              n32 = true;
+            } else if (c.tc.use_tc) {
               if (hs && s16 != c.taps.in_slope) return fail(MB_ERR_INVALID, "tc_forward: consumers of one buffer disagree on slope");
               n16 = true;
               s16 = c.taps.in_slope;
@@ -773,7 +893,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       int rc = scan(oop.dst, need16, need32, slope16, have_slope);
       if (rc != MB_OK) return rc;
       if (oop.taps.mode != EPI_STORE) need32 = true;
-      if (need32) y32 = make_ref(p32[oop.dst], LAYOUT_F32B, oop.cout, Lout);
+      if (need32) y32 = make_ref(p32[map32[oop.dst]], LAYOUT_F32B, oop.cout, Lout);
       if (need16) {
         y16 = make_ref(p16[map16[oop.dst]], LAYOUT_F16B, oop.cout, Lout);
         if (cur16[map16[oop.dst]].C != oop.cout || cur16[map16[oop.dst]].L != Lout) {
@@ -790,17 +910,18 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       bool n16 = false, n32 = true, hs = false;
       int rc = scan(oop.dst2, n16, n32, y2_slope, hs);
       if (rc != MB_OK) return rc;
-      y2_32 = make_ref(p32[oop.dst2], LAYOUT_F32B, oop.cout, Lout);
+      y2_32 = make_ref(p32[map32[oop.dst2]], LAYOUT_F32B, oop.cout, Lout);
       if (n16) {
         y2_16 = make_ref(p16[map16[oop.dst2]], LAYOUT_F16B, oop.cout, Lout);
         plane_slope[map16[oop.dst2]] = y2_slope;
       }
     }
-    TRef res32 = (oop.res >= 0 && !use_res16) ? make_ref(p32[oop.res], LAYOUT_F32B, oop.cout, Lout) : TRef{};
     if (fuse) {
       const TcOp& c2 = ops[i + 1];
       pp.L = Lin;
       pp.x16 = reinterpret_cast<const __half*>(fused_x16);
+      pp.x32 = reinterpret_cast<const float*>(fused_x32);
+      pp.slope_in = op.taps.in_slope;
       pp.x_Lp = f16_lp(Lin);
       pp.w1 = reinterpret_cast<const __half*>(tc_arena + op.tc.w16_off);
       pp.w2 = reinterpret_cast<const __half*>(tc_arena + c2.tc.w16_off);
@@ -826,7 +947,36 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       ++i;  // c2 is done as well
       continue;
     }
-    if (op.tc.use_tc) {
+    if (op.tc.split3 && op.src == BUF_IN && y16.p && !y32.p && op.res < 0 && op.dst2 < 0) {
+      // conv_pre on the tensor cores, fp32-accurate: split the fp32 input into fp16 hi/lo planes (scratch = any
+      // other buffer's fp16 storage; all planes are dead at this point of the forward)
+      int sidx = -1;
+      const size_t need = (size_t)B * 256 * f16_lp(Lin) * 2;
+      for (int j = 0; j < nb && sidx < 0; ++j)
+        if (j != map16[op.dst] && f16_plane_bytes(B, T, bufs[j].cr) >= need + kPlaneSlack) sidx = j;
+      if (sidx < 0) return fail(MB_ERR_WORKSPACE, "tc_forward: no scratch plane for %s", op.name);
+      TRef xs = make_ref(p16[sidx], LAYOUT_F16B, 256, Lin);
+      if (cur16[sidx].C != 256 || cur16[sidx].L != Lin) {
+        cudaError_t e = launch_zero_pads_f16(xs, B, st);
+        if (e != cudaSuccess) return fail(MB_ERR_CUDA, "zero_pads: %s", cudaGetErrorString(e));
+        count_launch();
+        cur16[sidx] = xs;
+      }
+      {
+        const size_t nthr = (size_t)B * 32 * Lin;
+        split3_input_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(mel, reinterpret_cast<__half*>(p16[sidx]), B, op.cin, Lin, lengths);
+        MB_LAUNCH_CHECK("split3_input_kernel");
+      }
+      for (int hf = 0; hf < op.cout / 256; ++hf) {
+        TcOp half = op;
+        half.taps.Cin = 256;
+        half.taps.Cout = 256;
+        half.tc.w16_off = op.tc.w16_off + (size_t)hf * kernel_count(op.taps) * 4 * op.tc.slab_bytes;
+        int rc = launch_tc(half, tc_arena, xs, TRef{}, TRef{}, 1.f, TRef{}, y16, slope16, lengths, B, Lin, st, hf * 256,
+                           op.b32 ? op.b32 + hf * 256 : nullptr);
+        if (rc != MB_OK) return rc;
+      }
+    } else if (op.tc.use_tc) {
       if (op.src < 0 || op.src >= nb) return fail(MB_ERR_INVALID, "tc_forward: tensor-core layer %s reads an external buffer", op.name);
       TRef x16 = make_ref(p16[map16[op.src]], LAYOUT_F16B, op.cin, Lin);
       int rc = launch_tc(op, tc_arena, x16, res32, res16, res_slope, y32, y16, slope16, lengths, B, Lin, st);
@@ -839,7 +989,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       p.lengths = lengths;
       TapConvIO io;
       if (op.src == BUF_IN) io.x = make_ref(const_cast<float*>(mel), LAYOUT_NCL, num_mels, Lin);
-      else if (op.src >= 0 && op.src < nb) io.x = make_ref(p32[op.src], LAYOUT_F32B, op.cin, Lin);
+      else if (op.src >= 0 && op.src < nb) io.x = make_ref(p32[map32[op.src]], LAYOUT_F32B, op.cin, Lin);
       else return fail(MB_ERR_INVALID, "tc_forward: bad src");
       io.res = res32;
       io.y32 = y32;

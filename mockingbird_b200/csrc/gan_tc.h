@@ -18,6 +18,8 @@ struct TcLayer {
   int mt = 1;            // 128-row accumulator tiles per work item
   size_t slab_bytes = 0; // one (kernel index, chunk) weight image: [kc/8][Cout][8] fp16
   size_t w16_off = 0;    // byte offset of this layer's images in the tensor-core arena section
+  int split3 = 0;        // 1: fp32-accurate 3-term fp16 split (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo) of a layer whose
+                         //    input is the external fp32 tensor (conv_pre): K = 3*Cin padded to 256 channels
 };
 
 struct TcLayerDesc {
@@ -62,6 +64,11 @@ struct TcPairParams {
   int a1_stages, a2_stages;
   int tiles_per_utt, n_work;
   uint32_t a1_stage_bytes, a2_bytes, a1_off, a2_off, w1_off, w2_off, bias_off, bar_off;
+  int f32in;                 // 1: the input is the fp32 F32B plane x32 (converted on the fly), no fp16 input plane
+  uint32_t s32_stage_bytes, s32_off;
+  int s32_stages;
+  const float* x32;
+  float slope_in;            // leaky-relu applied to the input by the converter (c1's in_slope)
   const __half* x16;
   int x_Lp;
   const __half* w1;
@@ -82,7 +89,7 @@ struct TcPairParams {
   const int32_t* lengths;
   int len_mul;
 };
-bool tc_pair_plan(int C, int k, int d1, TcPairParams* p);
+bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p);
 int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st);
 
 int tc_debug_layer(const TcOp& op, const char* tc_arena, const float* x, const float* residual, int B, int Lin,

@@ -12,6 +12,12 @@
 // issue order MMA1(i+1), MMA2(i) and E1(i+1), E2(i): the tensor core always has the other phase's tile
 // to chew on while the epilogue warps drain one (all four accumulators live in TMEM: 4*MT*N <= 512).
 // Both weight sets are shared-memory resident for the whole kernel.
+//
+// F32IN variant (full-rate stage, where the residual stream must stay fp32): the pair reads ONLY the fp32
+// F32B plane.  The producer stages the window's fp32 rows in shared memory (one bulk copy per channel
+// quad, clamped to the utterance), four converter warps apply the leaky-relu, round to fp16 and write
+// the swizzled A1 operand; the residual add re-reads the same fp32 rows (L2 hits).  No fp16 plane is
+// read or written: 420 MB instead of 630 MB of HBM traffic per pair at C = 32, L = 51 200, B = 32.
 #include <cstring>
 
 #include "gan_tc.h"
@@ -26,9 +32,11 @@ using namespace tcdev;
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kCvtWarps = 2;
+constexpr int kThreadsF32 = kThreads + 32 * kCvtWarps;
 
-template <int N, int MT, int CW>
-__global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_constant__ TcPairParams p) {
+template <int N, int MT, int CW, bool F32IN>
+__global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_kernel(const __grid_constant__ TcPairParams p) {
   constexpr uint32_t ROWB = CW * 2;
   constexpr int NK16 = CW / 16;
   constexpr uint32_t MT_STEP = (128u * ROWB) >> 4;
@@ -53,15 +61,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_const
   uint64_t* a2_empty = bars + 12;      // [2]
   uint64_t* acc2_full = bars + 14;     // [2]
   uint64_t* acc2_empty = bars + 16;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* s32_full = bars + 18;      // [2]  (F32IN: fp32 staging of the input window)
+  uint64_t* s32_empty = bars + 20;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint8_t* s32_base = smem + p.s32_off;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a1_full[i], 1);
+      mbar_init(&a1_full[i], F32IN ? 32 * kCvtWarps : 1);
       mbar_init(&a1_empty[i], 1);
+      mbar_init(&s32_full[i], 1);
+      mbar_init(&s32_empty[i], 32 * kCvtWarps);
       mbar_init(&w_full[i], 1);
       mbar_init(&acc1_full[i], 1);
       mbar_init(&acc1_empty[i], 32 * kEpiWarps);
@@ -77,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < N; i += kThreads) {
+  for (int i = threadIdx.x; i < N; i += (F32IN ? kThreadsF32 : kThreads)) {
     bias1_s[i] = p.bias1[i];
     bias2_s[i] = p.bias2[i];
   }
@@ -102,13 +115,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_const
         const int work = blockIdx.x + it * gridDim.x;
         const int b = work / p.tiles_per_utt;
         const int m0 = (work - b * p.tiles_per_utt) * p.M_out;
-        const int slot = it % p.a1_stages, ph = (it / p.a1_stages) & 1;
-        mbar_wait(&a1_empty[slot], ph ^ 1);
-        const uint32_t bytes = (uint32_t)p.W1 * ROWB;
-        mbar_expect_tx(&a1_full[slot], bytes);
-        const int row0 = (kPadRows + m0 - halo) & ~7;
-        const __half* src = p.x16 + ((size_t)b * p.x_Lp + (size_t)row0) * CW;
-        bulk_g2s(smem_u32(a1_base + (size_t)slot * p.a1_stage_bytes), src, bytes, &a1_full[slot]);
+        if constexpr (F32IN) {
+          // the fp32 window is staged in two row halves (two barriers): while the converter drains one half
+          // the other half's copies are already in flight
+          const int g0 = m0 - halo;
+          const int HW = p.W1 >> 1;
+          for (int hf = 0; hf < 2; ++hf) {
+            mbar_wait(&s32_empty[hf], (it & 1) ^ 1);
+            const int r0 = g0 + hf * HW;
+            const int lo = r0 < 0 ? 0 : r0;
+            const int hi = (r0 + HW < p.L) ? r0 + HW : p.L;
+            const uint32_t qbytes = hi > lo ? (uint32_t)(hi - lo) * 16u : 0u;
+            if (qbytes == 0) {
+              mbar_arrive(&s32_full[hf]);  // nothing to copy (window past the end): complete the phase by hand
+              continue;
+            }
+            mbar_expect_tx(&s32_full[hf], qbytes * (uint32_t)(N / 4));
+            uint8_t* dst = s32_base + (size_t)hf * p.s32_stage_bytes + (size_t)(lo - r0) * 16;
+            const float* src = p.x32 + ((size_t)b * (N / 4) * p.L + (size_t)lo) * 4;
+            for (int q = 0; q < N / 4; ++q)
+              bulk_g2s(smem_u32(dst + (size_t)q * HW * 16), src + (size_t)q * p.L * 4, qbytes, &s32_full[hf]);
+          }
+        } else {
+          const int slot = it % p.a1_stages, ph = (it / p.a1_stages) & 1;
+          mbar_wait(&a1_empty[slot], ph ^ 1);
+          const uint32_t bytes = (uint32_t)p.W1 * ROWB;
+          mbar_expect_tx(&a1_full[slot], bytes);
+          const int row0 = (kPadRows + m0 - halo) & ~7;
+          const __half* src = p.x16 + ((size_t)b * p.x_Lp + (size_t)row0) * CW;
+          bulk_g2s(smem_u32(a1_base + (size_t)slot * p.a1_stage_bytes), src, bytes, &a1_full[slot]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -156,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_const
       mbar_wait(&a1_full[slot], ph);
       mbar_wait(&acc1_empty[cslot], cph ^ 1);
       tc_fence_after();
-      const int delta = (kPadRows + m0 - halo) & 7;
+      const int delta = F32IN ? 0 : ((kPadRows + m0 - halo) & 7);  // the converter writes window row 0 at smem row 0
       const uint32_t d_tmem = tmem_base + (uint32_t)(cslot * MT * N);
       const uint32_t a_addr = smem_u32(a1_base + (size_t)slot * p.a1_stage_bytes);
       if (leader) {
@@ -176,6 +212,50 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_const
       if (it > 0) mma2(it - 1);
     }
     if (n_items > 0) mma2(n_items - 1);
+  } else if (F32IN && warp >= 2 + kEpiWarps) {
+    // ===================== converter warps (F32IN): fp32 staging -> lrelu -> fp16 swizzled A1 =====================
+    const int tid = threadIdx.x - 32 * (2 + kEpiWarps);
+    for (int it = 0; it < n_items; ++it) {
+      const int work = blockIdx.x + it * gridDim.x;
+      const int b = work / p.tiles_per_utt;
+      const int m0 = (work - b * p.tiles_per_utt) * p.M_out;
+      const int valid = p.lengths ? min(p.L, p.lengths[b] * p.len_mul) : p.L;
+      const int aslot = it % p.a1_stages, aph = (it / p.a1_stages) & 1;
+      mbar_wait(&a1_empty[aslot], aph ^ 1);
+      uint8_t* a1 = a1_base + (size_t)aslot * p.a1_stage_bytes;
+      const int g0 = m0 - halo;
+      const int HW = p.W1 >> 1;
+      for (int hf = 0; hf < 2; ++hf) {
+        mbar_wait(&s32_full[hf], it & 1);
+        const uint8_t* s32 = s32_base + (size_t)hf * p.s32_stage_bytes;
+        for (int jj = tid; jj < HW; jj += 32 * kCvtWarps) {
+          const int j = hf * HW + jj;
+          const int g = g0 + j;
+          const bool live = (g >= 0 && g < valid);
+          const int sw = f16_swz(CW, j);
+#pragma unroll
+          for (int c = 0; c < N / 8; ++c) {
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (live) {
+              const float4 lo4 = *reinterpret_cast<const float4*>(s32 + ((size_t)(2 * c) * HW + jj) * 16);
+              const float4 hi4 = *reinterpret_cast<const float4*>(s32 + ((size_t)(2 * c + 1) * HW + jj) * 16);
+              __half2 h0 = __floats2half2_rn(lrelu(lo4.x, p.slope_in), lrelu(lo4.y, p.slope_in));
+              __half2 h1 = __floats2half2_rn(lrelu(lo4.z, p.slope_in), lrelu(lo4.w, p.slope_in));
+              __half2 h2 = __floats2half2_rn(lrelu(hi4.x, p.slope_in), lrelu(hi4.y, p.slope_in));
+              __half2 h3 = __floats2half2_rn(lrelu(hi4.z, p.slope_in), lrelu(hi4.w, p.slope_in));
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            }
+            *reinterpret_cast<uint4*>(a1 + (size_t)j * ROWB + ((c ^ sw) << 4)) = pk;
+          }
+        }
+        mbar_arrive(&s32_empty[hf]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.shared -> visible to the UMMA operand fetch
+      mbar_arrive(&a1_full[aslot]);
+    }
   } else {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;
@@ -234,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_const
       mbar_arrive(&acc1_empty[cslot]);
     };
 
+    constexpr int UPG = (NUNITS + 1) / 2;  // units per epilogue group
     auto e2 = [&](int it) {
       const int work = blockIdx.x + it * gridDim.x;
       const int b = work / p.tiles_per_utt;
@@ -241,7 +322,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_pair_kernel(const __grid_const
       const int valid = p.lengths ? min(p.L, p.lengths[b] * p.len_mul) : p.L;
       const int cslot = it & 1, cph = (it >> 1) & 1;
       bool waited = false;
-      for (int u = grp; u < NUNITS; u += 2) {
+#pragma unroll
+      for (int ui = 0; ui < UPG; ++ui) {
+        const int u = grp + 2 * ui;
+        if (u >= NUNITS) break;
         const int mt = u / UPT;
         const int col0 = (u - mt * UPT) << 5;
         const int i = mt * 128 + row_in_tile;
@@ -354,8 +438,9 @@ constexpr uint32_t kSmemMax = 227 * 1024;
 
 }  // namespace
 
-bool tc_pair_plan(int C, int k, int d1, TcPairParams* p) {
+bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
   if (C != 64 && C != 32) return false;
+  if (f32in && C != 32) return false;  // instance list below
   const int row_bytes = C * 2;
   const int h1 = d1 * (k - 1) / 2, h2 = (k - 1) / 2;
   if (h1 + h2 > kPadRows) return false;
@@ -363,14 +448,24 @@ bool tc_pair_plan(int C, int k, int d1, TcPairParams* p) {
   const uint32_t wbytes = (uint32_t)align_up((size_t)k * slab, 1024);
   const uint32_t usable = kSmemMax - 1024;
   const int mt_max = (C == 64) ? 2 : 4;  // 4 accumulators of MT*N columns in 512 TMEM columns
+  // stage counts tried per tile count, best first: (fp32 staging, A1, A2).  Large tiles matter more than
+  // deep rings: the per-item dependency chain (load -> [convert] -> MMA1 -> E1 -> MMA2 -> E2) is a fixed
+  // latency, so fewer, bigger items amortise it.
+  static const int kTry16[][3] = {{0, 2, 2}, {0, 2, 1}, {0, 1, 1}};
+  static const int kTry32[][3] = {{1, 2, 2}, {1, 2, 1}, {1, 1, 1}, {1, 1, 1}};  // fp32 staging: one window, two row halves
   for (int mt = mt_max; mt >= 1; mt >>= 1) {
-    for (int stages = 2; stages >= 1; --stages) {
-      const int W1 = (mt * 128 + 2 * h1 + 7 + 7) & ~7;
+    for (int v = 0; v < (f32in ? 4 : 3); ++v) {
+      const int* st = f32in ? kTry32[v] : kTry16[v];
+      const int W1 = f32in ? ((mt * 128 + 2 * h1 + 15) & ~15) : ((mt * 128 + 2 * h1 + 7 + 7) & ~7);
       const int W2 = (mt * 128 + 16 + 7) & ~7;
       const uint32_t a1b = (uint32_t)align_up((size_t)W1 * row_bytes, 1024);
       const uint32_t a2b = (uint32_t)align_up((size_t)W2 * row_bytes, 1024);
-      const uint32_t total = stages * a1b + stages * a2b + 2 * wbytes + 1024 + 1024;
+      const uint32_t s32b = f32in ? (uint32_t)align_up((size_t)(W1 / 2) * C * 4, 1024) : 0u;  // one row half (W1 % 16 == 0 below)
+      const uint32_t total = 2 * s32b + st[1] * a1b + st[2] * a2b + 2 * wbytes + 1024 + 1024;
       if (total > usable) continue;
+      p->f32in = f32in ? 1 : 0;
+      p->s32_stage_bytes = s32b;
+      p->s32_stages = st[0] > 0 ? st[0] : 1;
       p->C = C;
       p->k = k;
       p->d1 = d1;
@@ -380,16 +475,17 @@ bool tc_pair_plan(int C, int k, int d1, TcPairParams* p) {
       p->M_out = mt * 128 - 2 * h2;
       p->W1 = W1;
       p->W2 = W2;
-      p->a1_stages = stages;
-      p->a2_stages = stages;
+      p->a1_stages = st[1];
+      p->a2_stages = st[2];
       p->a1_stage_bytes = a1b;
       p->a2_bytes = a2b;
       p->a1_off = 0;
-      p->a2_off = stages * a1b;
-      p->w1_off = p->a2_off + stages * a2b;
+      p->a2_off = st[1] * a1b;
+      p->w1_off = p->a2_off + st[2] * a2b;
       p->w2_off = p->w1_off + wbytes;
       p->bias_off = p->w2_off + wbytes;
       p->bar_off = p->bias_off + 1024;
+      p->s32_off = p->bar_off + 1024;
       return true;
     }
   }
@@ -400,12 +496,16 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
   p.tiles_per_utt = (p.L + p.M_out - 1) / p.M_out;
   p.n_work = B * p.tiles_per_utt;
   void (*kern)(const TcPairParams) = nullptr;
-  if (p.C == 64 && p.MT == 2) kern = tc_pair_kernel<64, 2, 64>;
-  else if (p.C == 64 && p.MT == 1) kern = tc_pair_kernel<64, 1, 64>;
-  else if (p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32>;
-  else if (p.C == 32 && p.MT == 2) kern = tc_pair_kernel<32, 2, 32>;
-  else if (p.C == 32 && p.MT == 1) kern = tc_pair_kernel<32, 1, 32>;
-  else return fail(MB_ERR_INVALID, "tc_pair: no kernel instance for C=%d MT=%d", p.C, p.MT);
+  if (p.f32in && p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32, true>;
+  else if (p.f32in && p.C == 32 && p.MT == 2) kern = tc_pair_kernel<32, 2, 32, true>;
+  else if (p.f32in && p.C == 32 && p.MT == 1) kern = tc_pair_kernel<32, 1, 32, true>;
+  else if (p.f32in) kern = nullptr;
+  else if (p.C == 64 && p.MT == 2) kern = tc_pair_kernel<64, 2, 64, false>;
+  else if (p.C == 64 && p.MT == 1) kern = tc_pair_kernel<64, 1, 64, false>;
+  else if (p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32, false>;
+  else if (p.C == 32 && p.MT == 2) kern = tc_pair_kernel<32, 2, 32, false>;
+  else if (p.C == 32 && p.MT == 1) kern = tc_pair_kernel<32, 1, 32, false>;
+  if (!kern) return fail(MB_ERR_INVALID, "tc_pair: no kernel instance for C=%d MT=%d f32in=%d", p.C, p.MT, p.f32in);
   MB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -415,7 +515,7 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(p.f32in ? kThreadsF32 : kThreads);
   cfg.dynamicSmemBytes = kSmemMax;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
