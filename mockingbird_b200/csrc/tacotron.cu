@@ -8,6 +8,7 @@
 // Activations are channels-last [rows][features]; Conv1d over time = shifted-row GEMM segments.
 #include "tacotron_kernels.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -213,6 +214,7 @@ struct mb_tacotron {
   float* arena = nullptr;
   bool finalized = false;
   int packed_r = 0;
+  float tc_inv_scale[2] = {1.f, 1.f};  // tensor-core LSTM weights: 1 / pack scale per layer
 };
 
 namespace {
@@ -259,7 +261,7 @@ struct Ws {
   // encoder
   size_t ids, emb, m_enc, p1, x0, bank, pool, pj1, y, hw12, gi_f, gi_b, gh, hst, seq, proj, style_q, style;
   // decoder
-  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, stopv, flags, dmask;
+  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, stopv, flags, dmask;
   // outputs / postnet
   size_t mel_all, scores_all, pbank, ppool, ppj1, ppj2, py, phw12, pgi_f, pgi_b, pgh, phst, pout, lin;
   size_t total;
@@ -307,6 +309,8 @@ Ws ws_layout(const mb_tacotron_config& c, int B, int Tc, int steps, int r) {
   L.pq = take((size_t)B * c.decoder_dims);
   L.x = take((size_t)B * c.lstm_dims);
   L.gates = take((size_t)B * 4 * c.lstm_dims);
+  L.a_hi = take(tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * c.lstm_dims) / 4);
+  L.a_lo = take(tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * c.lstm_dims) / 4);
   L.stopv = take(B);
   const int nst = (steps + r - 1) / r;
   L.flags = take(nst);
@@ -513,6 +517,8 @@ int mb_tacotron_create(const mb_tacotron_config* cfg, mb_tacotron** out) {
     slot(h, std::string(n) + ".bias_ih", 4 * c.lstm_dims);
     slot(h, std::string(n) + ".bias_hh", 4 * c.lstm_dims);
     slot(h, std::string(n) + ".bias_sum", 4 * c.lstm_dims);  // derived: b_hh + b_ih
+    slot(h, std::string(n) + ".tcw", tc_skinny_weight_bytes(4 * c.lstm_dims, 2 * c.lstm_dims) / 4);  // derived: hi/lo tiles
+    slot(h, std::string(n) + ".tcb", 4 * c.lstm_dims);                                                // derived: tile-order bias
   }
   slot(h, "decoder.mel_proj.weight", (size_t)c.n_mels * c.max_r * c.lstm_dims);
   slot(h, "decoder.mel_proj.packed", (size_t)c.n_mels * c.max_r * c.lstm_dims);  // derived for the current r
@@ -559,7 +565,8 @@ int mb_tacotron_finalize(mb_tacotron* h, void* stream) {
   auto derived = [](const std::string& n) {
     return n.find(".bn_scale") != std::string::npos || n.find(".bn_shift") != std::string::npos ||
            n.find(".W12") != std::string::npos || n.find(".b12") != std::string::npos || n == "gst.tanh_embed" ||
-           n == "gst.keys" || n == "gst.values" || n.find(".bias_sum") != std::string::npos ||
+           n == "gst.keys" || n == "gst.values" || n.find(".bias_sum") != std::string::npos || n.find(".tcw") != std::string::npos ||
+           n.find(".tcb") != std::string::npos ||
            n == "decoder.mel_proj.packed";
   };
   for (auto& kv : h->slots)
@@ -602,6 +609,35 @@ int mb_tacotron_finalize(mb_tacotron* h, void* stream) {
                        P(h, "gst.values"), c.gst_E);
     TK(launch_gemm(b, st));
   }
+  // tensor-core images of the two residual LSTMs: [W_ih | W_hh] gate-interleaved, scaled by a power of two so that
+  // max |w| lands near 2^12 (the lo parts of the fp16 split then stay clear of the subnormal range)
+  {
+    unsigned int* dmax = nullptr;
+    MB_CUDA_CHECK(cudaMalloc(&dmax, 2 * sizeof(unsigned int)));
+    MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, 2 * sizeof(unsigned int), st));
+    const size_t nw = (size_t)4 * c.lstm_dims * c.lstm_dims;
+    const char* names[2] = {"decoder.res_rnn1", "decoder.res_rnn2"};
+    for (int l = 0; l < 2; ++l) {
+      TK(tc_skinny_absmax(P(h, std::string(names[l]) + ".weight_ih"), nw, dmax + l, st));
+      TK(tc_skinny_absmax(P(h, std::string(names[l]) + ".weight_hh"), nw, dmax + l, st));
+    }
+    unsigned int hmax[2] = {0, 0};
+    MB_CUDA_CHECK(cudaMemcpyAsync(hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    MB_CUDA_CHECK(cudaFree(dmax));
+    for (int l = 0; l < 2; ++l) {
+      float mx;
+      memcpy(&mx, &hmax[l], sizeof(float));
+      int e = 0;
+      if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+      const float scale = ldexpf(1.f, 12 - e);
+      h->tc_inv_scale[l] = 1.f / scale;
+      const std::string n = names[l];
+      TK(tc_skinny_pack(P(h, n + ".weight_ih"), c.lstm_dims, P(h, n + ".weight_hh"), c.lstm_dims, P(h, n + ".bias_ih"),
+                        P(h, n + ".bias_hh"), 4 * c.lstm_dims, c.lstm_dims, scale, reinterpret_cast<__half*>(P(h, n + ".tcw")),
+                        P(h, n + ".tcb"), st));
+    }
+  }
   h->packed_r = 0;
   h->finalized = true;
   return MB_OK;
@@ -629,6 +665,12 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   float* ws = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   cudaStream_t st = (cudaStream_t)stream;
   const int E = c.encoder_dims, D = c.decoder_dims, LD = c.lstm_dims, PD = c.postnet_dims, NM = c.n_mels;
+  // MB_TACO_TC=0 keeps the decoder LSTMs on the FP32 FFMA kernels (A/B measurements); batches > 128 rows always do
+  static const bool tc_env = [] {
+    const char* e = getenv("MB_TACO_TC");
+    return e ? atoi(e) != 0 : true;
+  }();
+  const bool use_tc = tc_env && B <= 128 && LD % 64 == 0;
   const int SE = c.speaker_embedding_size, proj_dims = E + SE + c.gst_E;
   const int Me = B * Tc;
 
@@ -784,6 +826,29 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       const std::string n = l == 0 ? "decoder.res_rnn1" : "decoder.res_rnn2";
       float* hh = ws + (l == 0 ? L.h1 : L.h2);
       float* cc = ws + (l == 0 ? L.c1 : L.c2);
+      if (use_tc) {
+        // gates GEMM on the tensor cores (3-term fp16 split, FP32 accumulate) with the cell update fused
+        __half* a_hi = reinterpret_cast<__half*>(ws + L.a_hi);
+        __half* a_lo = reinterpret_cast<__half*>(ws + L.a_lo);
+        TK(launch_act_split(ws + L.x, LD, LD, hh, LD, LD, B, a_hi, a_lo, st));
+        TcSkinnyArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.a_hi = a_hi;
+        ta.a_lo = a_lo;
+        ta.w = reinterpret_cast<const __half*>(P(h, n + ".tcw"));
+        ta.bias = P(h, n + ".tcb");
+        ta.KB = 2 * LD / 64;
+        ta.M = B;
+        ta.N = 4 * LD;
+        ta.mode = TCS_LSTM;
+        ta.inv_scale = h->tc_inv_scale[l];
+        ta.c = cc;
+        ta.h = hh;
+        ta.x = ws + L.x;
+        ta.H = LD;
+        TK(launch_tc_skinny(ta, st));
+        continue;
+      }
       GemmArgs a;
       memset(&a, 0, sizeof(a));
       // gates = linear_hh(h) + linear_ih(x): two GEMMs chained through the residual input of the second

@@ -8,6 +8,7 @@
 // and epi = bias, activation, eval-BatchNorm affine (applied AFTER the ReLU like
 // common/batch_norm_conv.py:11-14), PreNet dropout mask, residual.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -60,6 +61,34 @@ cudaError_t launch_embedding(const int32_t* ids, const float* table, float* y, i
 // dst[m][off + j] = src[(m / rows_per_src)][j]  (broadcast a per-sequence vector along time) or row copy
 cudaError_t launch_copy_cols(const float* src, int ldsrc, int rows_per_src, float* dst, int lddst, int off, int M,
                              int n, cudaStream_t st);
+
+// ---- tensor-core skinny GEMM (tacotron_tc.cu): Y[M <= 128][N] = A[M][K] . W[N][K]^T as a 3-term fp16 split with
+// FP32 accumulation (FP32-equivalent), one CTA per 32 output columns ------------------------------------
+enum TcSkinnyMode : int { TCS_PLAIN = 0, TCS_LSTM = 1 };
+struct TcSkinnyArgs {
+  const __half* a_hi;   // activation tiles [K/64][rows_pad][64] (launch_act_split)
+  const __half* a_lo;
+  const __half* w;      // packed weight tiles (tc_skinny_pack)
+  const float* bias;    // packed bias [ceil32(N)] or nullptr
+  int KB, M, N, rows_pad, mode;
+  float inv_scale;      // 1 / (power-of-two weight scale used at pack time)
+  float* y;             // TCS_PLAIN: out [M][ldy]
+  int ldy;
+  float* c;             // TCS_LSTM: cell state [M][H] in/out, h [M][H] out, x [M][H] += h (residual, tacotron.py:121,126)
+  float* h;
+  float* x;
+  int H;
+};
+size_t tc_skinny_weight_bytes(int N, int K);
+size_t tc_skinny_act_bytes(int M, int K);
+// max |w| into *dev_out (uint bit pattern of a non-negative float; caller zeroes it first)
+cudaError_t tc_skinny_absmax(const float* w, size_t n, unsigned int* dev_out, cudaStream_t st);
+// weights [N][K0 | K1] (two row-major sources) * scale -> hi/lo tiles; lstm_H > 0: gate-interleaved rows
+cudaError_t tc_skinny_pack(const float* w0, int K0, const float* w1, int K1, const float* b0, const float* b1, int N,
+                           int lstm_H, float scale, __half* w_dst, float* bias_dst, cudaStream_t st);
+cudaError_t launch_act_split(const float* s0, int K0, int ld0, const float* s1, int K1, int ld1, int M, __half* a_hi,
+                             __half* a_lo, cudaStream_t st);
+cudaError_t launch_tc_skinny(const TcSkinnyArgs& a, cudaStream_t st);
 
 }  // namespace taco
 }  // namespace mb

@@ -1,0 +1,303 @@
+// Tensor-core GEMMs of the Tacotron decoder step (sm_100a: tcgen05 / TMEM / bulk-TMA), FP32-accurate.
+//
+// The decoder's LSTM cells (tacotron.py:118-127: two LSTMCell(1024) with residuals) are 84 % of the
+// per-step MACs with only batch-many (<= 128) rows: Y[M][4H] = [x | h] . [W_ih | W_hh]^T.  FP32 FFMA
+// kernels are compute-bound there at ~7 TFLOP/s; the tensor cores need fp16 operands, which alone would
+// break the 1e-3 parity bar after 200 recurrent steps.  So every product is computed as a 3-term split
+//     a*w ~= hi(a)*hi(w) + lo(a)*hi(w) + hi(a)*lo(w),   hi(v) = fp16(v), lo(v) = fp16(v - hi(v))
+// with FP32 accumulation in TMEM: ~2^-21 relative per product, i.e. FP32-equivalent (weights are
+// pre-scaled by a power of two so that their lo parts stay out of the fp16 subnormal range).
+//
+//   grid      : one CTA per 32 output columns (LSTM: the 4 gates of 8 hidden units, interleaved at pack
+//               time, so the cell update c' = f*c + i*g, h' = o*tanh(c') runs in the epilogue)
+//   operands  : K-major SWIZZLE_128B tiles of 64 k: activations [K/64][rows_pad][64] (hi and lo, written
+//               by act_split_kernel), weights [tile][K/64][hi|lo][32][64]; each tile is one bulk copy
+//   pipeline  : warp 0 producer (4-stage ring), warp 1 MMA issuer (12 MMAs M128 x N32 x K16 per stage),
+//               warps 2-5 epilogue (TMEM lane = batch row)
+#include <cuda_fp16.h>
+
+#include <cstring>
+
+#include "gan_tc_dev.cuh"
+#include "tacotron_kernels.cuh"
+
+namespace mb {
+namespace taco {
+
+namespace {
+
+using namespace tcdev;
+
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr uint32_t kATile = 16384;  // 128 rows x 128 B (rows >= rows_pad stay zero)
+constexpr uint32_t kWTile = 4096;   // 32 rows x 128 B
+constexpr uint32_t kStageBytes = 2 * kATile + 2 * kWTile;
+
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_constant__ TcSkinnyArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* acc_full = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kStages + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const uint32_t a_bytes = (uint32_t)p.rows_pad * 128u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < 32) bias_s[threadIdx.x] = p.bias ? p.bias[tile * 32 + threadIdx.x] : 0.f;
+  if (p.rows_pad < 128) {
+    // rows [rows_pad, 128) of every A slot are never written by the copies: zero them once
+    for (int s = 0; s < 2 * kStages; ++s) {
+      uint8_t* slot = smem + (size_t)(s >> 1) * kStageBytes + (size_t)(s & 1) * kATile + a_bytes;
+      for (uint32_t i = threadIdx.x * 16u; i < kATile - a_bytes; i += kThreads * 16u)
+        *reinterpret_cast<uint4*>(slot + i) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.w) + (size_t)tile * p.KB * (2 * kWTile);
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const int s = kb % kStages, ph = (kb / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * kStageBytes;
+        mbar_expect_tx(&full[s], 2 * a_bytes + 2 * kWTile);
+        bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(p.a_hi) + (size_t)kb * a_bytes, a_bytes, &full[s]);
+        bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(p.a_lo) + (size_t)kb * a_bytes, a_bytes, &full[s]);
+        bulk_g2s(smem_u32(st + 2 * kATile), wt + (size_t)kb * (2 * kWTile), 2 * kWTile, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t desc_hi = make_desc(0, 1024u, 2u, 0);
+    const bool leader = elect_one();
+    for (int kb = 0; kb < p.KB; ++kb) {
+      const int s = kb % kStages, ph = (kb / kStages) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
+      const uint64_t ah = desc_hi + (uint64_t)(base >> 4);
+      const uint64_t al = desc_hi + (uint64_t)((base + kATile) >> 4);
+      const uint64_t wh = desc_hi + (uint64_t)((base + 2 * kATile) >> 4);
+      const uint64_t wl = desc_hi + (uint64_t)((base + 2 * kATile + kWTile) >> 4);
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          tc_mma_f16(tmem_base, ah + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          tc_mma_f16(tmem_base, al + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, 1u);
+          tc_mma_f16(tmem_base, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u);
+        }
+        tc_commit(&empty[s]);
+      }
+    }
+    if (leader) tc_commit(acc_full);
+  } else {
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    uint32_t raw[32];
+    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16), raw);
+    if (m < p.M) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.inv_scale + bias_s[i];
+      if (p.mode == TCS_LSTM) {
+        const size_t o = (size_t)m * p.H + (size_t)tile * 8;
+        float cn[8], hn[8], xn[8];
+        const float4 c0 = *reinterpret_cast<const float4*>(p.c + o), c1 = *reinterpret_cast<const float4*>(p.c + o + 4);
+        const float co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float4 x0 = *reinterpret_cast<const float4*>(p.x + o), x1 = *reinterpret_cast<const float4*>(p.x + o + 4);
+        const float xo[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float ig = sigm(v[e]), fg = sigm(v[8 + e]), cg = tanhf(v[16 + e]), og = sigm(v[24 + e]);
+          cn[e] = fg * co[e] + ig * cg;
+          hn[e] = og * tanhf(cn[e]);
+          xn[e] = xo[e] + hn[e];
+        }
+        *reinterpret_cast<float4*>(p.c + o) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        *reinterpret_cast<float4*>(p.c + o + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+        *reinterpret_cast<float4*>(p.h + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        *reinterpret_cast<float4*>(p.h + o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        *reinterpret_cast<float4*>(p.x + o) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+        *reinterpret_cast<float4*>(p.x + o + 4) = make_float4(xn[4], xn[5], xn[6], xn[7]);
+      } else {
+        float* y = p.y + (size_t)m * p.ldy + (size_t)tile * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          if (tile * 32 + i < p.N) *reinterpret_cast<float4*>(y + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+  }
+}
+
+__device__ __forceinline__ __half split_hi(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ __half split_lo(float v) { return __float2half_rn(v - __half2float(__float2half_rn(v))); }
+
+// activations [M][K0 | K1] fp32 -> hi / lo operand tiles [KB][rows_pad][64] (16-byte chunks XOR (row & 7))
+__global__ void act_split_kernel(const float* __restrict__ s0, int K0, int ld0, const float* __restrict__ s1, int K1, int ld1,
+                                 int M, int rows_pad, int KB, __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 8 consecutive k of one row
+  const int n = KB * rows_pad * 8;
+  if (i >= n) return;
+  const int c8 = i & 7;
+  const int m = (i >> 3) % rows_pad;
+  const int kb = i / (8 * rows_pad);
+  __align__(16) __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kb * 64 + c8 * 8 + e;
+    float v = 0.f;
+    if (m < M) {
+      if (k < K0) v = s0[(size_t)m * ld0 + k];
+      else if (k < K0 + K1) v = s1[(size_t)m * ld1 + (k - K0)];
+    }
+    hi[e] = split_hi(v);
+    lo[e] = split_lo(v);
+  }
+  const size_t o = ((size_t)kb * rows_pad + m) * 8 + (size_t)(c8 ^ (m & 7));
+  reinterpret_cast<uint4*>(a_hi)[o] = *reinterpret_cast<const uint4*>(hi);
+  reinterpret_cast<uint4*>(a_lo)[o] = *reinterpret_cast<const uint4*>(lo);
+}
+
+// weights -> tiles [tile][KB][hi|lo][32][64].  Row n of tile j is source row
+//   lstm_H > 0 : (n / 8) * lstm_H + 8 j + (n % 8)   (gate-interleaved: i,f,g,o of 8 units)
+//   else       : 32 j + n  (rows >= N are zero)
+// and its K axis is [w0 (K0 columns) | w1 (K1 columns)], zero padded to 64 KB.
+__global__ void pack_split_w_kernel(const float* __restrict__ w0, int K0, const float* __restrict__ w1, int K1, int N,
+                                    int lstm_H, int KB, float scale, __half* __restrict__ dst) {
+  const size_t n_tiles = (size_t)(N + 31) / 32;
+  const size_t total = n_tiles * KB * 32 * 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i & 7);
+  const int n = (int)((i >> 3) & 31);
+  const int kb = (int)((i >> 8) % KB);
+  const int j = (int)(i / ((size_t)256 * KB));
+  const int row = lstm_H > 0 ? (n / 8) * lstm_H + 8 * j + (n % 8) : 32 * j + n;
+  __align__(16) __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kb * 64 + c8 * 8 + e;
+    float v = 0.f;
+    if (row < N) {
+      if (k < K0) v = w0[(size_t)row * K0 + k];
+      else if (k < K0 + K1) v = w1[(size_t)row * K1 + (k - K0)];
+    }
+    v *= scale;
+    hi[e] = split_hi(v);
+    lo[e] = split_lo(v);
+  }
+  const size_t t = ((size_t)j * KB + kb) * 2;
+  const size_t o = (size_t)n * 8 + (size_t)(c8 ^ (n & 7));
+  reinterpret_cast<uint4*>(dst)[(t + 0) * 256 + o] = *reinterpret_cast<const uint4*>(hi);
+  reinterpret_cast<uint4*>(dst)[(t + 1) * 256 + o] = *reinterpret_cast<const uint4*>(lo);
+}
+
+// bias in tile order (LSTM: gate-interleaved b_ih + b_hh)
+__global__ void pack_split_bias_kernel(const float* __restrict__ b0, const float* __restrict__ b1, int N, int lstm_H,
+                                       float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_pad = (N + 31) / 32 * 32;
+  if (i >= n_pad) return;
+  const int j = i / 32, n = i % 32;
+  const int row = lstm_H > 0 ? (n / 8) * lstm_H + 8 * j + (n % 8) : i;
+  float v = 0.f;
+  if (row < N) v = (b0 ? b0[row] : 0.f) + (b1 ? b1[row] : 0.f);
+  dst[i] = v;
+}
+
+__global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));  // non-negative floats order like their bit patterns
+}
+
+}  // namespace
+
+size_t tc_skinny_weight_bytes(int N, int K) {
+  const size_t n_tiles = (size_t)(N + 31) / 32, KB = (size_t)(K + 63) / 64;
+  return n_tiles * KB * 2 * kWTile;
+}
+
+size_t tc_skinny_act_bytes(int M, int K) {
+  const size_t KB = (size_t)(K + 63) / 64;
+  return KB * (size_t)(M <= 64 ? 64 : 128) * 128;
+}
+
+cudaError_t tc_skinny_absmax(const float* w, size_t n, unsigned int* dev_out, cudaStream_t st) {
+  absmax_kernel<<<148, 256, 0, st>>>(w, n, dev_out);
+  return cudaGetLastError();
+}
+
+cudaError_t tc_skinny_pack(const float* w0, int K0, const float* w1, int K1, const float* b0, const float* b1, int N,
+                           int lstm_H, float scale, __half* w_dst, float* bias_dst, cudaStream_t st) {
+  const int KB = (K0 + K1 + 63) / 64;
+  const size_t total = (size_t)((N + 31) / 32) * KB * 256;
+  pack_split_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w0, K0, w1, K1, N, lstm_H, KB, scale, w_dst);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int n_pad = (N + 31) / 32 * 32;
+  pack_split_bias_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(b0, b1, N, lstm_H, bias_dst);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_act_split(const float* s0, int K0, int ld0, const float* s1, int K1, int ld1, int M, __half* a_hi,
+                             __half* a_lo, cudaStream_t st) {
+  const int KB = (K0 + K1 + 63) / 64;
+  const int rows_pad = M <= 64 ? 64 : 128;
+  const int n = KB * rows_pad * 8;
+  act_split_kernel<<<(n + 255) / 256, 256, 0, st>>>(s0, K0, ld0, s1, K1, ld1, M, rows_pad, KB, a_hi, a_lo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_skinny(const TcSkinnyArgs& a, cudaStream_t st) {
+  if (a.M <= 0 || a.M > 128 || a.N <= 0 || a.KB <= 0) return cudaErrorInvalidValue;
+  TcSkinnyArgs p = a;
+  p.rows_pad = a.M <= 64 ? 64 : 128;
+  constexpr size_t smem = kStages * kStageBytes + 1024 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  tc_skinny_kernel<<<(a.N + 31) / 32, kThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace taco
+}  // namespace mb
