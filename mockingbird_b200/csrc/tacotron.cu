@@ -37,16 +37,21 @@ __global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__
                                                        float* __restrict__ scores_out, int scores_ld, float* ctx, int Tc) {
   extern __shared__ float sm[];
   float* s_cw = sm;                         // [32][31]
-  float* s_L = s_cw + ATT_F * ATT_K;        // [128][32]
-  float* s_v = s_L + ATT_D * ATT_F;         // [128]
+  float* s_Lt = s_cw + ATT_F * ATT_K;       // [32][128]  (L transposed: conflict-free for d-major threads)
+  float* s_v = s_Lt + ATT_D * ATT_F;        // [128]
   float* s_pq = s_v + ATT_D;                // [128]
   float* s_cb = s_pq + ATT_D;               // [32]
   float* s_cum = s_cb + ATT_F;              // [Tc + 30] zero padded
   float* s_u = s_cum + Tc + 2 * 15;         // [Tc]
   float* s_red = s_u + Tc;                  // [32]
+  float* s_loc = s_red + 32;                // [Tc][32]
+  float* s_part = s_loc + (size_t)Tc * ATT_F;  // [Tc][4]
   const int b = blockIdx.x, tid = threadIdx.x;
   for (int i = tid; i < ATT_F * ATT_K; i += blockDim.x) s_cw[i] = conv_w[i];
-  for (int i = tid; i < ATT_D * ATT_F; i += blockDim.x) s_L[i] = Lw[i];
+  for (int i = tid; i < ATT_D * ATT_F; i += blockDim.x) {
+    const int d = i / ATT_F, f = i - d * ATT_F;
+    s_Lt[f * ATT_D + d] = Lw[i];
+  }
   for (int i = tid; i < ATT_D; i += blockDim.x) {
     s_v[i] = vw[i];
     s_pq[i] = pq[(size_t)b * ATT_D + i];
@@ -57,22 +62,35 @@ __global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__
     s_cum[i] = (t >= 0 && t < Tc) ? cum[(size_t)b * Tc + t] : 0.f;
   }
   __syncthreads();
-  for (int t = tid; t < Tc; t += blockDim.x) {
-    float loc[ATT_F];
-#pragma unroll 4
-    for (int f = 0; f < ATT_F; ++f) {
-      float a = 0.f;
-      for (int j = 0; j < ATT_K; ++j) a = fmaf(s_cw[f * ATT_K + j], s_cum[t + j], a);
-      loc[f] = a + s_cb[f];
-    }
-    const float* pr = proj + ((size_t)b * Tc + t) * ATT_D;
-    float u = 0.f;
-    for (int d = 0; d < ATT_D; ++d) {
-      float pl = 0.f;
+  // location features loc[t][f] = conv1d(cumulative, k = 31)[t] + bias: one (t, f) per thread and pass
+  for (int i = tid; i < Tc * ATT_F; i += blockDim.x) {
+    const int t = i >> 5, f = i & 31;
+    float a = 0.f;
 #pragma unroll
-      for (int f = 0; f < ATT_F; ++f) pl = fmaf(s_L[d * ATT_F + f], loc[f], pl);
-      u = fmaf(s_v[d], tanhf(s_pq[d] + pr[d] + pl), u);
+    for (int j = 0; j < ATT_K; ++j) a = fmaf(s_cw[f * ATT_K + j], s_cum[t + j], a);
+    s_loc[i] = a + s_cb[f];
+  }
+  __syncthreads();
+  // energies: thread = (d, t parity); u[t] = sum_d v[d] * tanh(pq[d] + proj[t][d] + sum_f L[d][f] loc[t][f])
+  {
+    const int d = tid & (ATT_D - 1), tg = tid >> 7, wq = (tid >> 5) & 3;
+    float lreg[ATT_F];
+#pragma unroll
+    for (int f = 0; f < ATT_F; ++f) lreg[f] = s_Lt[f * ATT_D + d];
+    const float vd = s_v[d], pqd = s_pq[d];
+    for (int t = tg; t < Tc; t += 2) {
+      float pl = 0.f;
+      const float* lc = s_loc + (size_t)t * ATT_F;
+#pragma unroll
+      for (int f = 0; f < ATT_F; ++f) pl = fmaf(lreg[f], lc[f], pl);
+      float e = vd * tanhf(pqd + proj[((size_t)b * Tc + t) * ATT_D + d] + pl);
+      for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      if ((tid & 31) == 0) s_part[t * 4 + wq] = e;
     }
+  }
+  __syncthreads();
+  for (int t = tid; t < Tc; t += blockDim.x) {
+    const float u = (s_part[t * 4 + 0] + s_part[t * 4 + 1]) + (s_part[t * 4 + 2] + s_part[t * 4 + 3]);
     s_u[t] = chars[(size_t)b * Tc + t] != 0 ? u : 0.f;  // u * (chars != 0): padded positions score exp(0)
   }
   __syncthreads();
@@ -214,7 +232,7 @@ struct mb_tacotron {
   float* arena = nullptr;
   bool finalized = false;
   int packed_r = 0;
-  float tc_inv_scale[2] = {1.f, 1.f};  // tensor-core LSTM weights: 1 / pack scale per layer
+  std::map<std::string, float> tc_inv_scale;  // tensor-core weight images: 1 / pack scale per tensor
 };
 
 namespace {
@@ -254,6 +272,9 @@ void cbhg_slots(mb_tacotron* h, const std::string& p, int K, int cin, int ch, in
     slot(h, p + ".rnn.weight_hh_l0" + sfx, (size_t)3 * (ch / 2) * (ch / 2));
     slot(h, p + ".rnn.bias_ih_l0" + sfx, (size_t)3 * (ch / 2));
     slot(h, p + ".rnn.bias_hh_l0" + sfx, (size_t)3 * (ch / 2));
+    // derived: tensor-core images of W_hh (gates r|z|n interleaved per 8 units) + tile-order b_hh
+    slot(h, p + ".rnn.hh" + sfx + ".tcw", tc_gated_weight_bytes(ch / 2, ch / 2) / 4);
+    slot(h, p + ".rnn.hh" + sfx + ".tcb", (size_t)4 * (ch / 2));
   }
 }
 
@@ -361,7 +382,8 @@ GemmArgs gemm1(const float* x, int K, int ld, const float* W, int ldw, const flo
 // CBHG (sublayer/cbhg.py:42-79) on x [B*T][cin] channels-last -> out [B*T][ch] written at out (ld ldout)
 int run_cbhg(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p0, int p1, int nh, const float* x, int B,
              int T, float* bank, float* pool, float* pj1, float* y, float* hw12, float* gi_f, float* gi_b, float* gh,
-             float* hst, float* out, int ldout, cudaStream_t st) {
+             float* hst, float* out, int ldout, cudaStream_t st, float* tc_hi = nullptr, float* tc_lo = nullptr,
+             size_t tc_bytes = 0) {
   const int M = B * T;
   // convolution bank: k = 1..K, "same" padding k//2 cropped to T, ReLU then BatchNorm
   for (int i = 0; i < K; ++i) {
@@ -445,6 +467,47 @@ int run_cbhg(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p
                        gi_b, 3 * H);
     TK(launch_gemm(b, st));
   }
+  const size_t tile_bytes = tc_skinny_act_bytes(B, H);
+  if (tc_hi && tc_lo && B <= 128 && H % 64 == 0 && 4 * tile_bytes <= tc_bytes) {
+    // recurrences on the tensor cores: one launch per time step covers both directions; the epilogue applies
+    // the GRU cell and writes h_t straight into the next step's operand tiles (ping-pong)
+    MB_CUDA_CHECK(cudaMemsetAsync(hst, 0, sizeof(float) * 2 * B * H, st));
+    MB_CUDA_CHECK(cudaMemsetAsync(tc_hi, 0, 4 * tile_bytes, st));
+    MB_CUDA_CHECK(cudaMemsetAsync(tc_lo, 0, 4 * tile_bytes, st));
+    auto tile = [&](float* base, int dir, int par) {
+      return reinterpret_cast<__half*>(reinterpret_cast<char*>(base) + (size_t)(dir * 2 + par) * tile_bytes);
+    };
+    TcGruArgs g;
+    memset(&g, 0, sizeof(g));
+    g.ldgi = T * 3 * H;
+    g.ldout = T * ldout;
+    g.KB = H / 64;
+    g.M = B;
+    g.H = H;
+    g.ndir = 2;
+    const char* sfx[2] = {"", "_reverse"};
+    for (int d = 0; d < 2; ++d) {
+      g.w[d] = reinterpret_cast<const __half*>(P(h, p + ".rnn.hh" + sfx[d] + ".tcw"));
+      g.bias[d] = P(h, p + ".rnn.hh" + sfx[d] + ".tcb");
+      g.inv_scale[d] = h->tc_inv_scale[p + ".rnn.hh" + sfx[d]];
+      g.h[d] = hst + (size_t)d * B * H;
+    }
+    for (int s = 0; s < T; ++s) {
+      const int par = s & 1, t_b = T - 1 - s;
+      for (int d = 0; d < 2; ++d) {
+        g.a_hi[d] = tile(tc_hi, d, par);
+        g.a_lo[d] = tile(tc_lo, d, par);
+        g.nxt_hi[d] = tile(tc_hi, d, par ^ 1);
+        g.nxt_lo[d] = tile(tc_lo, d, par ^ 1);
+      }
+      g.gi[0] = gi_f + (size_t)s * 3 * H;
+      g.gi[1] = gi_b + (size_t)t_b * 3 * H;
+      g.out[0] = out + (size_t)s * ldout;
+      g.out[1] = out + (size_t)t_b * ldout + H;
+      TK(launch_tc_gru(g, st));
+    }
+    return MB_OK;
+  }
   MB_CUDA_CHECK(cudaMemsetAsync(hst, 0, sizeof(float) * 2 * B * H, st));
   float* hf = hst;
   float* hb = hst + (size_t)B * H;
@@ -464,6 +527,30 @@ int run_cbhg(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p
       TK(launch_gru_cell(gi_b + (size_t)t * 3 * H, T * 3 * H, ghb, hb, H, out + (size_t)t * ldout + H, T * ldout, B, H, st));
     }
   }
+  return MB_OK;
+}
+
+// absmax -> power-of-two scale (max |w| lands in [2^11, 2^12): the lo parts of the fp16 split stay clear of the
+// subnormal range) -> hi/lo tile images "<name>.tcw" + tile-order bias "<name>.tcb".  Synchronises the stream.
+int tc_prepare(mb_tacotron* h, const std::string& name, const float* w0, int K0, const float* w1, int K1, const float* b0,
+               const float* b1, int N, int lstm_H, cudaStream_t st) {
+  unsigned int* dmax = nullptr;
+  MB_CUDA_CHECK(cudaMalloc(&dmax, sizeof(unsigned int)));
+  MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, sizeof(unsigned int), st));
+  TK(tc_skinny_absmax(w0, (size_t)N * K0, dmax, st));
+  if (w1) TK(tc_skinny_absmax(w1, (size_t)N * K1, dmax, st));
+  unsigned int hmax = 0;
+  MB_CUDA_CHECK(cudaMemcpyAsync(&hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
+  MB_CUDA_CHECK(cudaStreamSynchronize(st));
+  MB_CUDA_CHECK(cudaFree(dmax));
+  float mx;
+  memcpy(&mx, &hmax, sizeof(float));
+  int e = 0;
+  if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+  const float scale = ldexpf(1.f, 12 - e);
+  h->tc_inv_scale[name] = 1.f / scale;
+  TK(tc_skinny_pack(w0, K0, w1, K1, b0, b1, N, lstm_H, scale, reinterpret_cast<__half*>(P(h, name + ".tcw")),
+                    P(h, name + ".tcb"), st));
   return MB_OK;
 }
 
@@ -522,6 +609,10 @@ int mb_tacotron_create(const mb_tacotron_config* cfg, mb_tacotron** out) {
   }
   slot(h, "decoder.mel_proj.weight", (size_t)c.n_mels * c.max_r * c.lstm_dims);
   slot(h, "decoder.mel_proj.packed", (size_t)c.n_mels * c.max_r * c.lstm_dims);  // derived for the current r
+  slot(h, "decoder.mel_proj.tcw", tc_skinny_weight_bytes(c.n_mels * c.max_r, c.lstm_dims) / 4);  // derived (current r)
+  slot(h, "decoder.mel_proj.tcb", (size_t)c.n_mels * c.max_r + 32);
+  slot(h, "decoder.rnn_input.tcw", tc_skinny_weight_bytes(c.lstm_dims, proj_dims + D) / 4);     // derived
+  slot(h, "decoder.rnn_input.tcb", c.lstm_dims);
   slot(h, "decoder.stop_proj.weight", (size_t)(proj_dims + c.lstm_dims));
   slot(h, "decoder.stop_proj.bias", 1);
   cbhg_slots(h, "postnet", c.postnet_K, c.n_mels, c.postnet_dims, c.postnet_dims, c.n_mels, c.num_highways);
@@ -566,7 +657,7 @@ int mb_tacotron_finalize(mb_tacotron* h, void* stream) {
     return n.find(".bn_scale") != std::string::npos || n.find(".bn_shift") != std::string::npos ||
            n.find(".W12") != std::string::npos || n.find(".b12") != std::string::npos || n == "gst.tanh_embed" ||
            n == "gst.keys" || n == "gst.values" || n.find(".bias_sum") != std::string::npos || n.find(".tcw") != std::string::npos ||
-           n.find(".tcb") != std::string::npos ||
+           n.find(".tcb") != std::string::npos || n.find(".tcw") != std::string::npos ||
            n == "decoder.mel_proj.packed";
   };
   for (auto& kv : h->slots)
@@ -609,34 +700,27 @@ int mb_tacotron_finalize(mb_tacotron* h, void* stream) {
                        P(h, "gst.values"), c.gst_E);
     TK(launch_gemm(b, st));
   }
-  // tensor-core images of the two residual LSTMs: [W_ih | W_hh] gate-interleaved, scaled by a power of two so that
-  // max |w| lands near 2^12 (the lo parts of the fp16 split then stay clear of the subnormal range)
+  // tensor-core images: the two residual LSTMs ([W_ih | W_hh], gate-interleaved) and rnn_input
   {
-    unsigned int* dmax = nullptr;
-    MB_CUDA_CHECK(cudaMalloc(&dmax, 2 * sizeof(unsigned int)));
-    MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, 2 * sizeof(unsigned int), st));
-    const size_t nw = (size_t)4 * c.lstm_dims * c.lstm_dims;
     const char* names[2] = {"decoder.res_rnn1", "decoder.res_rnn2"};
     for (int l = 0; l < 2; ++l) {
-      TK(tc_skinny_absmax(P(h, std::string(names[l]) + ".weight_ih"), nw, dmax + l, st));
-      TK(tc_skinny_absmax(P(h, std::string(names[l]) + ".weight_hh"), nw, dmax + l, st));
-    }
-    unsigned int hmax[2] = {0, 0};
-    MB_CUDA_CHECK(cudaMemcpyAsync(hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
-    MB_CUDA_CHECK(cudaStreamSynchronize(st));
-    MB_CUDA_CHECK(cudaFree(dmax));
-    for (int l = 0; l < 2; ++l) {
-      float mx;
-      memcpy(&mx, &hmax[l], sizeof(float));
-      int e = 0;
-      if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
-      const float scale = ldexpf(1.f, 12 - e);
-      h->tc_inv_scale[l] = 1.f / scale;
       const std::string n = names[l];
-      TK(tc_skinny_pack(P(h, n + ".weight_ih"), c.lstm_dims, P(h, n + ".weight_hh"), c.lstm_dims, P(h, n + ".bias_ih"),
-                        P(h, n + ".bias_hh"), 4 * c.lstm_dims, c.lstm_dims, scale, reinterpret_cast<__half*>(P(h, n + ".tcw")),
-                        P(h, n + ".tcb"), st));
+      int rc = tc_prepare(h, n, P(h, n + ".weight_ih"), c.lstm_dims, P(h, n + ".weight_hh"), c.lstm_dims, P(h, n + ".bias_ih"),
+                          P(h, n + ".bias_hh"), 4 * c.lstm_dims, c.lstm_dims, st);
+      if (rc != MB_OK) return rc;
     }
+    for (const std::string p : {std::string("encoder.cbhg"), std::string("postnet")}) {
+      const int H = (p == "postnet" ? c.postnet_dims : c.encoder_dims) / 2;
+      for (const char* sfx : {"", "_reverse"}) {
+        int rc = tc_prepare(h, p + ".rnn.hh" + sfx, P(h, p + ".rnn.weight_hh_l0" + sfx), H, nullptr, 0,
+                            P(h, p + ".rnn.bias_hh_l0" + sfx), nullptr, 3 * H, H, st);
+        if (rc != MB_OK) return rc;
+      }
+    }
+    const int pd = c.encoder_dims + c.speaker_embedding_size + c.gst_E;
+    int rc = tc_prepare(h, "decoder.rnn_input", P(h, "decoder.rnn_input.weight"), pd + c.decoder_dims, nullptr, 0,
+                        P(h, "decoder.rnn_input.bias"), nullptr, c.lstm_dims, 0, st);
+    if (rc != MB_OK) return rc;
   }
   h->packed_r = 0;
   h->finalized = true;
@@ -679,6 +763,8 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
     pack_melproj_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P(h, "decoder.mel_proj.weight"),
                                                                      P(h, "decoder.mel_proj.packed"), NM, c.max_r, r, LD);
     MB_LAUNCH_CHECK("pack_melproj_kernel");
+    int rc = tc_prepare(h, "decoder.mel_proj", P(h, "decoder.mel_proj.packed"), LD, nullptr, 0, nullptr, nullptr, r * NM, 0, st);
+    if (rc != MB_OK) return rc;
     h->packed_r = r;
   }
 
@@ -704,7 +790,8 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   }
   float* seq = ws + L.seq;
   int rc = run_cbhg(h, "encoder.cbhg", c.encoder_K, E, E, E, E, c.num_highways, ws + L.x0, B, Tc, ws + L.bank, ws + L.pool,
-                    ws + L.pj1, ws + L.y, ws + L.hw12, ws + L.gi_f, ws + L.gi_b, ws + L.gh, ws + L.hst, seq, proj_dims, st);
+                    ws + L.pj1, ws + L.y, ws + L.hw12, ws + L.gi_f, ws + L.gi_b, ws + L.gh, ws + L.hst, seq, proj_dims, st,
+                    use_tc ? ws + L.a_hi : nullptr, use_tc ? ws + L.a_lo : nullptr, tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * LD));
   if (rc != MB_OK) return rc;
   // speaker embedding per char (tacotron.py:236), style embedding (tacotron.py:238-253)
   TK(launch_copy_cols(spk, SE, Tc, seq, proj_dims, E, Me, SE, st));
@@ -744,7 +831,7 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   MB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * nst, st));
   uint8_t* dm = reinterpret_cast<uint8_t*>(ws + L.dmask);
   const size_t dmask_n = (size_t)B * 2 * D;
-  const size_t lsa_smem = sizeof(float) * (ATT_F * ATT_K + ATT_D * ATT_F + 2 * ATT_D + ATT_F + (Tc + 30) + Tc + 32);
+  const size_t lsa_smem = sizeof(float) * (ATT_F * ATT_K + ATT_D * ATT_F + 2 * ATT_D + ATT_F + (Tc + 30) + Tc + 32 + (size_t)Tc * ATT_F + (size_t)Tc * 4);
   if (lsa_smem > 48 * 1024) MB_CUDA_CHECK(cudaFuncSetAttribute(lsa_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsa_smem));
   int done_step = -1;
   std::vector<int> hflags(nst, 0);
@@ -806,7 +893,25 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
                                                 ws + L.scores_all + (size_t)si * Tc, nst * Tc, ws + L.ctx, Tc);
       MB_LAUNCH_CHECK("lsa_step_kernel");
     }
-    {  // rnn_input on [context, attn_hidden]
+    if (use_tc) {  // rnn_input on [context, attn_hidden] (tensor cores)
+      __half* a_hi = reinterpret_cast<__half*>(ws + L.a_hi);
+      __half* a_lo = reinterpret_cast<__half*>(ws + L.a_lo);
+      TK(launch_act_split(ws + L.ctx, proj_dims, proj_dims, ws + L.attn_h, D, D, B, a_hi, a_lo, st));
+      TcSkinnyArgs ta;
+      memset(&ta, 0, sizeof(ta));
+      ta.a_hi = a_hi;
+      ta.a_lo = a_lo;
+      ta.w = reinterpret_cast<const __half*>(P(h, "decoder.rnn_input.tcw"));
+      ta.bias = P(h, "decoder.rnn_input.tcb");
+      ta.KB = (proj_dims + D + 63) / 64;
+      ta.M = B;
+      ta.N = LD;
+      ta.mode = TCS_PLAIN;
+      ta.inv_scale = h->tc_inv_scale["decoder.rnn_input"];
+      ta.y = ws + L.x;
+      ta.ldy = LD;
+      TK(launch_tc_skinny(ta, st));
+    } else {  // rnn_input on [context, attn_hidden]
       GemmArgs a;
       memset(&a, 0, sizeof(a));
       a.nseg = 2;
@@ -841,7 +946,7 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
         ta.M = B;
         ta.N = 4 * LD;
         ta.mode = TCS_LSTM;
-        ta.inv_scale = h->tc_inv_scale[l];
+        ta.inv_scale = h->tc_inv_scale[n];
         ta.c = cc;
         ta.h = hh;
         ta.x = ws + L.x;
@@ -861,9 +966,29 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       TK(launch_lstm_cell(ws + L.gates, cc, hh, ws + L.x, B, LD, st));
     }
     {  // mel frames of this step, written straight into mel_all[b][t..t+r)[:]
-      GemmArgs a = gemm1(ws + L.x, LD, LD, P(h, "decoder.mel_proj.packed"), LD, nullptr, B, r * NM, mel_all + (size_t)t * NM,
-                         steps_alloc * NM);
-      TK(launch_gemm(a, st));
+      if (use_tc && (r * NM) % 4 == 0) {
+        __half* a_hi = reinterpret_cast<__half*>(ws + L.a_hi);
+        __half* a_lo = reinterpret_cast<__half*>(ws + L.a_lo);
+        TK(launch_act_split(ws + L.x, LD, LD, nullptr, 0, 0, B, a_hi, a_lo, st));
+        TcSkinnyArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.a_hi = a_hi;
+        ta.a_lo = a_lo;
+        ta.w = reinterpret_cast<const __half*>(P(h, "decoder.mel_proj.tcw"));
+        ta.bias = nullptr;
+        ta.KB = LD / 64;
+        ta.M = B;
+        ta.N = r * NM;
+        ta.mode = TCS_PLAIN;
+        ta.inv_scale = h->tc_inv_scale["decoder.mel_proj"];
+        ta.y = mel_all + (size_t)t * NM;
+        ta.ldy = steps_alloc * NM;
+        TK(launch_tc_skinny(ta, st));
+      } else {
+        GemmArgs a = gemm1(ws + L.x, LD, LD, P(h, "decoder.mel_proj.packed"), LD, nullptr, B, r * NM, mel_all + (size_t)t * NM,
+                           steps_alloc * NM);
+        TK(launch_gemm(a, st));
+      }
       GemmArgs s;
       memset(&s, 0, sizeof(s));
       s.nseg = 2;
@@ -911,7 +1036,8 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
     melc = mel_all;
   }
   rc = run_cbhg(h, "postnet", c.postnet_K, NM, PD, PD, NM, c.num_highways, melc, B, frames, ws + L.pbank, ws + L.ppool,
-                ws + L.ppj1, ws + L.py, ws + L.phw12, ws + L.pgi_f, ws + L.pgi_b, ws + L.pgh, ws + L.phst, ws + L.pout, PD, st);
+                ws + L.ppj1, ws + L.py, ws + L.phw12, ws + L.pgi_f, ws + L.pgi_b, ws + L.pgh, ws + L.phst, ws + L.pout, PD, st,
+                use_tc ? ws + L.a_hi : nullptr, use_tc ? ws + L.a_lo : nullptr, tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * LD));
   if (rc != MB_OK) return rc;
   {
     GemmArgs a = gemm1(ws + L.pout, PD, PD, P(h, "post_proj.weight"), PD, nullptr, B * frames, NM, ws + L.lin, NM);

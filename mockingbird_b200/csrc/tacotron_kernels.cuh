@@ -79,6 +79,22 @@ struct TcSkinnyArgs {
   float* x;
   int H;
 };
+// one recurrent GRU step for 1 or 2 directions (blockIdx.y); pointers per direction
+struct TcGruArgs {
+  const __half* a_hi[2];  // h_{t-1} operand tiles [H/64][rows_pad][64]
+  const __half* a_lo[2];
+  __half* nxt_hi[2];      // h_t operand tiles for the next step (ping-pong with a_hi / a_lo)
+  __half* nxt_lo[2];
+  const __half* w[2];     // W_hh images, gates r|z|n interleaved per 8 units (tc_skinny_pack with lstm_H = H, N = 3H)
+  const float* bias[2];   // tile-order b_hh
+  const float* gi[2];     // W_ih x_t + b_ih for this step: row m at gi + m * ldgi, [r | z | n] each H wide
+  float* h[2];            // state [M][H] in/out
+  float* out[2];          // output sequence slot of this step: row m at out + m * ldout
+  float inv_scale[2];
+  int ldgi, ldout, KB, M, H, rows_pad, ndir;
+};
+cudaError_t launch_tc_gru(const TcGruArgs& a, cudaStream_t st);
+size_t tc_gated_weight_bytes(int H, int K);
 size_t tc_skinny_weight_bytes(int N, int K);
 size_t tc_skinny_act_bytes(int M, int K);
 // max |w| into *dev_out (uint bit pattern of a non-negative float; caller zeroes it first)

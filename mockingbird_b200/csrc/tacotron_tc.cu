@@ -36,7 +36,11 @@ constexpr uint32_t kStageBytes = 2 * kATile + 2 * kWTile;
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_constant__ TcSkinnyArgs p) {
+// Shared main loop: operands for output tile `tile` stream through the ring; `epi(m, v)` is called by the
+// epilogue warps with the 32 accumulator columns (already scaled, bias added) of row m.
+template <typename Epi>
+__device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* a_lo_g, const __half* w_g, const float* bias,
+                                            int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -47,8 +51,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kStages + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const uint32_t a_bytes = (uint32_t)p.rows_pad * 128u;
+  const uint32_t a_bytes = (uint32_t)rows_pad * 128u;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -63,10 +66,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x < 32) bias_s[threadIdx.x] = p.bias ? p.bias[tile * 32 + threadIdx.x] : 0.f;
-  if (p.rows_pad < 128) {
+  if (threadIdx.x < 32) bias_s[threadIdx.x] = bias ? bias[tile * 32 + threadIdx.x] : 0.f;
+  if (rows_pad < 128) {
     // rows [rows_pad, 128) of every A slot are never written by the copies: zero them once
-    for (int s = 0; s < 2 * kStages; ++s) {
+    const int nst = KB < kStages ? KB : kStages;
+    for (int s = 0; s < 2 * nst; ++s) {
       uint8_t* slot = smem + (size_t)(s >> 1) * kStageBytes + (size_t)(s & 1) * kATile + a_bytes;
       for (uint32_t i = threadIdx.x * 16u; i < kATile - a_bytes; i += kThreads * 16u)
         *reinterpret_cast<uint4*>(slot + i) = make_uint4(0u, 0u, 0u, 0u);
@@ -80,14 +84,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.w) + (size_t)tile * p.KB * (2 * kWTile);
-      for (int kb = 0; kb < p.KB; ++kb) {
+      const uint8_t* wt = reinterpret_cast<const uint8_t*>(w_g) + (size_t)tile * KB * (2 * kWTile);
+      for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % kStages, ph = (kb / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * kStageBytes;
         mbar_expect_tx(&full[s], 2 * a_bytes + 2 * kWTile);
-        bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(p.a_hi) + (size_t)kb * a_bytes, a_bytes, &full[s]);
-        bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(p.a_lo) + (size_t)kb * a_bytes, a_bytes, &full[s]);
+        bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(a_hi_g) + (size_t)kb * a_bytes, a_bytes, &full[s]);
+        bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(a_lo_g) + (size_t)kb * a_bytes, a_bytes, &full[s]);
         bulk_g2s(smem_u32(st + 2 * kATile), wt + (size_t)kb * (2 * kWTile), 2 * kWTile, &full[s]);
       }
     }
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t desc_hi = make_desc(0, 1024u, 2u, 0);
     const bool leader = elect_one();
-    for (int kb = 0; kb < p.KB; ++kb) {
+    for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % kStages, ph = (kb / kStages) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after();
@@ -122,37 +126,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
     tc_fence_after();
     uint32_t raw[32];
     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16), raw);
-    if (m < p.M) {
+    if (m < M) {
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.inv_scale + bias_s[i];
-      if (p.mode == TCS_LSTM) {
-        const size_t o = (size_t)m * p.H + (size_t)tile * 8;
-        float cn[8], hn[8], xn[8];
-        const float4 c0 = *reinterpret_cast<const float4*>(p.c + o), c1 = *reinterpret_cast<const float4*>(p.c + o + 4);
-        const float co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        const float4 x0 = *reinterpret_cast<const float4*>(p.x + o), x1 = *reinterpret_cast<const float4*>(p.x + o + 4);
-        const float xo[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float ig = sigm(v[e]), fg = sigm(v[8 + e]), cg = tanhf(v[16 + e]), og = sigm(v[24 + e]);
-          cn[e] = fg * co[e] + ig * cg;
-          hn[e] = og * tanhf(cn[e]);
-          xn[e] = xo[e] + hn[e];
-        }
-        *reinterpret_cast<float4*>(p.c + o) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-        *reinterpret_cast<float4*>(p.c + o + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-        *reinterpret_cast<float4*>(p.h + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        *reinterpret_cast<float4*>(p.h + o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-        *reinterpret_cast<float4*>(p.x + o) = make_float4(xn[0], xn[1], xn[2], xn[3]);
-        *reinterpret_cast<float4*>(p.x + o + 4) = make_float4(xn[4], xn[5], xn[6], xn[7]);
-      } else {
-        float* y = p.y + (size_t)m * p.ldy + (size_t)tile * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          if (tile * 32 + i < p.N) *reinterpret_cast<float4*>(y + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        }
-      }
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * inv_scale + bias_s[i];
+      epi(m, v);
     }
   }
   tc_fence_before();
@@ -161,6 +139,81 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
   }
+}
+
+// 8 fp32 values of row m, hidden units [u0, u0 + 8) -> the 16-byte chunk of the hi / lo operand tiles of the NEXT GEMM
+__device__ __forceinline__ void store_split_chunk(const float* x, int m, int rows_pad, int k0, __half* t_hi, __half* t_lo) {
+  __align__(16) __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    hi[e] = __float2half_rn(x[e]);
+    lo[e] = __float2half_rn(x[e] - __half2float(hi[e]));
+  }
+  const int kb = k0 >> 6, c8 = (k0 & 63) >> 3;
+  const size_t o = ((size_t)kb * rows_pad + m) * 8 + (size_t)(c8 ^ (m & 7));
+  reinterpret_cast<uint4*>(t_hi)[o] = *reinterpret_cast<const uint4*>(hi);
+  reinterpret_cast<uint4*>(t_lo)[o] = *reinterpret_cast<const uint4*>(lo);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_constant__ TcSkinnyArgs p) {
+  const int tile = blockIdx.x;
+  skinny_body(p.a_hi, p.a_lo, p.w, p.bias, p.KB, p.M, p.rows_pad, p.inv_scale, tile, [&](int m, float* v) {
+    if (p.mode == TCS_LSTM) {
+      const size_t o = (size_t)m * p.H + (size_t)tile * 8;
+      float cn[8], hn[8], xn[8];
+      const float4 c0 = *reinterpret_cast<const float4*>(p.c + o), c1 = *reinterpret_cast<const float4*>(p.c + o + 4);
+      const float co[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float4 x0 = *reinterpret_cast<const float4*>(p.x + o), x1 = *reinterpret_cast<const float4*>(p.x + o + 4);
+      const float xo[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float ig = sigm(v[e]), fg = sigm(v[8 + e]), cg = tanhf(v[16 + e]), og = sigm(v[24 + e]);
+        cn[e] = fg * co[e] + ig * cg;
+        hn[e] = og * tanhf(cn[e]);
+        xn[e] = xo[e] + hn[e];
+      }
+      *reinterpret_cast<float4*>(p.c + o) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      *reinterpret_cast<float4*>(p.c + o + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+      *reinterpret_cast<float4*>(p.h + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      *reinterpret_cast<float4*>(p.h + o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+      *reinterpret_cast<float4*>(p.x + o) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+      *reinterpret_cast<float4*>(p.x + o + 4) = make_float4(xn[4], xn[5], xn[6], xn[7]);
+    } else {
+      float* y = p.y + (size_t)m * p.ldy + (size_t)tile * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (tile * 32 + i < p.N) *reinterpret_cast<float4*>(y + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  });
+}
+
+// One recurrent step of a (bi)directional GRU: blockIdx.y = direction, blockIdx.x = 8 hidden units.
+//   gh = W_hh h + b_hh (this GEMM, gates r|z|n interleaved per tile);  r = sig(gi_r + gh_r), z = sig(gi_z + gh_z),
+//   n = tanh(gi_n + r * gh_n), h' = (h - n) z + n   (ATen gru_cell; gi = W_ih x_t + b_ih precomputed for all t)
+// h' goes to the state, to the output sequence and - as hi/lo operand chunks - into the NEXT step's A tiles.
+__global__ void __launch_bounds__(kThreads, 1) tc_gru_kernel(const __grid_constant__ TcGruArgs p) {
+  const int tile = blockIdx.x, dir = blockIdx.y;
+  const int H = p.H;
+  skinny_body(p.a_hi[dir], p.a_lo[dir], p.w[dir], p.bias[dir], p.KB, p.M, p.rows_pad, p.inv_scale[dir], tile,
+              [&](int m, float* v) {
+                const float* gi = p.gi[dir] + (size_t)m * p.ldgi + (size_t)tile * 8;
+                float* hp = p.h[dir] + (size_t)m * H + (size_t)tile * 8;
+                float hn[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float r = sigm(v[e] + gi[e]);
+                  const float z = sigm(v[8 + e] + gi[H + e]);
+                  const float n = tanhf(gi[2 * H + e] + v[16 + e] * r);
+                  hn[e] = (hp[e] - n) * z + n;
+                }
+                *reinterpret_cast<float4*>(hp) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(hp + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                float* op = p.out[dir] + (size_t)m * p.ldout + (size_t)tile * 8;
+                *reinterpret_cast<float4*>(op) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(op + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                store_split_chunk(hn, m, p.rows_pad, tile * 8, p.nxt_hi[dir], p.nxt_lo[dir]);
+              });
 }
 
 __device__ __forceinline__ __half split_hi(float v) { return __float2half_rn(v); }
@@ -198,7 +251,7 @@ __global__ void act_split_kernel(const float* __restrict__ s0, int K0, int ld0, 
 // and its K axis is [w0 (K0 columns) | w1 (K1 columns)], zero padded to 64 KB.
 __global__ void pack_split_w_kernel(const float* __restrict__ w0, int K0, const float* __restrict__ w1, int K1, int N,
                                     int lstm_H, int KB, float scale, __half* __restrict__ dst) {
-  const size_t n_tiles = (size_t)(N + 31) / 32;
+  const size_t n_tiles = lstm_H > 0 ? (size_t)lstm_H / 8 : (size_t)(N + 31) / 32;
   const size_t total = n_tiles * KB * 32 * 8;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -206,7 +259,7 @@ __global__ void pack_split_w_kernel(const float* __restrict__ w0, int K0, const 
   const int n = (int)((i >> 3) & 31);
   const int kb = (int)((i >> 8) % KB);
   const int j = (int)(i / ((size_t)256 * KB));
-  const int row = lstm_H > 0 ? (n / 8) * lstm_H + 8 * j + (n % 8) : 32 * j + n;
+  const int row = lstm_H > 0 ? (n / 8) * lstm_H + 8 * j + (n % 8) : 32 * j + n;  // gate-interleaved: N / H gates of 8 units
   __align__(16) __half hi[8], lo[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -230,7 +283,7 @@ __global__ void pack_split_w_kernel(const float* __restrict__ w0, int K0, const 
 __global__ void pack_split_bias_kernel(const float* __restrict__ b0, const float* __restrict__ b1, int N, int lstm_H,
                                        float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n_pad = (N + 31) / 32 * 32;
+  const int n_pad = lstm_H > 0 ? lstm_H * 4 : (N + 31) / 32 * 32;
   if (i >= n_pad) return;
   const int j = i / 32, n = i % 32;
   const int row = lstm_H > 0 ? (n / 8) * lstm_H + 8 * j + (n % 8) : i;
@@ -253,6 +306,10 @@ size_t tc_skinny_weight_bytes(int N, int K) {
   return n_tiles * KB * 2 * kWTile;
 }
 
+size_t tc_gated_weight_bytes(int H, int K) {  // gate-interleaved images: H / 8 tiles whatever the gate count (<= 4)
+  return (size_t)(H / 8) * ((size_t)(K + 63) / 64) * 2 * kWTile;
+}
+
 size_t tc_skinny_act_bytes(int M, int K) {
   const size_t KB = (size_t)(K + 63) / 64;
   return KB * (size_t)(M <= 64 ? 64 : 128) * 128;
@@ -266,11 +323,11 @@ cudaError_t tc_skinny_absmax(const float* w, size_t n, unsigned int* dev_out, cu
 cudaError_t tc_skinny_pack(const float* w0, int K0, const float* w1, int K1, const float* b0, const float* b1, int N,
                            int lstm_H, float scale, __half* w_dst, float* bias_dst, cudaStream_t st) {
   const int KB = (K0 + K1 + 63) / 64;
-  const size_t total = (size_t)((N + 31) / 32) * KB * 256;
+  const size_t total = (size_t)(lstm_H > 0 ? lstm_H / 8 : (N + 31) / 32) * KB * 256;
   pack_split_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w0, K0, w1, K1, N, lstm_H, KB, scale, w_dst);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int n_pad = (N + 31) / 32 * 32;
+  const int n_pad = lstm_H > 0 ? lstm_H * 4 : (N + 31) / 32 * 32;
   pack_split_bias_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(b0, b1, N, lstm_H, bias_dst);
   return cudaGetLastError();
 }
@@ -281,6 +338,21 @@ cudaError_t launch_act_split(const float* s0, int K0, int ld0, const float* s1, 
   const int rows_pad = M <= 64 ? 64 : 128;
   const int n = KB * rows_pad * 8;
   act_split_kernel<<<(n + 255) / 256, 256, 0, st>>>(s0, K0, ld0, s1, K1, ld1, M, rows_pad, KB, a_hi, a_lo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_gru(const TcGruArgs& a, cudaStream_t st) {
+  if (a.M <= 0 || a.M > 128 || a.H <= 0 || a.H % 8 || a.KB <= 0 || a.ndir < 1 || a.ndir > 2) return cudaErrorInvalidValue;
+  TcGruArgs p = a;
+  p.rows_pad = a.M <= 64 ? 64 : 128;
+  constexpr size_t smem = kStages * kStageBytes + 1024 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  tc_gru_kernel<<<dim3(a.H / 8, a.ndir), kThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 
