@@ -224,7 +224,10 @@ size_t mb_tacotron_workspace_bytes(const mb_tacotron* h, int32_t batch, int32_t 
  *   mel / linear fp32 [B][n_mels][ceil(steps/r)*r] (first *frames_out_host frames valid, caller strides
  *     by *frames_out_host: the arrays are written densely as [B][n_mels][frames]), attn fp32
  *     [B][frames/r][Tc] or NULL.
- * Synchronises the stream (the early-stop rule of tacotron.py:275 is polled every 16 decoder steps). */
+ * The work runs on an internal non-blocking stream that is ordered after everything already enqueued on `stream`
+ * and that `stream` waits for before the call returns (events) - the decoder loop is replayed from a CUDA graph
+ * (groups of 8 steps; the step index lives in device memory) and capture is not legal on the legacy default
+ * stream.  The call blocks the host while polling the early-stop rule of tacotron.py:275 every 16 decoder steps. */
 int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk, int32_t batch, int32_t n_chars,
                          int32_t steps, int32_t r, int32_t style_idx, float min_stop_token, const uint8_t* enc_masks,
                          const uint8_t* dec_masks, uint64_t seed, float* mel, float* linear, float* attn,

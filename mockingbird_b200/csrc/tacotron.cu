@@ -34,8 +34,10 @@ __global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__
                                                        const int32_t* __restrict__ chars, float* cum,
                                                        const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                                                        const float* __restrict__ Lw, const float* __restrict__ vw,
-                                                       float* __restrict__ scores_out, int scores_ld, float* ctx, int Tc) {
+                                                       float* __restrict__ scores_out, int scores_ld, float* ctx, int Tc,
+                                                       const int* step_ptr, int step_j) {
   extern __shared__ float sm[];
+  scores_out += (size_t)step_index(step_ptr, step_j) * Tc;  // this decoder step's row of the alignment matrix
   float* s_cw = sm;                         // [32][31]
   float* s_Lt = s_cw + ATT_F * ATT_K;       // [32][128]  (L transposed: conflict-free for d-major threads)
   float* s_v = s_Lt + ATT_D * ATT_F;        // [128]
@@ -186,20 +188,28 @@ __global__ void pack_melproj_kernel(const float* __restrict__ W, float* __restri
   dst[i] = W[((size_t)m * max_r + j) * K + k];
 }
 
-__global__ void fill_masks_kernel(uint8_t* m, size_t n, uint64_t seed, uint32_t stream_id) {
+__global__ void fill_masks_kernel(uint8_t* m, size_t n, uint64_t seed, uint32_t stream_id, const int* step_ptr = nullptr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (step_ptr) stream_id += (uint32_t)*step_ptr;  // decoder step = *step_ptr + offset (graph replay)
   uint32_t o[4];
   mb_philox4x32((uint32_t)(i >> 2), (uint32_t)(i >> 34), stream_id, 0x7461636fu, (uint32_t)seed, (uint32_t)(seed >> 32), o);
   m[i] = (uint8_t)((o[i & 3] >> 16) & 1u);  // Bernoulli(0.5) keep flag
 }
 
-__global__ void stop_flag_kernel(const float* stopv, int B, float min_stop_token, int t, int* flag) {
+// decoder step si = (step_ptr ? *step_ptr : 0) + step_j; frame t = si * r; flags[si] = stop rule of tacotron.py:275
+__global__ void stop_flag_kernel(const float* stopv, int B, float min_stop_token, int r, int* flags, const int* step_ptr,
+                                 int step_j) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int si = step_index(step_ptr, step_j);
     bool all = true;
     for (int b = 0; b < B; ++b) all = all && (stopv[b] * 10.f > min_stop_token);
-    *flag = (all && t > 10) ? 1 : 0;
+    flags[si] = (all && si * r > 10) ? 1 : 0;
   }
+}
+
+__global__ void step_advance_kernel(int* step_ptr, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *step_ptr += n;
 }
 
 // [B][T][C] (first `frames` of `steps` rows) -> [B][C][frames]
@@ -233,6 +243,10 @@ struct mb_tacotron {
   bool finalized = false;
   int packed_r = 0;
   std::map<std::string, float> tc_inv_scale;  // tensor-core weight images: 1 / pack scale per tensor
+  // generate() runs on an internal non-blocking stream ordered after / before the caller's stream by events: the
+  // decoder loop is replayed from a CUDA graph, and stream capture is not allowed on the legacy default stream
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 namespace {
@@ -282,7 +296,7 @@ struct Ws {
   // encoder
   size_t ids, emb, m_enc, p1, x0, bank, pool, pj1, y, hw12, gi_f, gi_b, gh, hst, seq, proj, style_q, style;
   // decoder
-  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, stopv, flags, dmask;
+  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, stopv, step, flags, dmask;
   // outputs / postnet
   size_t mel_all, scores_all, pbank, ppool, ppj1, ppj2, py, phw12, pgi_f, pgi_b, pgh, phst, pout, lin;
   size_t total;
@@ -333,6 +347,7 @@ Ws ws_layout(const mb_tacotron_config& c, int B, int Tc, int steps, int r) {
   L.a_hi = take(tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * c.lstm_dims) / 4);
   L.a_lo = take(tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * c.lstm_dims) / 4);
   L.stopv = take(B);
+  L.step = take(64);
   const int nst = (steps + r - 1) / r;
   L.flags = take(nst);
   L.dmask = take(((size_t)2 * B * 2 * c.decoder_dims + 3) / 4 + 64);
@@ -621,7 +636,13 @@ int mb_tacotron_create(const mb_tacotron_config* cfg, mb_tacotron** out) {
   return MB_OK;
 }
 
-void mb_tacotron_destroy(mb_tacotron* h) { delete h; }
+void mb_tacotron_destroy(mb_tacotron* h) {
+  if (!h) return;
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
 
 size_t mb_tacotron_arena_bytes(const mb_tacotron* h) { return h ? h->total * sizeof(float) : 0; }
 
@@ -747,7 +768,15 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   const Ws L = ws_layout(c, B, Tc, steps_alloc, r);
   if (workspace_bytes < L.total * sizeof(float) + 256) return fail(MB_ERR_WORKSPACE, "mb_tacotron_generate: workspace too small");
   float* ws = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t caller = (cudaStream_t)stream;
+  if (!h->own_stream) {
+    MB_CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    MB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    MB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  }
+  cudaStream_t st = h->own_stream;
+  MB_CUDA_CHECK(cudaEventRecord(h->ev_in, caller));
+  MB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_in, 0));
   const int E = c.encoder_dims, D = c.decoder_dims, LD = c.lstm_dims, PD = c.postnet_dims, NM = c.n_mels;
   // MB_TACO_TC=0 keeps the decoder LSTMs on the FP32 FFMA kernels (A/B measurements); batches > 128 rows always do
   static const bool tc_env = [] {
@@ -836,31 +865,43 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   int done_step = -1;
   std::vector<int> hflags(nst, 0);
   int checked = 0;
-  for (int si = 0; si < nst; ++si) {
-    const int t = si * r;
+  // One decoder step.  The step index is (sp ? *sp : 0) + sj, resolved ON THE DEVICE by the few kernels that
+  // need it (PreNet input frame and dropout masks, alignment row, mel output frames, stop flag), so the same
+  // launch sequence can be captured once into a CUDA graph and replayed for every group of steps.
+  auto emit_step = [&](const int* sp, int sj) -> int {
     // PreNet on the last frame of the previous step (go frame = zeros)
-    const float* prenet_in = (si == 0) ? mel_all + (size_t)B * steps_alloc * NM  // zero tail row block
-                                       : mel_all + (size_t)(t - 1) * NM;
-    const int prenet_ld = (si == 0) ? 0 : steps_alloc * NM;
     const uint8_t* m1;
     const uint8_t* m2;
+    long long mstep = 0;
     if (dec_masks) {
-      m1 = dec_masks + (size_t)si * 2 * dmask_n;
+      m1 = dec_masks;
       m2 = m1 + dmask_n;
+      mstep = (long long)(2 * dmask_n);
     } else {
-      fill_masks_kernel<<<(unsigned)((2 * dmask_n + 255) / 256), 256, 0, st>>>(dm, 2 * dmask_n, seed, (uint32_t)si);
+      fill_masks_kernel<<<(unsigned)((2 * dmask_n + 255) / 256), 256, 0, st>>>(dm, 2 * dmask_n, seed, (uint32_t)sj, sp);
       MB_LAUNCH_CHECK("fill_masks_kernel");
       m1 = dm;
       m2 = dm + dmask_n;
     }
     {
-      GemmArgs a = gemm1(prenet_in, NM, prenet_ld, P(h, "decoder.prenet.fc1.weight"), NM, P(h, "decoder.prenet.fc1.bias"), B,
-                         2 * D, ws + L.dp1, 2 * D, ACT_RELU);
+      // frame (step * r - 1) of every utterance; step 0 reads the zero block behind mel_all with row stride 0
+      GemmArgs a = gemm1(mel_all - NM, NM, steps_alloc * NM, P(h, "decoder.prenet.fc1.weight"), NM,
+                         P(h, "decoder.prenet.fc1.bias"), B, 2 * D, ws + L.dp1, 2 * D, ACT_RELU);
       a.mask = m1;
+      a.step_mode = 1;
+      a.step_ptr = sp;
+      a.step_j = sj;
+      a.x_step = (long long)r * NM;
+      a.x_first = mel_all + (size_t)B * steps_alloc * NM;
+      a.mask_step = mstep;
       TK(launch_gemm(a, st));
       GemmArgs b = gemm1(ws + L.dp1, 2 * D, 2 * D, P(h, "decoder.prenet.fc2.weight"), 2 * D, P(h, "decoder.prenet.fc2.bias"),
                          B, 2 * D, ws + L.dp2, 2 * D, ACT_RELU);
       b.mask = m2;
+      b.step_mode = 1;
+      b.step_ptr = sp;
+      b.step_j = sj;
+      b.mask_step = mstep;
       TK(launch_gemm(b, st));
     }
     {  // attention GRU on [context, prenet]
@@ -890,7 +931,7 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       lsa_step_kernel<<<B, 256, lsa_smem, st>>>(ws + L.pq, ws + L.proj, seq, proj_dims, chars, ws + L.cum,
                                                 P(h, "decoder.attn_net.conv.weight"), P(h, "decoder.attn_net.conv.bias"),
                                                 P(h, "decoder.attn_net.L.weight"), P(h, "decoder.attn_net.v.weight"),
-                                                ws + L.scores_all + (size_t)si * Tc, nst * Tc, ws + L.ctx, Tc);
+                                                ws + L.scores_all, nst * Tc, ws + L.ctx, Tc, sp, sj);
       MB_LAUNCH_CHECK("lsa_step_kernel");
     }
     if (use_tc) {  // rnn_input on [context, attn_hidden] (tensor cores)
@@ -981,12 +1022,16 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
         ta.N = r * NM;
         ta.mode = TCS_PLAIN;
         ta.inv_scale = h->tc_inv_scale["decoder.mel_proj"];
-        ta.y = mel_all + (size_t)t * NM;
+        ta.y = mel_all;
         ta.ldy = steps_alloc * NM;
+        ta.step_ptr = sp;
+        ta.step_j = sj;
+        ta.y_step = (long long)r * NM;
         TK(launch_tc_skinny(ta, st));
       } else {
-        GemmArgs a = gemm1(ws + L.x, LD, LD, P(h, "decoder.mel_proj.packed"), LD, nullptr, B, r * NM, mel_all + (size_t)t * NM,
-                           steps_alloc * NM);
+        if (sp) return fail(MB_ERR_STATE, "mb_tacotron_generate: graph replay needs the tensor-core mel projection");
+        GemmArgs a = gemm1(ws + L.x, LD, LD, P(h, "decoder.mel_proj.packed"), LD, nullptr, B, r * NM,
+                           mel_all + (size_t)sj * r * NM, steps_alloc * NM);
         TK(launch_gemm(a, st));
       }
       GemmArgs s;
@@ -1004,18 +1049,72 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       s.Y = ws + L.stopv;
       s.ldy = 1;
       TK(launch_gemm(s, st));
-      stop_flag_kernel<<<1, 32, 0, st>>>(ws + L.stopv, B, min_stop_token, t, flags + si);
+      stop_flag_kernel<<<1, 32, 0, st>>>(ws + L.stopv, B, min_stop_token, r, flags, sp, sj);
       MB_LAUNCH_CHECK("stop_flag_kernel");
     }
-    // early-stop rule (tacotron.py:275) polled every 16 steps
+    return MB_OK;
+  };
+
+  // poll the early-stop rule (tacotron.py:275) after every group of 16 decoder steps
+  auto poll = [&](int upto) -> int {
+    MB_CUDA_CHECK(cudaMemcpyAsync(hflags.data() + checked, flags + checked, sizeof(int) * (upto + 1 - checked),
+                                  cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int j = checked; j <= upto && done_step < 0; ++j)
+      if (hflags[j]) done_step = j;
+    checked = upto + 1;
+    return MB_OK;
+  };
+  // Groups of kGraphSteps steps are captured once and replayed (the loop is launch-bound: ~20 kernels of a few
+  // microseconds per step); MB_TACO_GRAPH=0 or a capture failure falls back to direct launches.
+  constexpr int kGraphSteps = 8;
+  static const bool graph_env = [] {
+    const char* e = getenv("MB_TACO_GRAPH");
+    return e ? atoi(e) != 0 : true;
+  }();
+  int si = 0;
+  if (graph_env && use_tc && (r * NM) % 4 == 0 && nst >= 2 * kGraphSteps) {
+    int* step_dev = reinterpret_cast<int*>(ws + L.step);
+    MB_CUDA_CHECK(cudaMemsetAsync(step_dev, 0, sizeof(int), st));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const uint64_t launches_before = mb_launch_count();
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int rc_cap = MB_OK;
+    if (ok) {
+      for (int j = 0; j < kGraphSteps && rc_cap == MB_OK; ++j) rc_cap = emit_step(step_dev, j);
+      if (rc_cap == MB_OK) step_advance_kernel<<<1, 32, 0, st>>>(step_dev, kGraphSteps);
+      ok = cudaStreamEndCapture(st, &graph) == cudaSuccess && rc_cap == MB_OK && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    const int per_graph = (int)(mb_launch_count() - launches_before);
+    count_launch(-per_graph);  // captured, not launched; every replay below counts them
+    if (ok) {
+      while (si + kGraphSteps <= nst && done_step < 0) {
+        if (cudaGraphLaunch(exec, st) != cudaSuccess) {
+          cudaGraphExecDestroy(exec);
+          cudaGraphDestroy(graph);
+          return fail(MB_ERR_CUDA, "mb_tacotron_generate: cudaGraphLaunch failed");
+        }
+        count_launch(per_graph + 1);
+        si += kGraphSteps;
+        if ((si % 16) == 0 || si + kGraphSteps > nst) {
+          int rc2 = poll(si - 1);
+          if (rc2 != MB_OK) return rc2;
+        }
+      }
+    } else {
+      cudaGetLastError();  // clear the capture error; direct launches below
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+  for (; si < nst && done_step < 0; ++si) {  // tail (or everything, without the graph): direct launches
+    int rc2 = emit_step(nullptr, si);
+    if (rc2 != MB_OK) return rc2;
     if ((si % 16) == 15 || si == nst - 1) {
-      MB_CUDA_CHECK(cudaMemcpyAsync(hflags.data() + checked, flags + checked, sizeof(int) * (si + 1 - checked),
-                                    cudaMemcpyDeviceToHost, st));
-      MB_CUDA_CHECK(cudaStreamSynchronize(st));
-      for (int j = checked; j <= si && done_step < 0; ++j)
-        if (hflags[j]) done_step = j;
-      checked = si + 1;
-      if (done_step >= 0) break;
+      rc2 = poll(si);
+      if (rc2 != MB_OK) return rc2;
     }
   }
   const int nsteps_done = (done_step >= 0 ? done_step : nst - 1) + 1;
@@ -1055,6 +1154,8 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
         MB_CUDA_CHECK(cudaMemcpyAsync(attn_out + (size_t)b * nsteps_done * Tc, ws + L.scores_all + (size_t)b * nst * Tc,
                                       sizeof(float) * nsteps_done * Tc, cudaMemcpyDeviceToDevice, st));
   }
+  MB_CUDA_CHECK(cudaEventRecord(h->ev_out, st));
+  MB_CUDA_CHECK(cudaStreamWaitEvent(caller, h->ev_out, 0));
   return MB_OK;
 }
 

@@ -17,6 +17,20 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 }
 
 // 64 x BN output tile, 256 threads, thread tile 4 x (BN/16); operands staged k-major in shared memory
+__device__ __forceinline__ void step_seg0(const GemmArgs& a, Seg& sg) {
+  if (!a.step_mode) return;
+  const int si = step_index(a.step_ptr, a.step_j);
+  if (si == 0 && a.x_first) {
+    sg.x = a.x_first;
+    sg.ld = 0;
+  } else {
+    sg.x += (long long)si * a.x_step;
+  }
+}
+__device__ __forceinline__ const uint8_t* step_mask(const GemmArgs& a) {
+  return a.step_mode ? a.mask + (size_t)step_index(a.step_ptr, a.step_j) * (size_t)a.mask_step : a.mask;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
   constexpr int TN = BN / 16;
@@ -32,7 +46,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   for (int s = 0; s < a.nseg; ++s) {
-    const Seg sg = a.seg[s];
+    Seg sg = a.seg[s];
+    if (s == 0) step_seg0(a, sg);
     for (int k0 = 0; k0 < sg.K; k0 += BK) {
       // A tile: 64 rows x 16 k (k fastest -> coalesced along the feature axis)
       for (int i = tid; i < BM * BK; i += 256) {
@@ -90,7 +105,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs a) {
       if (a.bias) v += a.bias[n];
       v = act_fn(v, a.act);
       if (a.bn_scale) v = fmaf(v, a.bn_scale[n], a.bn_shift[n]);
-      if (a.mask) v = a.mask[(size_t)m * a.N + n] ? v * 2.f : 0.f;
+      if (a.mask) v = step_mask(a)[(size_t)m * a.N + n] ? v * 2.f : 0.f;
       if (a.res) v += a.res[(size_t)m * a.ldres + n];
       a.Y[(size_t)m * a.ldy + n] = v;
     }
@@ -127,7 +142,8 @@ __global__ void __launch_bounds__(256) gemm_big_kernel(const GemmArgs a) {
       c -= (a.seg[s].K + LBK - 1) / LBK;
       ++s;
     }
-    const Seg sg = a.seg[s];
+    Seg sg = a.seg[s];
+    if (s == 0) step_seg0(a, sg);
     const int k = c * LBK + lk;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -192,7 +208,7 @@ __global__ void __launch_bounds__(256) gemm_big_kernel(const GemmArgs a) {
       if (a.bias) v += a.bias[n];
       v = act_fn(v, a.act);
       if (a.bn_scale) v = fmaf(v, a.bn_scale[n], a.bn_shift[n]);
-      if (a.mask) v = a.mask[(size_t)m * a.N + n] ? v * 2.f : 0.f;
+      if (a.mask) v = step_mask(a)[(size_t)m * a.N + n] ? v * 2.f : 0.f;
       if (a.res) v += a.res[(size_t)m * a.ldres + n];
       a.Y[(size_t)m * a.ldy + n] = v;
     }
@@ -226,7 +242,8 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmArgs a) {
   const int lq = lane & 3, lr = lane >> 2;  // staging: 4 lanes x float4 cover 16 k of a row, 8 rows per pass
   int chunk = 0;
   for (int s = 0; s < a.nseg; ++s) {
-    const Seg sg = a.seg[s];
+    Seg sg = a.seg[s];
+    if (s == 0) step_seg0(a, sg);
     const bool vec = ((sg.ld & 3) == 0) && ((sg.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(sg.x) & 15) == 0);
     const bool wvec = (sg.w_stride == 1) && ((a.ldw & 3) == 0) && ((sg.w_off & 3) == 0) && ((sg.K & 3) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.W) & 15) == 0);
@@ -308,7 +325,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmArgs a) {
       if (a.bias) v += a.bias[n];
       v = act_fn(v, a.act);
       if (a.bn_scale) v = fmaf(v, a.bn_scale[n], a.bn_shift[n]);
-      if (a.mask) v = a.mask[(size_t)m * a.N + n] ? v * 2.f : 0.f;
+      if (a.mask) v = step_mask(a)[(size_t)m * a.N + n] ? v * 2.f : 0.f;
       if (a.res) v += a.res[(size_t)m * a.ldres + n];
       a.Y[(size_t)m * a.ldy + n] = v;
     }

@@ -43,7 +43,18 @@ struct GemmArgs {
   int ldres;
   float* Y;
   int ldy;
+  // decoder-step indirection (CUDA-graph replay): step = (step_ptr ? *step_ptr : 0) + step_j.  When step_mode != 0
+  // segment 0 reads x + step * x_step (or x_first with row stride 0 at step 0: the all-zero go frame) and the
+  // dropout mask is mask + step * mask_step.
+  int step_mode;
+  const int* step_ptr;
+  int step_j;
+  long long x_step;
+  const float* x_first;
+  long long mask_step;
 };
+
+__device__ __forceinline__ int step_index(const int* step_ptr, int step_j) { return (step_ptr ? *step_ptr : 0) + step_j; }
 
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st);
 
@@ -72,8 +83,11 @@ struct TcSkinnyArgs {
   const float* bias;    // packed bias [ceil32(N)] or nullptr
   int KB, M, N, rows_pad, mode;
   float inv_scale;      // 1 / (power-of-two weight scale used at pack time)
-  float* y;             // TCS_PLAIN: out [M][ldy]
+  float* y;             // TCS_PLAIN: out [M][ldy] (+ step * y_step, step = (step_ptr ? *step_ptr : 0) + step_j)
   int ldy;
+  const int* step_ptr;
+  int step_j;
+  long long y_step;
   float* c;             // TCS_LSTM: cell state [M][H] in/out, h [M][H] out, x [M][H] += h (residual, tacotron.py:121,126)
   float* h;
   float* x;

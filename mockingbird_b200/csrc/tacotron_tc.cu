@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
       *reinterpret_cast<float4*>(p.x + o) = make_float4(xn[0], xn[1], xn[2], xn[3]);
       *reinterpret_cast<float4*>(p.x + o + 4) = make_float4(xn[4], xn[5], xn[6], xn[7]);
     } else {
-      float* y = p.y + (size_t)m * p.ldy + (size_t)tile * 32;
+      float* y = p.y + (long long)step_index(p.step_ptr, p.step_j) * p.y_step + (size_t)m * p.ldy + (size_t)tile * 32;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         if (tile * 32 + i < p.N) *reinterpret_cast<float4*>(y + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
