@@ -122,12 +122,51 @@ __global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__
     scores_out[(size_t)b * scores_ld + t] = sc;
     cum[(size_t)b * Tc + t] = s_cum[t + 15] + sc;
   }
+  if (ctx == nullptr) return;  // context vector computed by lsa_ctx_kernel (more CTAs, vector loads)
   __syncthreads();
   for (int f = tid; f < seq_dim; f += blockDim.x) {
     float a = 0.f;
     const float* sp = seq + (size_t)b * Tc * seq_dim + f;
     for (int t = 0; t < Tc; ++t) a = fmaf(s_u[t], sp[(size_t)t * seq_dim], a);
     ctx[(size_t)b * seq_dim + f] = a;
+  }
+}
+
+// context = scores @ encoder_seq (tacotron.py:104 via lsa.py:40): ctx[b][f] = sum_t scores[b][t] seq[b][t][f].
+// grid (seq_dim / 256, B): 64 float4 feature lanes x 4 interleaved t-groups per CTA, partials reduced in smem.
+// The whole encoder sequence (B x Tc x 1024 fp32) is re-read every decoder step from L2: the kernel needs many
+// 16-byte loads in flight, which one CTA per batch row cannot provide.
+__global__ void __launch_bounds__(256) lsa_ctx_kernel(const float* __restrict__ scores, int scores_ld, const float* __restrict__ seq,
+                                                      int seq_dim, int Tc, float* __restrict__ ctx, const int* step_ptr,
+                                                      int step_j) {
+  __shared__ float4 part[4][64];
+  extern __shared__ float s_sc[];
+  const int b = blockIdx.y, f4 = blockIdx.x * 64 + (threadIdx.x & 63), tg = threadIdx.x >> 6;
+  const float* sc = scores + (size_t)step_index(step_ptr, step_j) * Tc + (size_t)b * scores_ld;
+  for (int t = threadIdx.x; t < Tc; t += 256) s_sc[t] = sc[t];
+  __syncthreads();
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* sp = reinterpret_cast<const float4*>(seq + (size_t)b * Tc * seq_dim) + f4;
+  const int q4 = seq_dim >> 2;
+#pragma unroll 6
+  for (int t = tg; t < Tc; t += 4) {
+    const float4 v = sp[(size_t)t * q4];
+    const float w = s_sc[t];
+    a.x = fmaf(w, v.x, a.x);
+    a.y = fmaf(w, v.y, a.y);
+    a.z = fmaf(w, v.z, a.z);
+    a.w = fmaf(w, v.w, a.w);
+  }
+  part[tg][threadIdx.x & 63] = a;
+  __syncthreads();
+  if (tg == 0) {
+    const float4 p0 = part[0][threadIdx.x], p1 = part[1][threadIdx.x], p2 = part[2][threadIdx.x], p3 = part[3][threadIdx.x];
+    float4 r;
+    r.x = (p0.x + p1.x) + (p2.x + p3.x);
+    r.y = (p0.y + p1.y) + (p2.y + p3.y);
+    r.z = (p0.z + p1.z) + (p2.z + p3.z);
+    r.w = (p0.w + p1.w) + (p2.w + p3.w);
+    reinterpret_cast<float4*>(ctx + (size_t)b * seq_dim)[f4] = r;
   }
 }
 
@@ -296,7 +335,7 @@ struct Ws {
   // encoder
   size_t ids, emb, m_enc, p1, x0, bank, pool, pj1, y, hw12, gi_f, gi_b, gh, hst, seq, proj, style_q, style;
   // decoder
-  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, stopv, step, flags, dmask;
+  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, ah_hi, ah_lo, stopv, step, flags, dmask;
   // outputs / postnet
   size_t mel_all, scores_all, pbank, ppool, ppj1, ppj2, py, phw12, pgi_f, pgi_b, pgh, phst, pout, lin;
   size_t total;
@@ -346,6 +385,8 @@ Ws ws_layout(const mb_tacotron_config& c, int B, int Tc, int steps, int r) {
   L.gates = take((size_t)B * 4 * c.lstm_dims);
   L.a_hi = take(tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * c.lstm_dims) / 4);
   L.a_lo = take(tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * c.lstm_dims) / 4);
+  L.ah_hi = take(2 * tc_skinny_act_bytes(B > 128 ? 128 : B, c.decoder_dims) / 4);  // attention-GRU state tiles, 2 parities
+  L.ah_lo = take(2 * tc_skinny_act_bytes(B > 128 ? 128 : B, c.decoder_dims) / 4);
   L.stopv = take(B);
   L.step = take(64);
   const int nst = (steps + r - 1) / r;
@@ -611,6 +652,10 @@ int mb_tacotron_create(const mb_tacotron_config* cfg, mb_tacotron** out) {
   slot(h, "decoder.attn_rnn.weight_hh", (size_t)3 * D * D);
   slot(h, "decoder.attn_rnn.bias_ih", 3 * D);
   slot(h, "decoder.attn_rnn.bias_hh", 3 * D);
+  slot(h, "decoder.attn_rnn.ih.tcw", tc_skinny_weight_bytes(3 * D, proj_dims + 2 * D) / 4);  // derived tensor-core images
+  slot(h, "decoder.attn_rnn.ih.tcb", 3 * D);
+  slot(h, "decoder.attn_rnn.hh.tcw", tc_gated_weight_bytes(D, D) / 4);
+  slot(h, "decoder.attn_rnn.hh.tcb", 4 * D);
   slot(h, "decoder.rnn_input.weight", (size_t)c.lstm_dims * (proj_dims + D));
   slot(h, "decoder.rnn_input.bias", c.lstm_dims);
   for (const char* n : {"decoder.res_rnn1", "decoder.res_rnn2"}) {
@@ -739,6 +784,15 @@ int mb_tacotron_finalize(mb_tacotron* h, void* stream) {
       }
     }
     const int pd = c.encoder_dims + c.speaker_embedding_size + c.gst_E;
+    {
+      const int Dd = c.decoder_dims;
+      int rc = tc_prepare(h, "decoder.attn_rnn.ih", P(h, "decoder.attn_rnn.weight_ih"), pd + 2 * Dd, nullptr, 0,
+                          P(h, "decoder.attn_rnn.bias_ih"), nullptr, 3 * Dd, 0, st);
+      if (rc != MB_OK) return rc;
+      rc = tc_prepare(h, "decoder.attn_rnn.hh", P(h, "decoder.attn_rnn.weight_hh"), Dd, nullptr, 0,
+                      P(h, "decoder.attn_rnn.bias_hh"), nullptr, 3 * Dd, Dd, st);
+      if (rc != MB_OK) return rc;
+    }
     int rc = tc_prepare(h, "decoder.rnn_input", P(h, "decoder.rnn_input.weight"), pd + c.decoder_dims, nullptr, 0,
                         P(h, "decoder.rnn_input.bias"), nullptr, c.lstm_dims, 0, st);
     if (rc != MB_OK) return rc;
@@ -854,6 +908,7 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
 
   // ------------------------------------------------------------------ decoder loop (tacotron.py:264-275)
   MB_CUDA_CHECK(cudaMemsetAsync(ws + L.attn_h, 0, sizeof(float) * (L.dp1 - L.attn_h), st));  // states, ctx, cum
+  MB_CUDA_CHECK(cudaMemsetAsync(ws + L.ah_hi, 0, sizeof(float) * (L.stopv - L.ah_hi), st));  // h0 = 0 operand tiles
   float* mel_all = ws + L.mel_all;
   MB_CUDA_CHECK(cudaMemsetAsync(mel_all, 0, sizeof(float) * ((size_t)B * steps_alloc * NM + (size_t)r * NM), st));
   int* flags = reinterpret_cast<int*>(ws + L.flags);
@@ -904,7 +959,46 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       b.mask_step = mstep;
       TK(launch_gemm(b, st));
     }
-    {  // attention GRU on [context, prenet]
+    if (use_tc && D % 64 == 0) {  // attention GRU on [context, prenet]: input projection + recurrent step on tensor cores
+      __half* a_hi = reinterpret_cast<__half*>(ws + L.a_hi);
+      __half* a_lo = reinterpret_cast<__half*>(ws + L.a_lo);
+      TK(launch_act_split(ws + L.ctx, proj_dims, proj_dims, ws + L.dp2, 2 * D, 2 * D, B, a_hi, a_lo, st));
+      TcSkinnyArgs ta;
+      memset(&ta, 0, sizeof(ta));
+      ta.a_hi = a_hi;
+      ta.a_lo = a_lo;
+      ta.w = reinterpret_cast<const __half*>(P(h, "decoder.attn_rnn.ih.tcw"));
+      ta.bias = P(h, "decoder.attn_rnn.ih.tcb");
+      ta.KB = (proj_dims + 2 * D + 63) / 64;
+      ta.M = B;
+      ta.N = 3 * D;
+      ta.mode = TCS_PLAIN;
+      ta.inv_scale = h->tc_inv_scale["decoder.attn_rnn.ih"];
+      ta.y = ws + L.dgi;
+      ta.ldy = 3 * D;
+      TK(launch_tc_skinny(ta, st));
+      const size_t tb = tc_skinny_act_bytes(B, D);
+      const int par = sj & 1;  // graph groups start at even steps, so the parity of (base + sj) is that of sj
+      TcGruArgs g;
+      memset(&g, 0, sizeof(g));
+      g.a_hi[0] = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(ws + L.ah_hi) + par * tb);
+      g.a_lo[0] = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(ws + L.ah_lo) + par * tb);
+      g.nxt_hi[0] = reinterpret_cast<__half*>(reinterpret_cast<char*>(ws + L.ah_hi) + (par ^ 1) * tb);
+      g.nxt_lo[0] = reinterpret_cast<__half*>(reinterpret_cast<char*>(ws + L.ah_lo) + (par ^ 1) * tb);
+      g.w[0] = reinterpret_cast<const __half*>(P(h, "decoder.attn_rnn.hh.tcw"));
+      g.bias[0] = P(h, "decoder.attn_rnn.hh.tcb");
+      g.gi[0] = ws + L.dgi;
+      g.h[0] = ws + L.attn_h;
+      g.out[0] = ws + L.attn_h;
+      g.inv_scale[0] = h->tc_inv_scale["decoder.attn_rnn.hh"];
+      g.ldgi = 3 * D;
+      g.ldout = D;
+      g.KB = D / 64;
+      g.M = B;
+      g.H = D;
+      g.ndir = 1;
+      TK(launch_tc_gru(g, st));
+    } else {  // attention GRU on [context, prenet]
       GemmArgs a;
       memset(&a, 0, sizeof(a));
       a.nseg = 2;
@@ -931,8 +1025,14 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       lsa_step_kernel<<<B, 256, lsa_smem, st>>>(ws + L.pq, ws + L.proj, seq, proj_dims, chars, ws + L.cum,
                                                 P(h, "decoder.attn_net.conv.weight"), P(h, "decoder.attn_net.conv.bias"),
                                                 P(h, "decoder.attn_net.L.weight"), P(h, "decoder.attn_net.v.weight"),
-                                                ws + L.scores_all, nst * Tc, ws + L.ctx, Tc, sp, sj);
+                                                ws + L.scores_all, nst * Tc, (proj_dims % 256 == 0) ? nullptr : ws + L.ctx, Tc,
+                                                sp, sj);
       MB_LAUNCH_CHECK("lsa_step_kernel");
+      if (proj_dims % 256 == 0) {
+        lsa_ctx_kernel<<<dim3(proj_dims / 256, B), 256, sizeof(float) * Tc, st>>>(ws + L.scores_all, nst * Tc, seq, proj_dims, Tc,
+                                                                                  ws + L.ctx, sp, sj);
+        MB_LAUNCH_CHECK("lsa_ctx_kernel");
+      }
     }
     if (use_tc) {  // rnn_input on [context, attn_hidden] (tensor cores)
       __half* a_hi = reinterpret_cast<__half*>(ws + L.a_hi);
