@@ -8,7 +8,10 @@
 // projection of the WHOLE sequence is one GEMM (M = rows*T); the recurrence then needs one
 // [rows x H] x [H x 4H] GEMM per time step whose epilogue adds that step's projected input row, followed
 // by the fused gate kernel that writes h_t straight into the layer's output sequence (the next step's
-// GEMM operand, and the next layer's input).
+// GEMM operand, and the next layer's input).  When hidden_size % 64 == 0 the recurrent step is ONE launch of
+// the tensor-core kernel tc_lstm_seq_kernel (tacotron_tc.cu: 3-term fp16 split, FP32-equivalent; cell update
+// in the epilogue; h_t written as the next step's operand tiles); MB_ENC_TC=0 keeps the FFMA path.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -30,6 +33,7 @@ struct mb_encoder {
   size_t total = 0;
   float* arena = nullptr;
   bool finalized = false;
+  float tc_inv_scale[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
 };
 
 namespace {
@@ -127,8 +131,16 @@ GemmArgs gemm1(const float* x, int K, int ld, const float* W, int ldw, const flo
 }
 
 struct Ws {
-  size_t xproj, seq0, seq1, gates, c, raw, total;
+  size_t xproj, seq0, seq1, gates, c, raw, t_hi, t_lo, total;
 };
+
+bool enc_use_tc(const mb_encoder_config& c) {
+  static const bool env = [] {
+    const char* e = getenv("MB_ENC_TC");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return env && c.hidden_size % 64 == 0;
+}
 
 Ws ws_layout(const mb_encoder_config& c, size_t R, size_t T) {
   Ws L;
@@ -145,6 +157,10 @@ Ws ws_layout(const mb_encoder_config& c, size_t R, size_t T) {
   L.gates = take(R * 4 * H);
   L.c = take(R * H);
   L.raw = take(R * (size_t)c.embedding_size);
+  const size_t rows_total = (R + 127) / 128 * 128;
+  const size_t tile_floats = (H / 64) * rows_total * 128 / 4;  // one operand plane (hi or lo) of h, in floats
+  L.t_hi = take(2 * tile_floats);                               // two parities
+  L.t_lo = take(2 * tile_floats);
   L.total = o;
   return L;
 }
@@ -169,6 +185,8 @@ int mb_encoder_create(const mb_encoder_config* cfg, mb_encoder** out) {
     slot(h, "lstm.bias_ih_l" + s, 4 * H);
     slot(h, "lstm.bias_hh_l" + s, 4 * H);
     slot(h, "lstm.bias_sum_l" + s, 4 * H);  // derived: b_ih + b_hh
+    slot(h, "lstm.hh_tcw_l" + s, tc_gated_weight_bytes((int)H, (int)H) / 4);  // derived: tensor-core images of W_hh
+    slot(h, "lstm.hh_tcb_l" + s, 4 * H);                                      // (unused zero bias of the images)
   }
   slot(h, "linear.weight", (size_t)c.embedding_size * H);
   slot(h, "linear.bias", c.embedding_size);
@@ -193,7 +211,8 @@ int mb_encoder_set_weight(mb_encoder* h, const char* name, const float* w, const
   if (!h || !name || !w) return fail(MB_ERR_INVALID, "mb_encoder_set_weight: null argument");
   if (!h->arena) return fail(MB_ERR_STATE, "mb_encoder_set_weight: call mb_encoder_set_arena first");
   auto it = h->slots.find(name);
-  if (it == h->slots.end() || std::string(name).find("bias_sum") != std::string::npos)
+  if (it == h->slots.end() || std::string(name).find("bias_sum") != std::string::npos ||
+      std::string(name).find("hh_tc") != std::string::npos)
     return fail(MB_ERR_INVALID, "mb_encoder_set_weight: unknown tensor '%s'", name);
   size_t n = 1;
   for (int i = 0; i < ndim; ++i) n *= (size_t)dims[i];
@@ -209,7 +228,7 @@ int mb_encoder_finalize(mb_encoder* h, void* stream) {
   if (!h) return fail(MB_ERR_INVALID, "mb_encoder_finalize: null handle");
   cudaStream_t st = (cudaStream_t)stream;
   for (auto& kv : h->slots)
-    if (!kv.second.set && kv.first.find("bias_sum") == std::string::npos)
+    if (!kv.second.set && kv.first.find("bias_sum") == std::string::npos && kv.first.find("hh_tc") == std::string::npos)
       return fail(MB_ERR_STATE, "mb_encoder_finalize: tensor %s was never set", kv.first.c_str());
   const int n = 4 * h->cfg.hidden_size;
   for (int l = 0; l < h->cfg.num_layers; ++l) {
@@ -217,6 +236,30 @@ int mb_encoder_finalize(mb_encoder* h, void* stream) {
     add_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(P(h, "lstm.bias_ih_l" + s), P(h, "lstm.bias_hh_l" + s),
                                                     P(h, "lstm.bias_sum_l" + s), n);
     MB_LAUNCH_CHECK("add_vec_kernel");
+  }
+  if (enc_use_tc(h->cfg)) {
+    // tensor-core images of every W_hh (power-of-two scale from max |w|, see tacotron.cu tc_prepare)
+    const int H = h->cfg.hidden_size;
+    unsigned int* dmax = nullptr;
+    MB_CUDA_CHECK(cudaMalloc(&dmax, 8 * sizeof(unsigned int)));
+    MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, 8 * sizeof(unsigned int), st));
+    for (int l = 0; l < h->cfg.num_layers; ++l)
+      TK(tc_skinny_absmax(P(h, "lstm.weight_hh_l" + std::to_string(l)), (size_t)4 * H * H, dmax + l, st));
+    unsigned int hmax[8] = {0};
+    MB_CUDA_CHECK(cudaMemcpyAsync(hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    MB_CUDA_CHECK(cudaFree(dmax));
+    for (int l = 0; l < h->cfg.num_layers; ++l) {
+      float mx;
+      memcpy(&mx, &hmax[l], sizeof(float));
+      int e = 0;
+      if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);
+      const float scale = ldexpf(1.f, 12 - e);
+      h->tc_inv_scale[l] = 1.f / scale;
+      const std::string s = std::to_string(l);
+      TK(tc_skinny_pack(P(h, "lstm.weight_hh_l" + s), H, nullptr, 0, nullptr, nullptr, 4 * H, H, scale,
+                        reinterpret_cast<__half*>(P(h, "lstm.hh_tcw_l" + s)), P(h, "lstm.hh_tcb_l" + s), st));
+    }
   }
   h->finalized = true;
   return MB_OK;
@@ -250,6 +293,37 @@ int mb_encoder_embed_frames(mb_encoder* h, const float* frames, int32_t rows, in
                        ws + L.xproj, 4 * H);
     TK(launch_gemm(a, st));
     const float* whh = P(h, "lstm.weight_hh_l" + s);
+    if (enc_use_tc(c)) {
+      const size_t rows_total = ((size_t)R + 127) / 128 * 128;
+      const size_t tile_bytes = (size_t)(H / 64) * rows_total * 128;
+      MB_CUDA_CHECK(cudaMemsetAsync(ws + L.t_hi, 0, 2 * tile_bytes, st));  // h_{-1} = 0 (and the rows past R)
+      MB_CUDA_CHECK(cudaMemsetAsync(ws + L.t_lo, 0, 2 * tile_bytes, st));
+      MB_CUDA_CHECK(cudaMemsetAsync(ws + L.c, 0, sizeof(float) * (size_t)R * H, st));
+      TcLstmSeqArgs ta;
+      memset(&ta, 0, sizeof(ta));
+      ta.w = reinterpret_cast<const __half*>(P(h, "lstm.hh_tcw_l" + s));
+      ta.c = ws + L.c;
+      ta.inv_scale = h->tc_inv_scale[l];
+      ta.ldgi = T * 4 * H;
+      ta.ldout = T * H;
+      ta.KB = H / 64;
+      ta.M = R;
+      ta.H = H;
+      ta.rows_total = (int)rows_total;
+      for (int t = 0; t < T; ++t) {
+        const int par = t & 1;
+        ta.a_hi = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(ws + L.t_hi) + par * tile_bytes);
+        ta.a_lo = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(ws + L.t_lo) + par * tile_bytes);
+        ta.nxt_hi = reinterpret_cast<__half*>(reinterpret_cast<char*>(ws + L.t_hi) + (par ^ 1) * tile_bytes);
+        ta.nxt_lo = reinterpret_cast<__half*>(reinterpret_cast<char*>(ws + L.t_lo) + (par ^ 1) * tile_bytes);
+        ta.gi = ws + L.xproj + (size_t)t * 4 * H;
+        ta.out = outseq + (size_t)t * H;
+        TK(launch_tc_lstm_seq(ta, st));
+      }
+      in = outseq;
+      in_dim = H;
+      continue;
+    }
     for (int t = 0; t < T; ++t) {
       const float* g = ws + L.xproj + (size_t)t * 4 * H;  // row r of step t at + r*T*4H
       size_t ldg = (size_t)T * 4 * H;

@@ -108,6 +108,20 @@ struct TcGruArgs {
   int ldgi, ldout, KB, M, H, rows_pad, ndir;
 };
 cudaError_t launch_tc_gru(const TcGruArgs& a, cudaStream_t st);
+// one time step of an LSTM layer over M rows (any M; operand tiles hold rows_total = ceil128(M) rows per k-block)
+struct TcLstmSeqArgs {
+  const __half* a_hi;   // h_{t-1} tiles [H/64][rows_total][64]
+  const __half* a_lo;
+  __half* nxt_hi;       // h_t tiles (ping-pong)
+  __half* nxt_lo;
+  const __half* w;      // W_hh images, gates i|f|g|o interleaved per 8 units (tc_skinny_pack, lstm_H = H, N = 4H)
+  const float* gi;      // W_ih x_t + b_ih + b_hh for this step: row m at gi + m * ldgi
+  float* c;             // cell state [M][H] in/out
+  float* out;           // h_t destination: row m at out + m * ldout
+  float inv_scale;
+  int ldgi, ldout, KB, M, H, rows_total;
+};
+cudaError_t launch_tc_lstm_seq(const TcLstmSeqArgs& a, cudaStream_t st);
 size_t tc_gated_weight_bytes(int H, int K);
 size_t tc_skinny_weight_bytes(int N, int K);
 size_t tc_skinny_act_bytes(int M, int K);

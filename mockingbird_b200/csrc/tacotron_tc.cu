@@ -40,7 +40,8 @@ __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); 
 // epilogue warps with the 32 accumulator columns (already scaled, bias added) of row m.
 template <typename Epi>
 __device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* a_lo_g, const __half* w_g, const float* bias,
-                                            int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi) {
+                                            int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi,
+                                            size_t a_kb_stride = 0) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -52,6 +53,7 @@ __device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = (uint32_t)rows_pad * 128u;
+  if (a_kb_stride == 0) a_kb_stride = a_bytes;  // bytes between the k-blocks of the activation tiles
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -90,8 +92,8 @@ __device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* 
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * kStageBytes;
         mbar_expect_tx(&full[s], 2 * a_bytes + 2 * kWTile);
-        bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(a_hi_g) + (size_t)kb * a_bytes, a_bytes, &full[s]);
-        bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(a_lo_g) + (size_t)kb * a_bytes, a_bytes, &full[s]);
+        bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(a_hi_g) + (size_t)kb * a_kb_stride, a_bytes, &full[s]);
+        bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(a_lo_g) + (size_t)kb * a_kb_stride, a_bytes, &full[s]);
         bulk_g2s(smem_u32(st + 2 * kATile), wt + (size_t)kb * (2 * kWTile), 2 * kWTile, &full[s]);
       }
     }
@@ -216,6 +218,40 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gru_kernel(const __grid_consta
               });
 }
 
+// One time step of one LSTM layer over many rows (speaker encoder: rows = partial windows): blockIdx.x = 8 hidden
+// units, blockIdx.y = block of 128 rows.  gates = W_hh h_{t-1} (this GEMM) + gi (W_ih x_t + b_ih + b_hh, precomputed
+// for all t); c' = f c + i g, h' = o tanh(c') (ATen lstm_cell, gate order i|f|g|o).  h' goes to the layer's
+// output sequence and - as hi/lo operand chunks - into the next step's A tiles (ping-pong).
+__global__ void __launch_bounds__(kThreads, 1) tc_lstm_seq_kernel(const __grid_constant__ TcLstmSeqArgs p) {
+  const int tile = blockIdx.x, mb = blockIdx.y;
+  const int H = p.H;
+  const int rows_here = min(128, p.M - mb * 128);
+  const size_t blk = (size_t)mb * 128 * 128;  // byte offset of this row block inside a k-block slab
+  skinny_body(reinterpret_cast<const __half*>(reinterpret_cast<const char*>(p.a_hi) + blk),
+              reinterpret_cast<const __half*>(reinterpret_cast<const char*>(p.a_lo) + blk), p.w, nullptr, p.KB, rows_here, 128,
+              p.inv_scale, tile,
+              [&](int ml, float* v) {
+                const int m = mb * 128 + ml;
+                const float* gi = p.gi + (size_t)m * p.ldgi + (size_t)tile * 8;
+                float* cp = p.c + (size_t)m * H + (size_t)tile * 8;
+                float hn[8], cn[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float ig = sigm(v[e] + gi[e]), fg = sigm(v[8 + e] + gi[H + e]);
+                  const float cg = tanhf(v[16 + e] + gi[2 * H + e]), og = sigm(v[24 + e] + gi[3 * H + e]);
+                  cn[e] = fg * cp[e] + ig * cg;
+                  hn[e] = og * tanhf(cn[e]);
+                }
+                *reinterpret_cast<float4*>(cp) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                *reinterpret_cast<float4*>(cp + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                float* op = p.out + (size_t)m * p.ldout + (size_t)tile * 8;
+                *reinterpret_cast<float4*>(op) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(op + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                store_split_chunk(hn, m, p.rows_total, tile * 8, p.nxt_hi, p.nxt_lo);
+              },
+              (size_t)p.rows_total * 128);
+}
+
 __device__ __forceinline__ __half split_hi(float v) { return __float2half_rn(v); }
 __device__ __forceinline__ __half split_lo(float v) { return __float2half_rn(v - __half2float(__float2half_rn(v))); }
 
@@ -338,6 +374,19 @@ cudaError_t launch_act_split(const float* s0, int K0, int ld0, const float* s1, 
   const int rows_pad = M <= 64 ? 64 : 128;
   const int n = KB * rows_pad * 8;
   act_split_kernel<<<(n + 255) / 256, 256, 0, st>>>(s0, K0, ld0, s1, K1, ld1, M, rows_pad, KB, a_hi, a_lo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_lstm_seq(const TcLstmSeqArgs& a, cudaStream_t st) {
+  if (a.M <= 0 || a.H <= 0 || a.H % 8 || a.KB <= 0 || a.rows_total % 128 || a.rows_total < a.M) return cudaErrorInvalidValue;
+  constexpr size_t smem = kStages * kStageBytes + 1024 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  tc_lstm_seq_kernel<<<dim3(a.H / 8, (a.M + 127) / 128), kThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
