@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -284,6 +285,7 @@ struct mb_tacotron {
   std::map<std::string, float> tc_inv_scale;  // tensor-core weight images: 1 / pack scale per tensor
   // generate() runs on an internal non-blocking stream ordered after / before the caller's stream by events: the
   // decoder loop is replayed from a CUDA graph, and stream capture is not allowed on the legacy default stream
+  std::set<std::string> big_packed;  // CBHG GEMMs whose tensor-core images ("<key>.bigw") are packed
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
@@ -311,6 +313,13 @@ void cbhg_slots(mb_tacotron* h, const std::string& p, int K, int cin, int ch, in
   bnconv(p + ".conv_project1", K * ch, p0, 3);
   bnconv(p + ".conv_project2", p0, p1, 3);
   if (p1 != ch) slot(h, p + ".pre_highway.weight", (size_t)ch * p1);
+  // derived: tensor-core images of the large-M GEMMs (cbhg_gemm), packed on first use
+  for (int i = 0; i < K; ++i) slot(h, p + ".conv1d_bank." + std::to_string(i) + ".bigw", tc_big_weight_bytes(ch, i + 1, cin) / 4);
+  slot(h, p + ".conv_project1.bigw", tc_big_weight_bytes(p0, 3, K * ch) / 4);
+  slot(h, p + ".conv_project2.bigw", tc_big_weight_bytes(p1, 3, p0) / 4);
+  if (p1 != ch) slot(h, p + ".pre_highway.bigw", tc_big_weight_bytes(ch, 1, p1) / 4);
+  for (int i = 0; i < nh; ++i) slot(h, p + ".highways." + std::to_string(i) + ".bigw", tc_big_weight_bytes(2 * ch, 1, ch) / 4);
+  for (const char* sfx : {"", "_reverse"}) slot(h, p + ".rnn.ih" + sfx + ".bigw", tc_big_weight_bytes(3 * (ch / 2), 1, ch) / 4);
   for (int i = 0; i < nh; ++i) {
     const std::string q = p + ".highways." + std::to_string(i);
     slot(h, q + ".W1.weight", (size_t)ch * ch);
@@ -336,6 +345,7 @@ struct Ws {
   size_t ids, emb, m_enc, p1, x0, bank, pool, pj1, y, hw12, gi_f, gi_b, gh, hst, seq, proj, style_q, style;
   // decoder
   size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, ah_hi, ah_lo, stopv, step, flags, dmask;
+  size_t big_hi, big_lo, big_bytes;
   // outputs / postnet
   size_t mel_all, scores_all, pbank, ppool, ppj1, ppj2, py, phw12, pgi_f, pgi_b, pgh, phst, pout, lin;
   size_t total;
@@ -406,6 +416,12 @@ Ws ws_layout(const mb_tacotron_config& c, int B, int Tc, int steps, int r) {
   L.phst = take((size_t)2 * B * (PD / 2));
   L.pout = take(Mp * PD);
   L.lin = take(Mp * c.n_mels);
+  {  // im2col operand planes of the large-M tensor-core GEMMs: the widest layer is conv_project1 (3 taps x K * ch)
+    const size_t enc = tc_big_act_bytes((int)Me, 3, c.encoder_K * E), post = tc_big_act_bytes((int)Mp, 3, c.postnet_K * PD);
+    L.big_bytes = enc > post ? enc : post;
+    L.big_hi = take(L.big_bytes / 4);
+    L.big_lo = take(L.big_bytes / 4);
+  }
   L.total = o;
   return L;
 }
@@ -435,12 +451,108 @@ GemmArgs gemm1(const float* x, int K, int ld, const float* W, int ldw, const flo
   return a;
 }
 
+struct BigWs {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  size_t bytes = 0;
+};
+
+// A large-M GEMM / conv of the CBHG stacks: tensor cores (tc_big_kernel, 3-term fp16 split) when the layer qualifies,
+// else the FP32 FFMA kernels.  MB_TACO_CONV_TC=0 disables the tensor-core route.
+int cbhg_gemm(mb_tacotron* h, const std::string& key, const GemmArgs& a, cudaStream_t st, const BigWs& bw) {
+  static const bool env = [] {
+    const char* e = getenv("MB_TACO_CONV_TC");
+    return e ? atoi(e) != 0 : true;
+  }();
+  bool ok = env && bw.hi && a.M >= 512 && a.N % 4 == 0 && a.nseg >= 1 && a.nseg <= kMaxSeg && !a.mask && !a.step_mode &&
+            a.act != ACT_SIGMOID && a.act != ACT_TANH && h->slots.count(key + ".bigw") && (a.ldy % 4) == 0 &&
+            (!a.res || (a.ldres % 4) == 0);
+  const int K = a.seg[0].K;
+  for (int s = 1; ok && s < a.nseg; ++s) ok = a.seg[s].K == K;
+  if (ok) ok = tc_big_act_bytes(a.M, a.nseg, K) <= bw.bytes && tc_big_weight_bytes(a.N, a.nseg, K) / 4 <= h->slots[key + ".bigw"].n;
+  if (!ok) {
+    TK(launch_gemm(a, st));
+    return MB_OK;
+  }
+  const int KBs = (K + 63) / 64;
+  __half* wimg = reinterpret_cast<__half*>(P(h, key + ".bigw"));
+  if (!h->big_packed.count(key)) {
+    unsigned int* dmax = nullptr;
+    MB_CUDA_CHECK(cudaMalloc(&dmax, sizeof(unsigned int)));
+    MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, sizeof(unsigned int), st));
+    TK(tc_skinny_absmax(a.W, (size_t)a.N * a.ldw, dmax, st));
+    unsigned int hmax = 0;
+    MB_CUDA_CHECK(cudaMemcpyAsync(&hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    MB_CUDA_CHECK(cudaFree(dmax));
+    float mx;
+    memcpy(&mx, &hmax, sizeof(float));
+    int e = 0;
+    if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);
+    TcBigPack q;
+    memset(&q, 0, sizeof(q));
+    q.W = a.W;
+    q.ldw = a.ldw;
+    q.N = a.N;
+    q.nseg = a.nseg;
+    q.K = K;
+    q.KBs = KBs;
+    for (int s = 0; s < a.nseg; ++s) {
+      q.w_off[s] = a.seg[s].w_off;
+      q.w_stride[s] = a.seg[s].w_stride;
+    }
+    q.scale = ldexpf(1.f, 12 - e);
+    h->tc_inv_scale[key + ".bigw"] = 1.f / q.scale;
+    TK(launch_pack_big_w(q, wimg, st));
+    h->big_packed.insert(key);
+  }
+  TcIm2col q;
+  memset(&q, 0, sizeof(q));
+  for (int s = 0; s < a.nseg; ++s) {
+    q.x[s] = a.seg[s].x;
+    q.ld[s] = a.seg[s].ld;
+    q.shift[s] = a.seg[s].shift;
+  }
+  q.nseg = a.nseg;
+  q.K = K;
+  q.KBs = KBs;
+  q.M = a.M;
+  q.T = a.T > 0 ? a.T : 1;
+  q.rows_total = (a.M + 127) / 128 * 128;
+  TK(launch_im2col_split(q, reinterpret_cast<__half*>(bw.hi), reinterpret_cast<__half*>(bw.lo), st));
+  TcBigArgs t;
+  memset(&t, 0, sizeof(t));
+  t.a_hi = reinterpret_cast<const __half*>(bw.hi);
+  t.a_lo = reinterpret_cast<const __half*>(bw.lo);
+  t.w = wimg;
+  t.bias = a.bias;
+  t.KB = a.nseg * KBs;
+  t.M = a.M;
+  t.N = a.N;
+  t.rows_total = q.rows_total;
+  t.act = a.act;
+  t.inv_scale = h->tc_inv_scale[key + ".bigw"];
+  t.bn_scale = a.bn_scale;
+  t.bn_shift = a.bn_shift;
+  t.res = a.res;
+  t.ldres = a.ldres;
+  t.y = a.Y;
+  t.ldy = a.ldy;
+  TK(launch_tc_big(t, st));
+  return MB_OK;
+}
+
 // CBHG (sublayer/cbhg.py:42-79) on x [B*T][cin] channels-last -> out [B*T][ch] written at out (ld ldout)
 int run_cbhg(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p0, int p1, int nh, const float* x, int B,
              int T, float* bank, float* pool, float* pj1, float* y, float* hw12, float* gi_f, float* gi_b, float* gh,
              float* hst, float* out, int ldout, cudaStream_t st, float* tc_hi = nullptr, float* tc_lo = nullptr,
-             size_t tc_bytes = 0) {
+             size_t tc_bytes = 0, const BigWs& bw = BigWs()) {
   const int M = B * T;
+#define CG(key, args)                                 \
+  do {                                                \
+    int _rc = cbhg_gemm(h, (key), (args), st, bw);    \
+    if (_rc != MB_OK) return _rc;                     \
+  } while (0)
   // convolution bank: k = 1..K, "same" padding k//2 cropped to T, ReLU then BatchNorm
   for (int i = 0; i < K; ++i) {
     const int k = i + 1;
@@ -459,7 +571,7 @@ int run_cbhg(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p
     a.bn_shift = P(h, n + ".bn_shift");
     a.Y = bank + (size_t)i * ch;
     a.ldy = K * ch;
-    TK(launch_gemm(a, st));
+    CG(n, a);
   }
   TK(launch_maxpool2(bank, pool, B, T, K * ch, st));
   {
@@ -477,7 +589,7 @@ int run_cbhg(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p
     a.bn_shift = P(h, p + ".conv_project1.bn_shift");
     a.Y = pj1;
     a.ldy = p0;
-    TK(launch_gemm(a, st));
+    CG(p + ".conv_project1", a);
   }
   float* cur = y;  // [M][ch] highway stream
   {
@@ -499,29 +611,29 @@ int run_cbhg(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p
     if (p1 != ch) {
       a.Y = hw12;  // scratch: [M][p1] before the pre_highway projection
       a.ldy = p1;
-      TK(launch_gemm(a, st));
+      CG(p + ".conv_project2", a);
       GemmArgs b = gemm1(hw12, p1, p1, P(h, p + ".pre_highway.weight"), p1, nullptr, M, ch, cur, ch);
-      TK(launch_gemm(b, st));
+      CG(p + ".pre_highway", b);
     } else {
       a.Y = cur;
       a.ldy = ch;
-      TK(launch_gemm(a, st));
+      CG(p + ".conv_project2", a);
     }
   }
   for (int i = 0; i < nh; ++i) {
     const std::string q = p + ".highways." + std::to_string(i);
     GemmArgs a = gemm1(cur, ch, ch, P(h, q + ".W12"), ch, P(h, q + ".b12"), M, 2 * ch, hw12, 2 * ch);
-    TK(launch_gemm(a, st));
+    CG(q, a);
     TK(launch_highway(hw12, cur, M, ch, st));
   }
   // bidirectional GRU: input projections for all t, then the two recurrences
   const int H = ch / 2;
   {
     GemmArgs a = gemm1(cur, ch, ch, P(h, p + ".rnn.weight_ih_l0"), ch, P(h, p + ".rnn.bias_ih_l0"), M, 3 * H, gi_f, 3 * H);
-    TK(launch_gemm(a, st));
+    CG(p + ".rnn.ih", a);
     GemmArgs b = gemm1(cur, ch, ch, P(h, p + ".rnn.weight_ih_l0_reverse"), ch, P(h, p + ".rnn.bias_ih_l0_reverse"), M, 3 * H,
                        gi_b, 3 * H);
-    TK(launch_gemm(b, st));
+    CG(p + ".rnn.ih_reverse", b);
   }
   const size_t tile_bytes = tc_skinny_act_bytes(B, H);
   if (tc_hi && tc_lo && B <= 128 && H % 64 == 0 && 4 * tile_bytes <= tc_bytes) {
@@ -677,6 +789,7 @@ int mb_tacotron_create(const mb_tacotron_config* cfg, mb_tacotron** out) {
   slot(h, "decoder.stop_proj.bias", 1);
   cbhg_slots(h, "postnet", c.postnet_K, c.n_mels, c.postnet_dims, c.postnet_dims, c.n_mels, c.num_highways);
   slot(h, "post_proj.weight", (size_t)c.n_mels * c.postnet_dims);
+  slot(h, "post_proj.bigw", tc_big_weight_bytes(c.n_mels, 1, c.postnet_dims) / 4);
   *out = h;
   return MB_OK;
 }
@@ -723,7 +836,7 @@ int mb_tacotron_finalize(mb_tacotron* h, void* stream) {
     return n.find(".bn_scale") != std::string::npos || n.find(".bn_shift") != std::string::npos ||
            n.find(".W12") != std::string::npos || n.find(".b12") != std::string::npos || n == "gst.tanh_embed" ||
            n == "gst.keys" || n == "gst.values" || n.find(".bias_sum") != std::string::npos || n.find(".tcw") != std::string::npos ||
-           n.find(".tcb") != std::string::npos || n.find(".tcw") != std::string::npos ||
+           n.find(".tcb") != std::string::npos || n.find(".tcw") != std::string::npos || n.find(".bigw") != std::string::npos ||
            n == "decoder.mel_proj.packed";
   };
   for (auto& kv : h->slots)
@@ -838,6 +951,10 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
     return e ? atoi(e) != 0 : true;
   }();
   const bool use_tc = tc_env && B <= 128 && LD % 64 == 0;
+  BigWs bw;
+  bw.hi = ws + L.big_hi;
+  bw.lo = ws + L.big_lo;
+  bw.bytes = L.big_bytes;
   const int SE = c.speaker_embedding_size, proj_dims = E + SE + c.gst_E;
   const int Me = B * Tc;
 
@@ -874,7 +991,7 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   float* seq = ws + L.seq;
   int rc = run_cbhg(h, "encoder.cbhg", c.encoder_K, E, E, E, E, c.num_highways, ws + L.x0, B, Tc, ws + L.bank, ws + L.pool,
                     ws + L.pj1, ws + L.y, ws + L.hw12, ws + L.gi_f, ws + L.gi_b, ws + L.gh, ws + L.hst, seq, proj_dims, st,
-                    use_tc ? ws + L.a_hi : nullptr, use_tc ? ws + L.a_lo : nullptr, tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * LD));
+                    use_tc ? ws + L.a_hi : nullptr, use_tc ? ws + L.a_lo : nullptr, tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * LD), bw);
   if (rc != MB_OK) return rc;
   // speaker embedding per char (tacotron.py:236), style embedding (tacotron.py:238-253)
   TK(launch_copy_cols(spk, SE, Tc, seq, proj_dims, E, Me, SE, st));
@@ -1236,11 +1353,12 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   }
   rc = run_cbhg(h, "postnet", c.postnet_K, NM, PD, PD, NM, c.num_highways, melc, B, frames, ws + L.pbank, ws + L.ppool,
                 ws + L.ppj1, ws + L.py, ws + L.phw12, ws + L.pgi_f, ws + L.pgi_b, ws + L.pgh, ws + L.phst, ws + L.pout, PD, st,
-                use_tc ? ws + L.a_hi : nullptr, use_tc ? ws + L.a_lo : nullptr, tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * LD));
+                use_tc ? ws + L.a_hi : nullptr, use_tc ? ws + L.a_lo : nullptr, tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * LD), bw);
   if (rc != MB_OK) return rc;
   {
     GemmArgs a = gemm1(ws + L.pout, PD, PD, P(h, "post_proj.weight"), PD, nullptr, B * frames, NM, ws + L.lin, NM);
-    TK(launch_gemm(a, st));
+    int rc2 = cbhg_gemm(h, "post_proj", a, st, bw);
+    if (rc2 != MB_OK) return rc2;
   }
   // outputs in the reference's layouts: mel [B][80][frames], linear [B][80][frames], attn [B][nsteps][Tc]
   {

@@ -108,6 +108,41 @@ struct TcGruArgs {
   int ldgi, ldout, KB, M, H, rows_pad, ndir;
 };
 cudaError_t launch_tc_gru(const TcGruArgs& a, cudaStream_t st);
+// ---- large-M tensor-core GEMM / conv over time (CBHG stacks), 128 x 128 output tiles ---------------------------
+struct TcIm2col {       // im2col of the layer input into hi/lo operand tiles (one K segment per conv tap)
+  const float* x[kMaxSeg];
+  int ld[kMaxSeg];
+  int shift[kMaxSeg];
+  int nseg, K, KBs;     // K features per segment, KBs = ceil(K / 64) k-blocks per segment
+  int M, T, rows_total;
+};
+struct TcBigPack {      // weights as GemmArgs describes them: W[n * ldw + w_off_s + k * w_stride_s]
+  const float* W;
+  int ldw, N, nseg, K, KBs;
+  int w_off[kMaxSeg];
+  int w_stride[kMaxSeg];
+  float scale;
+};
+struct TcBigArgs {
+  const __half* a_hi;   // [nseg * KBs][rows_total][64]
+  const __half* a_lo;
+  const __half* w;      // [ceil(N / 128)][nseg * KBs][hi|lo][128][64]
+  const float* bias;    // [N] or nullptr (natural order)
+  int KB, M, N, rows_total, act;
+  float inv_scale;
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* res;
+  int ldres;
+  float* y;
+  int ldy;
+};
+size_t tc_big_weight_bytes(int N, int nseg, int K);
+size_t tc_big_act_bytes(int M, int nseg, int K);
+cudaError_t launch_im2col_split(const TcIm2col& q, __half* a_hi, __half* a_lo, cudaStream_t st);
+cudaError_t launch_pack_big_w(const TcBigPack& q, __half* dst, cudaStream_t st);
+cudaError_t launch_tc_big(const TcBigArgs& a, cudaStream_t st);
+
 // one time step of an LSTM layer over M rows (any M; operand tiles hold rows_total = ceil128(M) rows per k-block)
 struct TcLstmSeqArgs {
   const __half* a_hi;   // h_{t-1} tiles [H/64][rows_total][64]

@@ -28,20 +28,28 @@ namespace {
 
 using namespace tcdev;
 
-constexpr int kStages = 4;
+constexpr int kStages = 4;          // ring depth of the 32-column kernels
+constexpr int kBigStages = 3;       // ring depth of the 128-column kernel (64 KB per stage)
 constexpr int kThreads = 192;
 constexpr uint32_t kATile = 16384;  // 128 rows x 128 B (rows >= rows_pad stay zero)
 constexpr uint32_t kWTile = 4096;   // 32 rows x 128 B
 constexpr uint32_t kStageBytes = 2 * kATile + 2 * kWTile;
+template <int NT>
+__host__ __device__ constexpr uint32_t w_tile_bytes() { return (uint32_t)NT * 128u; }
+template <int NT>
+__host__ __device__ constexpr uint32_t stage_bytes() { return 2 * kATile + 2 * w_tile_bytes<NT>(); }
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
 // Shared main loop: operands for output tile `tile` stream through the ring; `epi(m, v)` is called by the
 // epilogue warps with the 32 accumulator columns (already scaled, bias added) of row m.
-template <typename Epi>
-__device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* a_lo_g, const __half* w_g, const float* bias,
-                                            int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi,
-                                            size_t a_kb_stride = 0) {
+template <int NT, int STAGES, typename Epi>
+__device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half* a_lo_g, const __half* w_g, const float* bias,
+                                              int n_valid, int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi,
+                                              size_t a_kb_stride = 0) {
+  constexpr int kStages = STAGES;
+  constexpr uint32_t kWTile = w_tile_bytes<NT>();
+  constexpr uint32_t kStageBytes = stage_bytes<NT>();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -64,11 +72,11 @@ __device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(NT)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x < 32) bias_s[threadIdx.x] = bias ? bias[tile * 32 + threadIdx.x] : 0.f;
+  if (threadIdx.x < NT) bias_s[threadIdx.x] = (bias && tile * NT + (int)threadIdx.x < n_valid) ? bias[tile * NT + threadIdx.x] : 0.f;
   if (rows_pad < 128) {
     // rows [rows_pad, 128) of every A slot are never written by the copies: zero them once
     const int nst = KB < kStages ? KB : kStages;
@@ -98,7 +106,7 @@ __device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* 
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t desc_hi = make_desc(0, 1024u, 2u, 0);
     const bool leader = elect_one();
     for (int kb = 0; kb < KB; ++kb) {
@@ -126,21 +134,33 @@ __device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* 
     const int m = quarter * 32 + lane;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    uint32_t raw[32];
-    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16), raw);
-    if (m < M) {
-      float v[32];
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, raw);
+      if (m < M) {
+        float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * inv_scale + bias_s[i];
-      epi(m, v);
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * inv_scale + bias_s[c0 + i];
+        epi(m, v, c0);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NT) : "memory");
   }
+}
+
+// the 32-column instance used by the recurrent kernels (bias already in tile order, all 32 columns valid)
+template <typename Epi>
+__device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* a_lo_g, const __half* w_g, const float* bias,
+                                            int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi,
+                                            size_t a_kb_stride = 0) {
+  skinny_body_t<32, kStages>(a_hi_g, a_lo_g, w_g, bias, 0x7fffffff, KB, M, rows_pad, inv_scale, tile,
+                             [&](int m, float* v, int) { epi(m, v); }, a_kb_stride);
 }
 
 // 8 fp32 values of row m, hidden units [u0, u0 + 8) -> the 16-byte chunk of the hi / lo operand tiles of the NEXT GEMM
@@ -250,6 +270,102 @@ __global__ void __launch_bounds__(kThreads, 1) tc_lstm_seq_kernel(const __grid_c
                 store_split_chunk(hn, m, p.rows_total, tile * 8, p.nxt_hi, p.nxt_lo);
               },
               (size_t)p.rows_total * 128);
+}
+
+// Large-M GEMM / Conv1d-over-time of the CBHG stacks (encoder, postnet), same 3-term split: blockIdx.x = 128 output
+// columns, blockIdx.y = 128 rows.  The operand tiles hold the im2col of the layer input (one K segment per conv
+// tap, im2col_split_kernel); epilogue = bias, ReLU, eval-BatchNorm affine (after the ReLU, batch_norm_conv.py:11-14),
+// residual -> fp32 channels-last.
+__global__ void __launch_bounds__(kThreads, 1) tc_big_kernel(const __grid_constant__ TcBigArgs p) {
+  const int tile = blockIdx.x, mb = blockIdx.y;
+  const int rows_here = min(128, p.M - mb * 128);
+  const size_t blk = (size_t)mb * 128 * 128;
+  skinny_body_t<128, kBigStages>(
+      reinterpret_cast<const __half*>(reinterpret_cast<const char*>(p.a_hi) + blk),
+      reinterpret_cast<const __half*>(reinterpret_cast<const char*>(p.a_lo) + blk), p.w, p.bias, p.N, p.KB, rows_here, 128,
+      p.inv_scale, tile,
+      [&](int ml, float* v, int c0) {
+        const int m = mb * 128 + ml;
+        const int n0 = tile * 128 + c0;
+        if (n0 >= p.N) return;
+        float* y = p.y + (size_t)m * p.ldy + n0;
+        const float* res = p.res ? p.res + (size_t)m * p.ldres + n0 : nullptr;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          if (n0 + i >= p.N) break;
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float t = v[i + e];
+            if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
+            if (p.bn_scale) t = fmaf(t, p.bn_scale[n0 + i + e], p.bn_shift[n0 + i + e]);
+            if (res) t += res[i + e];
+            o[e] = t;
+          }
+          *reinterpret_cast<float4*>(y + i) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      },
+      (size_t)p.rows_total * 128);
+}
+
+// im2col of a channels-last fp32 tensor into hi / lo operand tiles [nseg * KBs][rows_total][64]: segment s holds
+// x[row + shift_s][0 .. K) (zero outside the row's own length-T sequence, zero for k >= K and rows >= M)
+__global__ void im2col_split_kernel(const TcIm2col q, __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 16-byte chunk
+  const size_t total = (size_t)q.nseg * q.KBs * q.rows_total * 8;
+  if (i >= total) return;
+  const int c8 = (int)(i & 7);
+  const int m = (int)((i >> 3) % q.rows_total);
+  const int kb = (int)(i / ((size_t)8 * q.rows_total));
+  const int sg = kb / q.KBs, kbs = kb - sg * q.KBs;
+  __align__(16) __half hi[8], lo[8];
+  bool ok = m < q.M;
+  int row = m;
+  if (ok && q.shift[sg] != 0) {
+    const int t = m % q.T + q.shift[sg];
+    ok = (t >= 0 && t < q.T);
+    row = m + q.shift[sg];
+  }
+  const float* src = q.x[sg] + (size_t)row * q.ld[sg];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kbs * 64 + c8 * 8 + e;
+    const float v = (ok && k < q.K) ? src[k] : 0.f;
+    hi[e] = __float2half_rn(v);
+    lo[e] = __float2half_rn(v - __half2float(hi[e]));
+  }
+  const size_t o = ((size_t)kb * q.rows_total + m) * 8 + (size_t)(c8 ^ (m & 7));
+  reinterpret_cast<uint4*>(a_hi)[o] = *reinterpret_cast<const uint4*>(hi);
+  reinterpret_cast<uint4*>(a_lo)[o] = *reinterpret_cast<const uint4*>(lo);
+}
+
+// weights described like GemmArgs segments (W[n * ldw + w_off_s + k * w_stride_s]) * scale -> tiles
+// [n_tile(128)][nseg * KBs][hi|lo][128][64]
+__global__ void pack_big_w_kernel(const TcBigPack q, __half* __restrict__ dst) {
+  const size_t n_tiles = (size_t)(q.N + 127) / 128;
+  const size_t KB = (size_t)q.nseg * q.KBs;
+  const size_t total = n_tiles * KB * 128 * 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i & 7);
+  const int n = (int)((i >> 3) & 127);
+  const int kb = (int)((i >> 10) % KB);
+  const int j = (int)(i / ((size_t)1024 * KB));
+  const int sg = kb / q.KBs, kbs = kb - sg * q.KBs;
+  const int row = 128 * j + n;
+  __align__(16) __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kbs * 64 + c8 * 8 + e;
+    float v = 0.f;
+    if (row < q.N && k < q.K) v = q.W[(size_t)row * q.ldw + q.w_off[sg] + (size_t)k * q.w_stride[sg]] * q.scale;
+    hi[e] = __float2half_rn(v);
+    lo[e] = __float2half_rn(v - __half2float(hi[e]));
+  }
+  const size_t t = ((size_t)j * KB + kb) * 2;
+  const size_t o = (size_t)n * 8 + (size_t)(c8 ^ (n & 7));
+  reinterpret_cast<uint4*>(dst)[(t + 0) * 1024 + o] = *reinterpret_cast<const uint4*>(hi);
+  reinterpret_cast<uint4*>(dst)[(t + 1) * 1024 + o] = *reinterpret_cast<const uint4*>(lo);
 }
 
 __device__ __forceinline__ __half split_hi(float v) { return __float2half_rn(v); }
@@ -374,6 +490,38 @@ cudaError_t launch_act_split(const float* s0, int K0, int ld0, const float* s1, 
   const int rows_pad = M <= 64 ? 64 : 128;
   const int n = KB * rows_pad * 8;
   act_split_kernel<<<(n + 255) / 256, 256, 0, st>>>(s0, K0, ld0, s1, K1, ld1, M, rows_pad, KB, a_hi, a_lo);
+  return cudaGetLastError();
+}
+
+size_t tc_big_weight_bytes(int N, int nseg, int K) {
+  return (size_t)((N + 127) / 128) * nseg * ((K + 63) / 64) * 2 * w_tile_bytes<128>();
+}
+size_t tc_big_act_bytes(int M, int nseg, int K) {  // one plane (hi or lo)
+  return (size_t)nseg * ((K + 63) / 64) * ((size_t)(M + 127) / 128 * 128) * 128;
+}
+
+cudaError_t launch_im2col_split(const TcIm2col& q, __half* a_hi, __half* a_lo, cudaStream_t st) {
+  const size_t total = (size_t)q.nseg * q.KBs * q.rows_total * 8;
+  im2col_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q, a_hi, a_lo);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_big_w(const TcBigPack& q, __half* dst, cudaStream_t st) {
+  const size_t total = (size_t)((q.N + 127) / 128) * q.nseg * q.KBs * 1024;
+  pack_big_w_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_big(const TcBigArgs& a, cudaStream_t st) {
+  if (a.M <= 0 || a.N <= 0 || a.N % 4 || a.KB <= 0 || a.rows_total % 128 || a.rows_total < a.M) return cudaErrorInvalidValue;
+  constexpr size_t smem = kBigStages * stage_bytes<128>() + 1024 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  tc_big_kernel<<<dim3((a.N + 127) / 128, (a.M + 127) / 128), kThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -74,6 +74,28 @@ def test_vs_oracle_longer_and_early_stop(sd, model):
     assert mel.shape[2] < steps  # the min_stop_token=4 run stopped early
 
 
+def test_large_batch_tensor_core_cbhg(sd, model):
+    """B = 12 x 48 chars (576 encoder rows) x 96 frames (1152 postnet rows): the CBHG convolutions, highways and GRU
+    input projections take the large-M tensor-core route (3-term fp16 split) - same FP32-level tolerance vs the oracle"""
+    g = torch.Generator().manual_seed(321)
+    B, Tc, steps = 12, 48, 96
+    chars = torch.randint(2, 75, (B, Tc), generator=g)
+    chars[2, 30:] = 0
+    chars[7, 11:] = 0
+    emb = torch.rand(B, 256, generator=g)
+    emb = emb / emb.norm(dim=1, keepdim=True)
+    nst = steps // 2
+    enc = (torch.rand(2, B, Tc, 256, generator=g) < 0.5)
+    dec = (torch.rand(nst, 2, B, 256, generator=g) < 0.5)
+    masks = [enc[0], enc[1]] + [dec[i, j] for i in range(nst) for j in range(2)]
+    mel_r, lin_r, attn_r = to.generate(sd, chars, emb, steps, -1, 10, masks, r=2)
+    mel, lin, attn = model.generate(chars, emb, steps=steps, style_idx=-1, min_stop_token=10, dropout_masks=(enc, dec))
+    assert mel.shape == mel_r.shape == (B, 80, steps)
+    assert _rel(mel.cpu(), mel_r) <= TOL, _rel(mel.cpu(), mel_r)
+    assert _rel(lin.cpu(), lin_r) <= TOL, _rel(lin.cpu(), lin_r)
+    assert _rel(attn.cpu(), attn_r) <= TOL, _rel(attn.cpu(), attn_r)
+
+
 def test_device_dropout_is_seeded(model):
     chars = torch.randint(2, 75, (2, 10), generator=torch.Generator().manual_seed(1))
     emb = torch.rand(2, 256, generator=torch.Generator().manual_seed(2))
