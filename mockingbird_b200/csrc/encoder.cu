@@ -34,6 +34,8 @@ struct mb_encoder {
   float* arena = nullptr;
   bool finalized = false;
   float tc_inv_scale[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+  float big_inv_scale[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};  // input-projection images (packed on first use)
+  bool big_packed[8] = {false, false, false, false, false, false, false, false};
 };
 
 namespace {
@@ -131,7 +133,7 @@ GemmArgs gemm1(const float* x, int K, int ld, const float* W, int ldw, const flo
 }
 
 struct Ws {
-  size_t xproj, seq0, seq1, gates, c, raw, t_hi, t_lo, total;
+  size_t xproj, seq0, seq1, gates, c, raw, t_hi, t_lo, big_hi, big_lo, total;
 };
 
 bool enc_use_tc(const mb_encoder_config& c) {
@@ -161,6 +163,9 @@ Ws ws_layout(const mb_encoder_config& c, size_t R, size_t T) {
   const size_t tile_floats = (H / 64) * rows_total * 128 / 4;  // one operand plane (hi or lo) of h, in floats
   L.t_hi = take(2 * tile_floats);                               // two parities
   L.t_lo = take(2 * tile_floats);
+  const int kmax = c.hidden_size > c.mel_n_channels ? c.hidden_size : c.mel_n_channels;
+  L.big_hi = take(tc_big_act_bytes((int)(R * T), 1, kmax) / 4);  // operand tiles of the whole-sequence input projection
+  L.big_lo = take(tc_big_act_bytes((int)(R * T), 1, kmax) / 4);
   L.total = o;
   return L;
 }
@@ -187,6 +192,7 @@ int mb_encoder_create(const mb_encoder_config* cfg, mb_encoder** out) {
     slot(h, "lstm.bias_sum_l" + s, 4 * H);  // derived: b_ih + b_hh
     slot(h, "lstm.hh_tcw_l" + s, tc_gated_weight_bytes((int)H, (int)H) / 4);  // derived: tensor-core images of W_hh
     slot(h, "lstm.hh_tcb_l" + s, 4 * H);                                      // (unused zero bias of the images)
+    slot(h, "lstm.ih_bigw_l" + s, tc_big_weight_bytes((int)(4 * H), 1, (int)in) / 4);  // derived: images of W_ih
   }
   slot(h, "linear.weight", (size_t)c.embedding_size * H);
   slot(h, "linear.bias", c.embedding_size);
@@ -212,7 +218,7 @@ int mb_encoder_set_weight(mb_encoder* h, const char* name, const float* w, const
   if (!h->arena) return fail(MB_ERR_STATE, "mb_encoder_set_weight: call mb_encoder_set_arena first");
   auto it = h->slots.find(name);
   if (it == h->slots.end() || std::string(name).find("bias_sum") != std::string::npos ||
-      std::string(name).find("hh_tc") != std::string::npos)
+      std::string(name).find("hh_tc") != std::string::npos || std::string(name).find("ih_bigw") != std::string::npos)
     return fail(MB_ERR_INVALID, "mb_encoder_set_weight: unknown tensor '%s'", name);
   size_t n = 1;
   for (int i = 0; i < ndim; ++i) n *= (size_t)dims[i];
@@ -228,7 +234,8 @@ int mb_encoder_finalize(mb_encoder* h, void* stream) {
   if (!h) return fail(MB_ERR_INVALID, "mb_encoder_finalize: null handle");
   cudaStream_t st = (cudaStream_t)stream;
   for (auto& kv : h->slots)
-    if (!kv.second.set && kv.first.find("bias_sum") == std::string::npos && kv.first.find("hh_tc") == std::string::npos)
+    if (!kv.second.set && kv.first.find("bias_sum") == std::string::npos && kv.first.find("hh_tc") == std::string::npos &&
+        kv.first.find("ih_bigw") == std::string::npos)
       return fail(MB_ERR_STATE, "mb_encoder_finalize: tensor %s was never set", kv.first.c_str());
   const int n = 4 * h->cfg.hidden_size;
   for (int l = 0; l < h->cfg.num_layers; ++l) {
@@ -289,9 +296,69 @@ int mb_encoder_embed_frames(mb_encoder* h, const float* frames, int32_t rows, in
     const std::string s = std::to_string(l);
     float* outseq = seq[l & 1];
     // input projection of the whole sequence: xproj[r*T + t] = W_ih x_t + (b_ih + b_hh)
-    GemmArgs a = gemm1(in, in_dim, in_dim, P(h, "lstm.weight_ih_l" + s), in_dim, P(h, "lstm.bias_sum_l" + s), R * T, 4 * H,
-                       ws + L.xproj, 4 * H);
-    TK(launch_gemm(a, st));
+    if (enc_use_tc(c) && (size_t)R * T >= 512) {
+      // whole-sequence input projection on the 128x128-tile tensor-core GEMM (3-term split; images packed on first use)
+      __half* wimg = reinterpret_cast<__half*>(P(h, "lstm.ih_bigw_l" + s));
+      const int KBs = (in_dim + 63) / 64;
+      if (!h->big_packed[l]) {
+        unsigned int* dmax = nullptr;
+        MB_CUDA_CHECK(cudaMalloc(&dmax, sizeof(unsigned int)));
+        MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, sizeof(unsigned int), st));
+        TK(tc_skinny_absmax(P(h, "lstm.weight_ih_l" + s), (size_t)4 * H * in_dim, dmax, st));
+        unsigned int hmax = 0;
+        MB_CUDA_CHECK(cudaMemcpyAsync(&hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
+        MB_CUDA_CHECK(cudaStreamSynchronize(st));
+        MB_CUDA_CHECK(cudaFree(dmax));
+        float mx;
+        memcpy(&mx, &hmax, sizeof(float));
+        int e = 0;
+        if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);
+        TcBigPack q;
+        memset(&q, 0, sizeof(q));
+        q.W = P(h, "lstm.weight_ih_l" + s);
+        q.ldw = in_dim;
+        q.N = 4 * H;
+        q.nseg = 1;
+        q.K = in_dim;
+        q.KBs = KBs;
+        q.w_off[0] = 0;
+        q.w_stride[0] = 1;
+        q.scale = ldexpf(1.f, 12 - e);
+        h->big_inv_scale[l] = 1.f / q.scale;
+        TK(launch_pack_big_w(q, wimg, st));
+        h->big_packed[l] = true;
+      }
+      TcIm2col q;
+      memset(&q, 0, sizeof(q));
+      q.x[0] = in;
+      q.ld[0] = in_dim;
+      q.nseg = 1;
+      q.K = in_dim;
+      q.KBs = KBs;
+      q.M = R * T;
+      q.T = 1;
+      q.rows_total = (R * T + 127) / 128 * 128;
+      TK(launch_im2col_split(q, reinterpret_cast<__half*>(ws + L.big_hi), reinterpret_cast<__half*>(ws + L.big_lo), st));
+      TcBigArgs t;
+      memset(&t, 0, sizeof(t));
+      t.a_hi = reinterpret_cast<const __half*>(ws + L.big_hi);
+      t.a_lo = reinterpret_cast<const __half*>(ws + L.big_lo);
+      t.w = wimg;
+      t.bias = P(h, "lstm.bias_sum_l" + s);
+      t.KB = KBs;
+      t.M = R * T;
+      t.N = 4 * H;
+      t.rows_total = q.rows_total;
+      t.act = ACT_NONE;
+      t.inv_scale = h->big_inv_scale[l];
+      t.y = ws + L.xproj;
+      t.ldy = 4 * H;
+      TK(launch_tc_big(t, st));
+    } else {
+      GemmArgs a = gemm1(in, in_dim, in_dim, P(h, "lstm.weight_ih_l" + s), in_dim, P(h, "lstm.bias_sum_l" + s), R * T, 4 * H,
+                         ws + L.xproj, 4 * H);
+      TK(launch_gemm(a, st));
+    }
     const float* whh = P(h, "lstm.weight_hh_l" + s);
     if (enc_use_tc(c)) {
       const size_t rows_total = ((size_t)R + 127) / 128 * 128;
