@@ -366,10 +366,10 @@ def run_ours_hifigan(args):
     if rank == 0 and not args.no_cpu_baseline:
         threads = host_threads()
         log(f"cpu baseline on {threads} threads")
-        r = cpu_child("hifigan_cfg2", 2, threads, 240.0)
+        r = cpu_child("hifigan_cfg2", 4, threads, 240.0)
         if r is not None:
             cpu = {"value": r["value"], "unit": "samples/s", "cores": threads, "kind": "port",
-                   "sample": f"2 passes x 32 utterances x 256 frames ({r['seconds']:.1f} s), torch-CPU oracle "
+                   "sample": f"4 passes x 32 utterances x 256 frames ({r['seconds']:.1f} s), torch-CPU oracle "
                              "(bit-identical to the reference forward), batch-1 calls like hifigan/inference.py"}
     if rank == 0:
         line = {

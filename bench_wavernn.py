@@ -153,10 +153,10 @@ def run_ours(args):
             from bench import cpu_child, host_threads
 
             threads = host_threads()
-            r = cpu_child("wavernn_cfg3", 60, threads, 240.0)
+            r = cpu_child("wavernn_cfg3", 1200, threads, 240.0)
             v, dt = (r["value"], r["seconds"]) if r else (float("nan"), float("nan"))
             cpu = {"value": v * delivered / (folds * steps), "unit": "samples/s", "cores": threads, "kind": "port",
-                   "sample": f"60 of 8800 steps x 58 folds ({dt:.1f} s), C twin with OpenMP over folds; reference "
+                   "sample": f"1200 of 8800 steps x 58 folds ({dt:.1f} s), C twin with OpenMP over folds; reference "
                              "torch-CPU path: 11.5k samples/s on 8 cores (SURVEY.md section 6)"}
         print(json.dumps({
             "metric": "vocoder audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": k,
