@@ -81,14 +81,28 @@ __global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__
 #pragma unroll
     for (int f = 0; f < ATT_F; ++f) lreg[f] = s_Lt[f * ATT_D + d];
     const float vd = s_v[d], pqd = s_pq[d];
-    for (int t = tg; t < Tc; t += 2) {
-      float pl = 0.f;
-      const float* lc = s_loc + (size_t)t * ATT_F;
+    const float* pb = proj + (size_t)b * Tc * ATT_D + d;
+    // blocks of 8 time steps: the 8 (independent) loads of the processed memory are issued before any is used -
+    // a plain loop is bound by one L2 round trip per step
+    for (int t0 = tg; t0 < Tc; t0 += 16) {
+      float pr[8];
 #pragma unroll
-      for (int f = 0; f < ATT_F; ++f) pl = fmaf(lreg[f], lc[f], pl);
-      float e = vd * tanhf(pqd + proj[((size_t)b * Tc + t) * ATT_D + d] + pl);
-      for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-      if ((tid & 31) == 0) s_part[t * 4 + wq] = e;
+      for (int j = 0; j < 8; ++j) {
+        const int t = t0 + 2 * j;
+        pr[j] = t < Tc ? pb[(size_t)t * ATT_D] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int t = t0 + 2 * j;
+        if (t >= Tc) break;  // warp-uniform
+        float pl = 0.f;
+        const float* lc = s_loc + (size_t)t * ATT_F;
+#pragma unroll
+        for (int f = 0; f < ATT_F; ++f) pl = fmaf(lreg[f], lc[f], pl);
+        float e = vd * tanhf(pqd + pr[j] + pl);
+        for (int o = 16; o; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if ((tid & 31) == 0) s_part[t * 4 + wq] = e;
+      }
     }
   }
   __syncthreads();

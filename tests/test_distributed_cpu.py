@@ -66,3 +66,27 @@ def test_shard_is_a_partition_single_process():
         shards = [mbd.shard_utterances(lengths, r, ws) for r in range(ws)]
         assert sorted(i for s in shards for i in s) == list(range(len(lengths)))
         assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+
+
+def test_encoder_module_protocol_without_gpu():
+    """host-side surface of the speaker-encoder drop-in: names, defaults and error behaviour need no GPU"""
+    import numpy as np
+    import pytest
+
+    from mockingbird_b200.encoder import audio, inference
+
+    assert inference.partials_n_frames == 160 and inference.sampling_rate == 16000 and inference.mel_n_channels == 40
+    assert not inference.is_loaded() or inference._model is not None
+    saved = inference._model
+    inference._model = None
+    try:
+        with pytest.raises(Exception, match="Model was not loaded"):
+            inference.embed_frames_batch(np.zeros((1, 160, 40), np.float32))
+    finally:
+        inference._model = saved
+    with pytest.raises(NotImplementedError, match="N2"):
+        audio.wav_to_mel_spectrogram(np.zeros(16000, np.float32))
+    # every partial slice has the requested length and the wav / mel slices stay aligned (160 samples per frame)
+    w, m = inference.compute_partial_slices(40000, overlap=0.25)
+    assert all(s.stop - s.start == 160 for s in m)
+    assert all(ws.start == ms.start * 160 and ws.stop == ms.stop * 160 for ws, ms in zip(w, m))
