@@ -16,6 +16,7 @@
 //               warps 2-5 epilogue (TMEM lane = batch row)
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "gan_tc_dev.cuh"
@@ -91,6 +92,11 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM allocation, bias, zero fill) touched no tensor
+  // another kernel writes and may overlap the tail of the previous launch (recurrences are chains of these
+  // kernels); its outputs are only read below.  A plain launch makes both instructions no-ops.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -453,6 +459,27 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned in
 
 }  // namespace
 
+// launch with the programmatic-stream-serialization attribute (MB_TACO_PDL=0: plain launches)
+template <typename Args>
+cudaError_t launch_pdl(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& args) {
+  static const bool pdl = [] {
+    const char* e = getenv("MB_TACO_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
 size_t tc_skinny_weight_bytes(int N, int K) {
   const size_t n_tiles = (size_t)(N + 31) / 32, KB = (size_t)(K + 63) / 64;
   return n_tiles * KB * 2 * kWTile;
@@ -521,8 +548,7 @@ cudaError_t launch_tc_big(const TcBigArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  tc_big_kernel<<<dim3((a.N + 127) / 128, (a.M + 127) / 128), kThreads, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(tc_big_kernel, dim3((a.N + 127) / 128, (a.M + 127) / 128), smem, st, a);
 }
 
 cudaError_t launch_tc_lstm_seq(const TcLstmSeqArgs& a, cudaStream_t st) {
@@ -534,8 +560,7 @@ cudaError_t launch_tc_lstm_seq(const TcLstmSeqArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  tc_lstm_seq_kernel<<<dim3(a.H / 8, (a.M + 127) / 128), kThreads, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(tc_lstm_seq_kernel, dim3(a.H / 8, (a.M + 127) / 128), smem, st, a);
 }
 
 cudaError_t launch_tc_gru(const TcGruArgs& a, cudaStream_t st) {
@@ -549,8 +574,7 @@ cudaError_t launch_tc_gru(const TcGruArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  tc_gru_kernel<<<dim3(a.H / 8, a.ndir), kThreads, smem, st>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(tc_gru_kernel, dim3(a.H / 8, a.ndir), smem, st, p);
 }
 
 cudaError_t launch_tc_skinny(const TcSkinnyArgs& a, cudaStream_t st) {
@@ -564,8 +588,7 @@ cudaError_t launch_tc_skinny(const TcSkinnyArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  tc_skinny_kernel<<<(a.N + 31) / 32, kThreads, smem, st>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(tc_skinny_kernel, dim3((a.N + 31) / 32), smem, st, p);
 }
 
 }  // namespace taco
