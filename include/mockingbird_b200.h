@@ -267,6 +267,41 @@ int mb_encoder_embed_frames(mb_encoder* h, const float* frames, int32_t rows, in
 int mb_encoder_reduce_partials(mb_encoder* h, const float* partial_embeds, const int32_t* offsets,
                                int32_t n_utterances, float* utterance_embeds, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Mel-spectrogram front-ends
+ *   replaces  models/encoder/audio.py:53-65 (wav_to_mel_spectrogram: librosa.feature.melspectrogram, power, [frames][40])
+ *             models/synthesizer/audio.py:59-65,115-121,156-206 (melspectrogram: preemphasis, librosa.stft,
+ *             librosa.filters.mel, amp_to_db, symmetric normalisation to +-4)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mb_melspec_config {
+  int32_t sample_rate;
+  int32_t n_fft;          /* <= 2048 */
+  int32_t hop_length;
+  int32_t win_length;     /* periodic Hann, zero padded (centered) to n_fft */
+  int32_t n_mels;
+  float fmin, fmax;       /* Slaney mel scale, area-normalised triangles (librosa.filters.mel defaults) */
+  int32_t pad_mode;       /* centered frames: 0 = reflect padding, 1 = zero padding */
+  float preemphasis;      /* 0: none; else y[n] = x[n] - k x[n-1] before framing (synthesizer/audio.py:19-22) */
+  int32_t power;          /* 1: magnitude, 2: power spectrogram before the mel projection */
+  int32_t to_db;          /* 1: 20 log10(max(10^(min_level_db/20), x)) - ref_level_db (audio.py:133-135) */
+  float min_level_db, ref_level_db;
+  int32_t normalize;      /* 1: clip((2 A) (S - min_level_db) / (-min_level_db) - A, -A, A) if symmetric, else [0, A] */
+  float max_abs_value;
+  int32_t symmetric;
+  int32_t transpose_out;  /* 1: out [frames][n_mels] (encoder), 0: out [n_mels][frames] (synthesizer) */
+} mb_melspec_config;
+
+typedef struct mb_melspec mb_melspec;
+
+int mb_melspec_create(const mb_melspec_config* cfg, mb_melspec** out);
+void mb_melspec_destroy(mb_melspec* h);
+size_t mb_melspec_arena_bytes(const mb_melspec* h);
+/* uploads the window, the DFT twiddles and the mel basis (computed on the host at create time) */
+int mb_melspec_set_arena(mb_melspec* h, void* arena, size_t bytes, void* stream);
+int32_t mb_melspec_num_frames(const mb_melspec* h, int32_t n_samples);   /* 1 + n_samples / hop_length */
+/* wav fp32 [n_samples] (device) -> out fp32 [frames][n_mels] or [n_mels][frames] (device) */
+int mb_melspec_forward(mb_melspec* h, const float* wav, int32_t n_samples, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

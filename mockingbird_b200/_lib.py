@@ -67,6 +67,14 @@ class EncoderConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("mel_n_channels", "hidden_size", "num_layers", "embedding_size")]
 
 
+class MelSpecConfig(C.Structure):
+    _fields_ = [("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("hop_length", C.c_int32), ("win_length", C.c_int32),
+                ("n_mels", C.c_int32), ("fmin", C.c_float), ("fmax", C.c_float), ("pad_mode", C.c_int32),
+                ("preemphasis", C.c_float), ("power", C.c_int32), ("to_db", C.c_int32), ("min_level_db", C.c_float),
+                ("ref_level_db", C.c_float), ("normalize", C.c_int32), ("max_abs_value", C.c_float),
+                ("symmetric", C.c_int32), ("transpose_out", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/mockingbird_b200.h declares
 SIGNATURES = {
     "mb_last_error": (C.c_char_p, []),
@@ -126,6 +134,12 @@ SIGNATURES = {
     "mb_encoder_embed_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p]),
     "mb_encoder_reduce_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mb_melspec_create": (C.c_int, [C.POINTER(MelSpecConfig), C.POINTER(C.c_void_p)]),
+    "mb_melspec_destroy": (None, [C.c_void_p]),
+    "mb_melspec_arena_bytes": (C.c_size_t, [C.c_void_p]),
+    "mb_melspec_set_arena": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mb_melspec_num_frames": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "mb_melspec_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -93,8 +93,8 @@ def embed_utterances_frames(partials: Sequence[np.ndarray]) -> np.ndarray:
 
 
 def embed_utterance_frames(frames: np.ndarray, wav_len: int = None, using_partials=True, return_partials=False, **kwargs):
-    """embed_utterance (inference.py:128-172) from the utterance's mel frames [n_frames, 40]; the wav ->
-    mel front-end (encoder/audio.py:53-65, librosa) is SURVEY.md §8f row N2."""
+    """embed_utterance (inference.py:128-172) from the utterance's mel frames [n_frames, 40] (for callers that already
+    hold them; embed_utterance(wav) computes them with mockingbird_b200.encoder.audio)."""
     if not using_partials:
         embed = embed_frames_batch(frames[None, ...])[0]
         return (embed, None, None) if return_partials else embed
@@ -112,7 +112,7 @@ def embed_utterance_frames(frames: np.ndarray, wav_len: int = None, using_partia
 
 
 def embed_utterance(wav, using_partials=True, return_partials=False, **kwargs):
-    """inference.py:128-172.  Needs the 40-mel front-end (mockingbird_b200.encoder.audio)."""
+    """inference.py:128-172: wav -> 40-mel frames (device kernel) -> partial slices -> embeddings -> L2(mean)."""
     from . import audio
 
     if not using_partials:

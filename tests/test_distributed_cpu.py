@@ -84,8 +84,13 @@ def test_encoder_module_protocol_without_gpu():
             inference.embed_frames_batch(np.zeros((1, 160, 40), np.float32))
     finally:
         inference._model = saved
-    with pytest.raises(NotImplementedError, match="N2"):
-        audio.wav_to_mel_spectrogram(np.zeros(16000, np.float32))
+    import torch
+
+    if not torch.cuda.is_available():  # the front-end is a CUDA kernel: it must fail loudly, never fall back to the CPU
+        from mockingbird_b200 import _lib
+
+        with pytest.raises(_lib.MbError, match="no CPU fallback"):
+            audio.wav_to_mel_spectrogram(np.zeros(16000, np.float32))
     # every partial slice has the requested length and the wav / mel slices stay aligned (160 samples per frame)
     w, m = inference.compute_partial_slices(40000, overlap=0.25)
     assert all(s.stop - s.start == 160 for s in m)

@@ -171,3 +171,40 @@ def test_encoder_partial_slices_match_reference_rule():
         for n in (1000, 25601, 48000, 51199, 160000):
             for kw in ({}, {"overlap": 0.25}, {"rate": 1.3}, {"min_pad_coverage": 0.5}):
                 assert compute_partial_slices(n, **kw) == ref_inf.compute_partial_slices(n, **kw)
+
+
+def test_melspec_oracle_stft_matches_torch_and_mel_basis_matches_transformers():
+    """The mel front-end oracle cannot be pinned to the reference (librosa is absent and unpinned there); its two
+    halves are cross-checked against independent implementations of the same published algorithms instead."""
+    import melspec_oracle as mo
+
+    rng = np.random.default_rng(0)
+    y = (rng.standard_normal(5000) * 0.1).astype(np.float32)
+    for n_fft, hop, mode in ((400, 160, "reflect"), (1024, 256, "constant"), (1024, 256, "reflect")):
+        D = mo.stft(y, n_fft, hop, n_fft, mode)
+        T = torch.stft(torch.from_numpy(y).double(), n_fft, hop, n_fft,
+                       window=torch.hann_window(n_fft, periodic=True, dtype=torch.float64), center=True, pad_mode=mode,
+                       return_complex=True).numpy()
+        assert D.shape == T.shape == (1 + n_fft // 2, 1 + len(y) // hop)
+        assert np.abs(D - T).max() < 1e-10
+    # transformers.audio_utils.mel_filter_bank is an independent implementation of librosa.filters.mel; it runs in a
+    # fresh interpreter because the reference-import stubs of this test module shadow optional audio packages
+    import subprocess
+    import sys
+
+    code = ("import numpy as np, sys\n"
+            "from transformers.audio_utils import mel_filter_bank as m\n"
+            "np.savez(sys.argv[1], a=m(201, 40, 0.0, 8000.0, 16000, norm='slaney', mel_scale='slaney').T,"
+            " b=m(513, 80, 55.0, 7600.0, 16000, norm='slaney', mel_scale='slaney').T)\n")
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([sys.executable, "-c", code, d + "/mel.npz"], capture_output=True, text=True, timeout=300)
+        if r.returncode != 0:  # pragma: no cover
+            pytest.skip("transformers.audio_utils not usable: " + r.stderr[-200:])
+        z = np.load(d + "/mel.npz")
+        for key, (sr, n_fft, n_mels, fmin, fmax) in (("a", (16000, 400, 40, 0.0, 8000.0)), ("b", (16000, 1024, 80, 55.0, 7600.0))):
+            ours = mo.mel_basis(sr, n_fft, n_mels, fmin, fmax)
+            theirs = z[key]
+            assert ours.shape == theirs.shape
+            assert np.abs(ours - theirs).max() < 1e-6 * max(1.0, float(np.abs(theirs).max()))
