@@ -95,3 +95,29 @@ def test_encoder_module_protocol_without_gpu():
     w, m = inference.compute_partial_slices(40000, overlap=0.25)
     assert all(s.stop - s.start == 160 for s in m)
     assert all(ws.start == ms.start * 160 and ws.stop == ms.stop * 160 for ws, ms in zip(w, m))
+
+
+def test_vocoder_on_disk_formats(tmp_path):
+    """train.txt rows and [frames, 80] .npy mels"""
+    import numpy as np
+
+    from mockingbird_b200.vocoder import formats
+
+    mel = np.arange(7 * 80, dtype=np.float32).reshape(7, 80)
+    np.save(tmp_path / "mel-a.npy", mel, allow_pickle=False)
+    (tmp_path / "train.txt").write_text("audio-a.npy|mel-a.npy|embed-a.npy|1400|7|ni3 hao3\n"
+                                        "audio-b.npy|mel-b.npy|embed-b.npy|0|0|dropped\n"
+                                        "audio-c.npy|mel-c.npy|embed-c.npy|2000|10|text with | pipe\n", encoding="utf-8")
+    rows = formats.read_metadata(tmp_path / "train.txt")
+    assert [r.mel_fname for r in rows] == ["mel-a.npy", "mel-c.npy"]
+    assert rows[0].n_samples == 1400 and rows[0].n_frames == 7 and rows[0].text == "ni3 hao3"
+    assert rows[1].text == "text with | pipe"
+    m = formats.load_mel(tmp_path / "mel-a.npy")
+    assert m.shape == (80, 7) and m.dtype == np.float32 and m.flags["C_CONTIGUOUS"] and m[3, 2] == mel[2, 3]
+
+    class FakeVocoder:
+        def infer_waveform(self, mel):
+            return np.zeros(mel.shape[1] * 200, np.float32), 16000
+
+    wavs = formats.vocode_files([tmp_path / "mel-a.npy"], FakeVocoder())
+    assert len(wavs) == 1 and wavs[0].shape == (1400,)
