@@ -2,7 +2,7 @@
 """bench.py - headline benchmark of the B200 vocoder hot path (contract: see DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload hifigan_cfg2|wavernn_cfg3|tacotron_cfg4|e2e_cfg5] [--precision f16tc|fp32]
+                    [--workload hifigan_cfg2|fregan_cfg2|wavernn_cfg3|tacotron_cfg4|e2e_cfg5] [--precision f16tc|fp32]
 
 Default workload = BASELINE.json configs[1]: HiFi-GAN Generator forward, batch 32 random mels of
 256 frames x 80 bins, per GPU.  A "step" is one forward over one batch.  Prints ONE JSON line
@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hifigan_cfg2", choices=["hifigan_cfg2", "wavernn_cfg3", "tacotron_cfg4", "e2e_cfg5"])
+    ap.add_argument("--workload", default="hifigan_cfg2", choices=["hifigan_cfg2", "fregan_cfg2", "wavernn_cfg3", "tacotron_cfg4", "e2e_cfg5"])
     ap.add_argument("--precision", default=os.environ.get("MOCKINGBIRD_B200_GAN_PRECISION", "f16tc"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-child", nargs=3, default=None, help=argparse.SUPPRESS)
@@ -140,7 +140,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_hifigan(batch_rows: int, passes: int, threads: int):
+def cpu_hifigan(batch_rows: int, passes: int, threads: int, fregan: bool = False):
     """The CPU implementation (oracle port of the reference forward), batch-1 calls like
     hifigan/inference.py:66-70.  Returns (samples_per_s, seconds, samples)."""
     sys.path.insert(0, str(ROOT / "oracle"))
@@ -149,16 +149,17 @@ def cpu_hifigan(batch_rows: int, passes: int, threads: int):
     import ref_init as ri
 
     torch.set_num_threads(threads)
-    cfg = ri.HIFIGAN_CONFIG_16K
-    sd = ri.hifigan_state_dict(cfg, 0)
+    cfg = ri.FREGAN_CONFIG if fregan else ri.HIFIGAN_CONFIG_16K
+    sd = go.fold_weight_norm(ri.fregan_state_dict(cfg, 0)) if fregan else ri.hifigan_state_dict(cfg, 0)
+    fwd = go.fregan_forward if fregan else go.hifigan_forward
     mel = torch.rand(32, 80, 256, generator=torch.Generator().manual_seed(2)) * 8 - 4
     with torch.no_grad():
-        go.hifigan_forward(sd, cfg, mel[:1])  # warm-up
+        fwd(sd, cfg, mel[:1])  # warm-up
         t0 = time.perf_counter()
         n = 0
         for _ in range(passes):
             for i in range(batch_rows):
-                y = go.hifigan_forward(sd, cfg, mel[i:i + 1])
+                y = fwd(sd, cfg, mel[i:i + 1])
                 n += y.numel()
         dt = time.perf_counter() - t0
     return n / dt, dt, n
@@ -185,7 +186,7 @@ def run_reference(args):
     total = 0
     for s in range(args.warmup + args.steps):
         log(f"reference step {s}")
-        v, dt, n = cpu_hifigan(32, 1, threads)
+        v, dt, n = cpu_hifigan(32, 1, threads, fregan=(args.workload == "fregan_cfg2"))
         if s >= args.warmup:
             per_step.append(dt)
             total += n
@@ -196,7 +197,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "rtf": (secs / args.steps) / (32 * 51200 / 16000.0), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "hifigan_cfg2: Generator fwd, batch 32 x 256 frames x 80 mels (batch-1 calls)",
+        "config": {"workload": f"{args.workload}: Generator fwd, batch 32 x 256 frames x 80 mels (batch-1 calls)",
                    "per_gpu_batch": 32, "frames": 256},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x 32 utterances x 256 frames, torch-CPU oracle "
@@ -215,6 +216,7 @@ def run_ours_hifigan(args):
     sys.path.insert(0, str(ROOT / "oracle"))  # ref_init only: seeded random-init weights (no checkpoints exist)
     import ref_init as ri
     from mockingbird_b200 import _lib
+    from mockingbird_b200.vocoder.fregan.models import FreGAN
     from mockingbird_b200.vocoder.hifigan.models import Generator
 
     rank = int(os.environ.get("RANK", "0"))
@@ -227,16 +229,18 @@ def run_ours_hifigan(args):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = ri.HIFIGAN_CONFIG_16K
+    fre = args.workload == "fregan_cfg2"  # SURVEY.md row C1 on the same batch shape (not a BASELINE.json config)
+    cfg = ri.FREGAN_CONFIG if fre else ri.HIFIGAN_CONFIG_16K
+    make_sd = (lambda: ri.fregan_state_dict(cfg, 0)) if fre else (lambda: ri.hifigan_state_dict(cfg, 0))
     B, T = 32, 256
-    g = Generator(cfg, precision=args.precision).to(dev)
+    g = (FreGAN(cfg, precision=args.precision) if fre else Generator(cfg, precision=args.precision)).to(dev)
     # rank 0 builds + packs the weights, NCCL broadcasts the packed arena (the only collective)
     if rank == 0:
-        g.load_state_dict(ri.hifigan_state_dict(cfg, 0))
+        g.load_state_dict(make_sd())
         g.eval()
         g.remove_weight_norm()
     else:
-        g.load_state_dict(ri.hifigan_state_dict(cfg, 0))  # shapes only; contents overwritten below
+        g.load_state_dict(make_sd())  # shapes only; contents overwritten below
         g.eval()
         g.remove_weight_norm()
     if world > 1:
@@ -338,7 +342,7 @@ def run_ours_hifigan(args):
             traffic = None
             launches_per_fw = None
             tj = ROOT / "profiles" / "r01_hifigan_dram_traffic.json"
-            if tj.exists():
+            if tj.exists() and not fre:
                 tr = json.loads(tj.read_text())
                 traffic = tr["tc_dram_bytes_per_launch"]
                 launches_per_fw = tr["tc_launches_per_forward"]
@@ -357,7 +361,7 @@ def run_ours_hifigan(args):
                     "frac": tf / peak, "traffic": None, "peak_source": "nominal fp32 FFMA (parity-anchor path)",
                     "launches_timed": cnt, "share_of_step": (t_ms / reps) / ms_step}
         # north-star view: layer-granular fp32 bytes of the whole step / step time vs measured HBM copy BW
-        step_bytes = sum(v[2] for v in acc.values()) / reps + 51_902_980
+        step_bytes = sum(v[2] for v in acc.values()) / reps + (68_926_660 if fre else 51_902_980)  # + fp32 weights once
         gbs = step_bytes / (ms_step * 1e-3) / 1e9
         roof_hbm = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                     "bytes_per_step": step_bytes, "definition": "layer-granular fp32 bytes (SURVEY.md 8d) / step time"}
@@ -366,7 +370,7 @@ def run_ours_hifigan(args):
     if rank == 0 and not args.no_cpu_baseline:
         threads = host_threads()
         log(f"cpu baseline on {threads} threads")
-        r = cpu_child("hifigan_cfg2", 4, threads, 240.0)
+        r = cpu_child(args.workload, 4, threads, 240.0)
         if r is not None:
             cpu = {"value": r["value"], "unit": "samples/s", "cores": threads, "kind": "port",
                    "sample": f"4 passes x 32 utterances x 256 frames ({r['seconds']:.1f} s), torch-CPU oracle "
@@ -378,7 +382,7 @@ def run_ours_hifigan(args):
             "rtf": (ms_step * 1e-3) / (samples_per_step / 16000.0), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate + f32 residual" if args.precision == "f16tc" else "f32",
             "data": "synthetic",
-            "config": {"workload": "hifigan_cfg2: Generator fwd, batch 32 x 256 frames x 80 mels per GPU",
+            "config": {"workload": f"{args.workload}: Generator fwd, batch 32 x 256 frames x 80 mels per GPU",
                        "per_gpu_batch": B, "frames": T, "precision": args.precision, "parallelism": f"dp{world}",
                        "l2": "per-step working set (2.9 GB of activations) >> 126 MB L2; no explicit flush",
                        "weights": "random init, torch.manual_seed(0) order of the reference constructor"},
@@ -397,8 +401,8 @@ def main():
     args = parse()
     if args.cpu_child is not None:
         workload, amount, threads = args.cpu_child[0], int(args.cpu_child[1]), int(args.cpu_child[2])
-        if workload == "hifigan_cfg2":
-            v, dt, n = cpu_hifigan(32, amount, threads)
+        if workload in ("hifigan_cfg2", "fregan_cfg2"):
+            v, dt, n = cpu_hifigan(32, amount, threads, fregan=(workload == "fregan_cfg2"))
         elif workload == "tacotron_cfg4":
             import bench_tacotron
 
@@ -415,7 +419,7 @@ def main():
         return
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "hifigan_cfg2":
+    if args.workload in ("hifigan_cfg2", "fregan_cfg2"):
         return run_ours_hifigan(args)
     if args.workload == "tacotron_cfg4":
         import bench_tacotron
