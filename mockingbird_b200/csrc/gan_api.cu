@@ -1,6 +1,7 @@
 // GAN generator plan + C ABI (mb_gan_*): HiFi-GAN Generator.forward (hifigan/models.py:134-150) and
 // FreGAN.forward (fregan/generator.py:137-166) lowered to a list of tap-conv ops over a handful of
 // workspace buffers.  See include/mockingbird_b200.h for the contract.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@ struct Layer {
   OpKind kind = OP_CONV;
   std::string name;  // state_dict prefix ("ups.0", "resblocks.4.convs2.1", ...)
   int cin = 0, cout = 0, k = 1, dil = 1, stride = 1;
+  int cin_w = 0, cout_w = 0;  // channel counts of the checkpoint tensors (cin / cout may be zero-padded, see pad_channels)
   bool transposed = false;
   int nearest = 1;  // nearest-neighbour upsample factor in front of a 1x1 conv (Fre-GAN res_output)
   float in_slope = 1.f;
@@ -117,11 +119,26 @@ void touch(mb_gan* h, int buf, int c, int rate) {
   }
 }
 
+// Tensor-core path: internal tensors with fewer than 32 channels (Fre-GAN's full-rate stage has 16) are carried with
+// 32 channels, the extra ones identically zero (zero weight rows / columns and biases), so that the whole stage runs
+// on the C = 32 tcgen05 kernels instead of the FP32 FFMA kernels.  MB_GAN_PAD16=0 disables it.
+int pad_channels(const mb_gan* h, int c) {
+  static const bool env = [] {
+    const char* e = getenv("MB_GAN_PAD16");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return (env && h->cfg.precision == MB_PREC_F16TC && c > 1 && c < 32) ? 32 : c;
+}
+
 Layer& add_conv(mb_gan* h, const std::string& name, int cin, int cout, int k, int dil, int stride,
                 bool transposed, int nearest, float in_slope, int src, int dst, int res, int rate_in) {
   Layer L;
   L.kind = OP_CONV;
   L.name = name;
+  L.cin_w = cin;
+  L.cout_w = cout;
+  if (src != BUF_IN) cin = pad_channels(h, cin);
+  if (dst != BUF_OUT) cout = pad_channels(h, cout);
   L.cin = cin;
   L.cout = cout;
   L.k = k;
@@ -269,7 +286,8 @@ int build_plan(mb_gan* h) {
         Layer A;
         A.kind = OP_ADD;
         A.name = "output+=x";
-        A.cin = A.cout = ch;
+        A.cin_w = A.cout_w = ch;
+        A.cin = A.cout = pad_channels(h, ch);
         A.src = S;
         A.dst = output;
         A.rate_in = A.rate_out = rate;
@@ -417,18 +435,19 @@ int mb_gan_set_weight(mb_gan* h, const char* name, const float* w, const int64_t
   for (Layer& L : h->layers) {
     if (L.kind != OP_CONV || L.name != base) continue;
     if (leaf == "bias") {
-      if (ndim != 1 || dims[0] != L.cout)
-        return fail(MB_ERR_INVALID, "mb_gan_set_weight: %s expects [%d]", name, L.cout);
-      MB_CUDA_CHECK(cudaMemcpyAsync(h->arena + L.b_off, w, sizeof(float) * L.cout, cudaMemcpyDeviceToDevice, st));
+      if (ndim != 1 || dims[0] != L.cout_w)
+        return fail(MB_ERR_INVALID, "mb_gan_set_weight: %s expects [%d]", name, L.cout_w);
+      if (L.cout != L.cout_w) MB_CUDA_CHECK(cudaMemsetAsync(h->arena + L.b_off, 0, sizeof(float) * L.cout, st));
+      MB_CUDA_CHECK(cudaMemcpyAsync(h->arena + L.b_off, w, sizeof(float) * L.cout_w, cudaMemcpyDeviceToDevice, st));
       L.b_set = true;
       return MB_OK;
     }
     if (leaf == "weight") {
-      const int64_t d0 = L.transposed ? L.cin : L.cout, d1 = L.transposed ? L.cout : L.cin;
+      const int64_t d0 = L.transposed ? L.cin_w : L.cout_w, d1 = L.transposed ? L.cout_w : L.cin_w;
       if (ndim != 3 || dims[0] != d0 || dims[1] != d1 || dims[2] != L.k)
         return fail(MB_ERR_INVALID, "mb_gan_set_weight: %s expects [%lld,%lld,%d]", name, (long long)d0,
                     (long long)d1, L.k);
-      cudaError_t e = launch_pack_slabs_f32(w, h->arena + L.w_off, L.cout, L.cin, L.k, L.transposed, st);
+      cudaError_t e = launch_pack_slabs_f32(w, h->arena + L.w_off, L.cout_w, L.cin_w, L.k, L.transposed, st, L.cout, L.cin);
       if (e != cudaSuccess) return fail(MB_ERR_CUDA, "pack_slabs: %s", cudaGetErrorString(e));
       count_launch();
       if (h->cfg.precision == MB_PREC_F16TC) {
@@ -550,11 +569,11 @@ int mb_gan_layer_work(const mb_gan* h, int32_t i, int32_t batch, int32_t frames,
   if (L.kind == OP_CONV) {
     // every output row receives k/stride taps of Cin x Cout (transposed), or k taps (conv)
     const double taps = L.transposed ? (double)L.k / L.stride : (double)L.k;
-    if (macs) *macs = rows_out * taps * L.cin * L.cout;
-    if (bytes) *bytes = 4.0 * (rows_in * L.cin + rows_out * L.cout);
+    if (macs) *macs = rows_out * taps * L.cin_w * L.cout_w;  // algorithmic work: the checkpoint's channel counts
+    if (bytes) *bytes = 4.0 * (rows_in * L.cin_w + rows_out * L.cout_w);
   } else {
     if (macs) *macs = 0;
-    if (bytes) *bytes = 4.0 * 3.0 * rows_out * L.cout;
+    if (bytes) *bytes = 4.0 * 3.0 * rows_out * L.cout_w;
   }
   return MB_OK;
 }

@@ -244,8 +244,9 @@ __global__ void convert_layout_kernel(TRef src, TRef dst, int B, float slope) {
   tstore(dst, b, c, l, lrelu(tload(src, b, c, l), slope));
 }
 
+// dst slabs are [K][Cin_p][Cout_p] (Cin_p >= Cin, Cout_p >= Cout: zero-padded channels, the caller clears dst first)
 __global__ void pack_slabs_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cin,
-                                  int K, int transposed) {
+                                  int K, int transposed, int Cout_p, int Cin_p) {
   const size_t n = (size_t)Cout * Cin * K;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -253,7 +254,7 @@ __global__ void pack_slabs_kernel(const float* __restrict__ w, float* __restrict
   const int ci = (int)((i / Cout) % Cin);
   const int k = (int)(i / ((size_t)Cout * Cin));
   const size_t src = transposed ? ((size_t)ci * Cout + co) * K + k : ((size_t)co * Cin + ci) * K + k;
-  dst[i] = w[src];
+  dst[((size_t)k * Cin_p + ci) * Cout_p + co] = w[src];
 }
 
 }  // namespace
@@ -300,9 +301,15 @@ cudaError_t launch_convert_layout(const TRef& src, const TRef& dst, int B, float
 }
 
 cudaError_t launch_pack_slabs_f32(const float* w, float* dst, int Cout, int Cin, int K, bool transposed,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, int Cout_p, int Cin_p) {
   const size_t n = (size_t)Cout * Cin * K;
-  pack_slabs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w, dst, Cout, Cin, K, transposed ? 1 : 0);
+  if (Cout_p < Cout) Cout_p = Cout;
+  if (Cin_p < Cin) Cin_p = Cin;
+  if (Cout_p != Cout || Cin_p != Cin) {
+    cudaError_t e = cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)K * Cin_p * Cout_p, stream);
+    if (e != cudaSuccess) return e;
+  }
+  pack_slabs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w, dst, Cout, Cin, K, transposed ? 1 : 0, Cout_p, Cin_p);
   return cudaGetLastError();
 }
 

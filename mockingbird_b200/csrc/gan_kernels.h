@@ -105,8 +105,8 @@ cudaError_t launch_zero_pads_f16(const TRef& plane, int B, cudaStream_t stream);
 cudaError_t launch_convert_layout(const TRef& src, const TRef& dst, int B, float slope, cudaStream_t stream);
 
 // weight repack: Conv1d weight [Cout][Cin][K] or ConvTranspose1d weight [Cin][Cout][K]
-//   -> slabs [K][Cin][Cout]
+//   -> slabs [K][Cin_p][Cout_p] (zero-padded channels when Cin_p / Cout_p exceed the checkpoint's)
 cudaError_t launch_pack_slabs_f32(const float* w, float* dst, int Cout, int Cin, int K, bool transposed,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, int Cout_p = 0, int Cin_p = 0);
 
 }  // namespace mb
