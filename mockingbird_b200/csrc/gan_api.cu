@@ -130,6 +130,16 @@ int pad_channels(const mb_gan* h, int c) {
   return (env && h->cfg.precision == MB_PREC_F16TC && c > 1 && c < 32) ? 32 : c;
 }
 
+// run-time switches of the Fre-GAN lowering on the tensor-core path (A/B measurements):
+//   MB_FREGAN_SPLIT=0   keep "x += cond_up(mel)" fused as a second destination of the cond_up layer (FP32 kernel);
+//                       default: cond_up is a plain (tensor-core) transposed conv followed by an add op
+//   MB_GAN_NEAREST_TC=1 try the nearest-upsample + 1x1 layers (res_output) on the tensor cores (default 0: their source
+//                       buffer is also read by `ups` with a different activation, which the plane analysis rejects)
+bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) != 0 : dflt;
+}
+
 Layer& add_conv(mb_gan* h, const std::string& name, int cin, int cout, int k, int dil, int stride,
                 bool transposed, int nearest, float in_slope, int src, int dst, int res, int rate_in) {
   Layer L;
@@ -256,11 +266,23 @@ int build_plan(mb_gan* h) {
         const int dstc = (cond == CA) ? CB : CA;
         Layer& cu = add_conv(h, "cond_up." + std::to_string(j), cond_ch, ch, k, 1, u, true, 1, 1.f, cond, dstc,
                              BUF_NONE, cond_rate);
-        cu.dst2 = S;  // x += mel  (generator.py:143-144)
+        const bool split = c.precision == MB_PREC_F16TC && j > 0 && env_flag("MB_FREGAN_SPLIT", true);
+        if (!split) cu.dst2 = S;  // x += mel  (generator.py:143-144) fused as a second destination
         cond = dstc;
         cond_ch = ch;
         cond_rate *= u;
         if (cond_rate != rate) return fail(MB_ERR_INVALID, "mb_gan_create: fregan cond rate mismatch");
+        if (split) {  // x += mel as its own op, so that cond_up itself is tensor-core capable
+          Layer A;
+          A.kind = OP_ADD;
+          A.name = "x+=cond_up." + std::to_string(j);
+          A.cin_w = A.cout_w = ch;
+          A.cin = A.cout = pad_channels(h, ch);
+          A.src = dstc;
+          A.dst = S;
+          A.rate_in = A.rate_out = rate;
+          h->layers.push_back(A);
+        }
       }
       if (i > cond_level) {
         const int j = i - cond_level - 1;
@@ -391,7 +413,9 @@ int mb_gan_create(const mb_gan_config* cfg, mb_gan** out) {
     for (Layer& L : h->layers) {
       TcLayerDesc d{};
       d.is_conv = (L.kind == OP_CONV);
-      d.force_f32 = (L.dst2 != BUF_NONE) || (L.nearest > 1);
+      // (res_output reads its source un-activated while ups reads the same buffer through leaky-relu: one fp16 plane
+      //  cannot serve both, so the nearest-upsample layers stay on the FP32 kernel unless explicitly requested)
+      d.force_f32 = (L.dst2 != BUF_NONE) || (L.nearest > 1 && !env_flag("MB_GAN_NEAREST_TC", false));
       d.taps = &L.taps;
       d.k = L.k;
       d.tc = &L.tc;

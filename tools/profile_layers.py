@@ -1,5 +1,5 @@
 """Per-layer CUDA-event timing of the GAN generator plan (mb_gan_forward_profiled).
-usage: python tools/profile_layers.py [--precision f16tc] [--batch 32] [--frames 256] [--reps 5] [--out file.tsv]"""
+usage: python tools/profile_layers.py [--model hifigan|fregan] [--precision f16tc] [--batch 32] [--frames 256] [--reps 5] [--out file.tsv]"""
 import argparse
 import sys
 from pathlib import Path
@@ -16,15 +16,23 @@ from mockingbird_b200.vocoder.hifigan.models import Generator  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="hifigan", choices=["hifigan", "fregan"])
     ap.add_argument("--precision", default="f16tc")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    cfg = ri.HIFIGAN_CONFIG_16K
-    g = Generator(cfg, precision=a.precision).cuda()
-    g.load_state_dict(ri.hifigan_state_dict(cfg, 0))
+    if a.model == "fregan":
+        from mockingbird_b200.vocoder.fregan.models import FreGAN
+
+        cfg = ri.FREGAN_CONFIG
+        g = FreGAN(cfg, precision=a.precision).cuda()
+        g.load_state_dict(ri.fregan_state_dict(cfg, 0))
+    else:
+        cfg = ri.HIFIGAN_CONFIG_16K
+        g = Generator(cfg, precision=a.precision).cuda()
+        g.load_state_dict(ri.hifigan_state_dict(cfg, 0))
     g.eval()
     g.remove_weight_norm()
     mel = (torch.rand(a.batch, 80, a.frames, generator=torch.Generator().manual_seed(2)) * 8 - 4).cuda()
