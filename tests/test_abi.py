@@ -134,3 +134,35 @@ def test_tacotron_handle_and_missing_weight_errors():
     assert _lib.lib().mb_tacotron_arena_bytes(t._handle) > 32_000_000 * 4
     assert _lib.lib().mb_tacotron_workspace_bytes(t._handle, 2, 10, 20, 2) > 0
     assert _lib.lib().mb_tacotron_finalize(t._handle, None) == 2  # weights never set
+
+
+def test_gan_plan_structure_on_cpu():
+    """mb_gan_create is host-only: the lowering of the two generators can be checked without a GPU.
+    HiFi-GAN: conv_pre + 4 x (ups + 3 resblocks x 3 x 2 convs) + conv_post = 78 ops.
+    Fre-GAN (tensor-core path): the 16-channel full-rate stage is carried with 32 channels, `x += cond_up(mel)` is a
+    separate add op for cond_up.1-3 (cond_up.0 reads the caller's fp32 mel and keeps the fused form); the FP32 path
+    keeps the checkpoint's channel counts and the fused form everywhere."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
+    import ref_init as ri
+    from mockingbird_b200.vocoder.fregan.models import FreGAN
+    from mockingbird_b200.vocoder.hifigan.models import Generator
+
+    h = Generator(ri.HIFIGAN_CONFIG_16K, precision="f16tc")
+    assert h.num_layers() == 78 and h.hop == 200
+    tc = FreGAN(ri.FREGAN_CONFIG, precision="f16tc")
+    info = [tc.layer_info(i) for i in range(tc.num_layers())]
+    assert tc.hop == 200
+    assert sum(s.startswith("add x+=cond_up.") for s in info) == 3 and not any("x+=cond_up.0" in s for s in info)
+    assert any(s.startswith("conv resblocks.12.convs1.0 cin=32 cout=32") for s in info)
+    assert any(s.startswith("conv conv_post cin=32 cout=1") for s in info)
+    # the add follows its cond_up immediately and precedes the res_output / ups of the same stage
+    i = next(k for k, s in enumerate(info) if s.startswith("conv cond_up.2"))
+    assert info[i + 1].startswith("add x+=cond_up.2") and info[i + 2].startswith("conv res_output.1.1")
+    f32 = FreGAN(ri.FREGAN_CONFIG, precision="fp32")
+    info32 = [f32.layer_info(i) for i in range(f32.num_layers())]
+    assert not any(s.startswith("add x+=") for s in info32)
+    assert any(s.startswith("conv resblocks.12.convs1.0 cin=16 cout=16") for s in info32)
+    assert len(info32) == len(info) - 3
