@@ -90,3 +90,32 @@ def test_ref_init_wavernn_bit_identical_to_reference_constructor():
     ref = m.state_dict()
     assert set(sd) == set(ref)
     assert all(torch.equal(sd[k], ref[k]) for k in sd)
+
+
+def test_three_term_fp16_split_is_fp32_equivalent():
+    """Arithmetic contract of the tensor-core recurrent GEMMs (csrc/tacotron_tc.cu): every product is computed as
+    hi(a)hi(w) + lo(a)hi(w) + hi(a)lo(w) with hi = fp16(v), lo = fp16(v - hi), weights pre-scaled by a power of two,
+    FP32 accumulation.  Emulated here in numpy on a K = 2048 dot product (the decoder LSTM shape): the split's error
+    against float64 is of the order of a plain FP32 dot product's and ~1000x below a plain fp16-operand product's."""
+    rng = np.random.default_rng(0)
+    K, N = 2048, 512
+    a = rng.standard_normal((8, K)).astype(np.float32)                      # activations O(1)
+    w = (rng.uniform(-1, 1, (N, K)) / 32).astype(np.float32)                 # LSTM init scale 1/sqrt(1024)
+    exact = a.astype(np.float64) @ w.astype(np.float64).T
+    scale = np.float32(2.0 ** (12 - np.frexp(np.abs(w).max())[1]))           # max |w| * scale in [2^11, 2^12)
+    ws = w * scale
+
+    def hi(v):
+        return v.astype(np.float16).astype(np.float32)
+
+    def lo(v):
+        return (v - hi(v)).astype(np.float16).astype(np.float32)
+
+    split = (hi(a) @ hi(ws).T + lo(a) @ hi(ws).T + hi(a) @ lo(ws).T) / scale  # float32 matmuls = fp32 accumulation
+    plain32 = a @ w.T
+    plain16 = hi(a) @ hi(w).T
+    ref = np.abs(exact).max()
+    e_split, e32, e16 = (np.abs(x - exact).max() / ref for x in (split, plain32, plain16))
+    assert e_split < 4 * max(e32, 1e-7), (e_split, e32)
+    assert e_split < e16 / 200, (e_split, e16)
+    assert e_split < 5e-6
