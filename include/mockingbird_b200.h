@@ -178,6 +178,34 @@ int mb_wavernn_generate(mb_wavernn* h, const int32_t* fold_starts_host, int32_t 
 int mb_wavernn_last_logits(mb_wavernn* h, float* logits, int32_t folds, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Reference-identical sampling noise (mt_stream.cu)
+ *   replaces  the per-step `Categorical(...).sample()` draw of fatchord_version.py:223-226, i.e. ATen's CPU
+ *             `exponential_` on the global torch generator: serial MT19937, two 32-bit draws per element,
+ *             q = (float)(-log1p(-((hi<<32|lo) & (2^53-1)) * 2^-53)).
+ *   A host worker thread continues the generator's MT19937 sequence from its exact state into a ring of pinned
+ *   buffers (allocated at create); per chunk the raw draws are copied on a side stream and converted on the device
+ *   into the fp32 noise tensor `mb_wavernn_generate` consumes; `finish` returns the advanced generator state.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mb_mtstream mb_mtstream;
+/* ring of `nslots` (2..8) pinned slots of `slot_words` 32-bit draws each; one side stream; current device */
+int mb_mtstream_create(uint64_t slot_words, int32_t nslots, mb_mtstream** out);
+void mb_mtstream_destroy(mb_mtstream* ms);
+/* start producing `total_words` draws in chunks of `words_per_chunk` from the at::mt19937 position
+ * (state[624], left_, next_) */
+int mb_mtstream_begin(mb_mtstream* ms, const uint32_t* state624, int32_t left, int32_t next, uint64_t total_words,
+                      uint64_t words_per_chunk);
+/* next chunk: H2D into dev_raw (2*n_elems words) + conversion into dev_noise (n_elems fp32) on the side stream;
+ * `main_stream` is made to wait for the result */
+int mb_mtstream_next(mb_mtstream* ms, uint64_t n_elems, void* dev_raw, float* dev_noise, void* main_stream);
+/* mark the chunk handed out last as consumed by the work enqueued on main_stream so far */
+int mb_mtstream_consumed(mb_mtstream* ms, void* main_stream);
+int mb_mtstream_finish(mb_mtstream* ms, uint32_t* state624_out, int32_t* left_out, int32_t* next_out);
+/* host-only: n raw draws continuing from (state, left, next), which are advanced in place */
+int mb_mt19937_fill(uint32_t* state624, int32_t* left, int32_t* next, uint32_t* out, uint64_t n);
+/* device conversion alone: raw draws [n_elems][2] (device) -> Exp(1) fp32 [n_elems] */
+int mb_mt_to_exp(const void* dev_raw, float* dev_noise, uint64_t n_elems, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Tacotron mel synthesizer
  *   replaces  models/synthesizer/models/tacotron.py:140-298 (Tacotron.forward / generate: Encoder + CBHG,
  *             global style token, attention decoder loop, postnet CBHG + post_proj),

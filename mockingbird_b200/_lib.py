@@ -112,6 +112,14 @@ SIGNATURES = {
                                       C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p]),
     "mb_wavernn_last_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mb_mtstream_create": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "mb_mtstream_destroy": (None, [C.c_void_p]),
+    "mb_mtstream_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64]),
+    "mb_mtstream_next": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_mtstream_consumed": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mb_mtstream_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mb_mt19937_fill": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_uint64]),
+    "mb_mt_to_exp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "mb_tacotron_create": (C.c_int, [C.POINTER(TacotronConfig), C.POINTER(C.c_void_p)]),
     "mb_tacotron_destroy": (None, [C.c_void_p]),
     "mb_tacotron_arena_bytes": (C.c_size_t, [C.c_void_p]),

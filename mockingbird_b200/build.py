@@ -18,18 +18,18 @@ STAMP = PKG_DIR / ".libmockingbird_b200.hash"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-shared", "-lpthread",
 ]
 
 
 def sources() -> list[Path]:
-    return sorted(CSRC.glob("*.cu"))
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cpp"))
 
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh"))
-                    + [PKG_DIR.parent / "include" / "mockingbird_b200.h"]):
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh"))
+                    + [PKG_DIR.parent / "include" / "mockingbird_b200.h", PKG_DIR.parent / "include" / "mb_wavernn_math.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -45,19 +45,60 @@ def find_nvcc() -> str | None:
     return cand if os.path.isfile(cand) else None
 
 
+def _obj_digest(src: Path, headers_digest: str) -> str:
+    h = hashlib.sha256()
+    h.update(src.read_bytes())
+    h.update(headers_digest.encode())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source into one shared library.  Raises on failure."""
+    """Compile every CUDA / C++ source into one shared library (objects are cached per source under
+    csrc/.obj and recompiled only when the source, any header or the flags changed).  Raises on failure."""
     if not force and is_fresh():
         return LIB_PATH
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libmockingbird_b200.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(s) for s in sources()]]
-    if verbose:
-        print(" ".join(cmd))
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = CSRC / ".obj"
+    objdir.mkdir(exist_ok=True)
+    hd = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "mockingbird_b200.h",
+                                                                           PKG_DIR.parent / "include" / "mb_wavernn_math.h"]):
+        if p.is_file():
+            hd.update(p.name.encode())
+            hd.update(p.read_bytes())
+    headers_digest = hd.hexdigest()
+    cflags = [f for f in NVCC_FLAGS if f not in ("-shared", "-lpthread")]
+
+    def compile_one(src: Path):
+        obj = objdir / (src.name + ".o")
+        stamp = objdir / (src.name + ".hash")
+        dig = _obj_digest(src, headers_digest)
+        if obj.is_file() and stamp.is_file() and stamp.read_text() == dig:
+            return obj, None
+        cmd = [nvcc, *cflags, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            print(" ".join(cmd))
+        proc = subprocess.run(cmd, cwd=str(CSRC), capture_output=True, text=True)
+        if proc.returncode != 0:
+            return obj, f"{src.name}:\n{proc.stdout}\n{proc.stderr}"
+        stamp.write_text(dig)
+        return obj, None
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, sources()))
+    errs = [e for _, e in results if e]
+    if errs:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(errs))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *[str(o) for o, _ in results],
+           "-lpthread"]
     proc = subprocess.run(cmd, cwd=str(CSRC), capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{proc.stdout}\n{proc.stderr}")
+        raise RuntimeError(f"link failed:\n{proc.stdout}\n{proc.stderr}")
     STAMP.write_text(_digest())
     return LIB_PATH
 

@@ -6,11 +6,14 @@ keeps only what the reference also does on the host in float64 numpy: cross-fade
 decoding, de-emphasis and the fade-out (fatchord_version.py:236-253).
 
 Sampling noise.  ``Categorical(p).sample()`` is ``argmax(p / q)`` with ``q = empty_like(p).exponential_(1)``
-drawn from the global torch generator.  ``rng="torch"`` (default) replays exactly
-that stream on the host - two ``nn.GRUCell`` constructions, then one ``exponential_([B,512])`` per
-step - and feeds it to the kernel, so under ``torch.manual_seed(s)`` the integer samples equal the
-reference's CPU run.  ``rng="device"`` uses the library's counter-based generator (no host noise,
-the throughput mode).
+drawn from the global torch generator.  ``rng="torch"`` (default) continues exactly
+that stream - two ``nn.GRUCell`` constructions, then 2 MT19937 draws per element in ATen's order - from the
+generator's own state: a host thread of the library runs the Mersenne Twister ~50x faster than ATen's serial
+``exponential_`` and the device applies ATen's ``-log1p(-u)`` (csrc/mt_stream.cu), so under
+``torch.manual_seed(s)`` the integer samples equal the reference's CPU run at full kernel speed, and the
+global generator is left in the state the reference would leave it in.  ``rng="torch_host"`` is the plain
+replay (one ``exponential_([B,512])`` per step on the host; A/B reference for the fast path);
+``rng="device"`` uses the library's counter-based generator (no host noise).
 """
 from __future__ import annotations
 
@@ -37,6 +40,24 @@ def fold_geometry(total_len: int, target: int, overlap: int):
     if remaining != 0:
         num_folds += 1
     return num_folds, np.arange(num_folds, dtype=np.int32) * (target + overlap)
+
+
+def torch_cpu_generator_position():
+    """(state[624] uint32, left, next) of the global torch CPU generator (at::mt19937 inside the legacy
+    CPUGeneratorImplState layout: seed u64 @0, left i32 @8, seeded i32 @12, next u64 @16, state u64[624] @24)"""
+    st = torch.get_rng_state().numpy()
+    left = int(st[8:12].view(np.int32)[0])
+    nxt = int(st[16:24].view(np.uint64)[0])
+    state = np.ascontiguousarray(st[24:24 + 624 * 8].view(np.uint64).astype(np.uint32))
+    return state, left, nxt
+
+
+def set_torch_cpu_generator_position(state: np.ndarray, left: int, nxt: int) -> None:
+    st = torch.get_rng_state().numpy().copy()
+    st[8:12] = np.array([left], np.int32).view(np.uint8)
+    st[16:24] = np.array([nxt], np.uint64).view(np.uint8)
+    st[24:24 + 624 * 8] = state.astype(np.uint64).view(np.uint8)
+    torch.set_rng_state(torch.from_numpy(st))
 
 
 def xfade_and_unfold(y: np.ndarray, target: int, overlap: int) -> np.ndarray:
@@ -96,6 +117,8 @@ class WaveRNN:
         self._state: Optional[Dict[str, torch.Tensor]] = None
         self._arena = None
         self._ws = None
+        self._mt = None          # mb_mtstream handle (pinned ring + side stream), created at first use
+        self._mt_words = 0
         self._device = None
         self._ready = False
         self.training = True
@@ -197,43 +220,70 @@ class WaveRNN:
                                               ws.numel(), C.c_void_p(stream.cuda_stream)))
             out = torch.empty(B, steps, dtype=torch.int16, device=dev)
             starts_c = (C.c_int32 * B)(*[int(s) for s in starts])
-            use_host_noise = noise is not None or self.rng == "torch"
+            if self.rng not in ("torch", "torch_host", "device"):
+                raise ValueError(f"rng must be 'torch', 'torch_host' or 'device', got {self.rng!r}")
+            use_host_noise = noise is not None or self.rng in ("torch", "torch_host")
+            use_mt = noise is None and self.rng == "torch"
             if use_host_noise and noise is None:
                 # the reference constructs two GRUCells before the loop: they consume the global RNG
                 # (fatchord_version.py:160-161, 265-271)
                 nn.GRUCell(self.rnn_dims, self.rnn_dims)
                 nn.GRUCell(self.rnn_dims + self.aux_dims, self.rnn_dims)
+            per_step = B * self.n_classes
             bufs = [torch.empty(CHUNK, B, self.n_classes, dtype=torch.float32).pin_memory() for _ in range(2)] \
-                if use_host_noise and noise is None else None
+                if use_host_noise and noise is None and not use_mt else None
             dbufs = [torch.empty(CHUNK, B, self.n_classes, dtype=torch.float32, device=dev) for _ in range(2)] \
                 if use_host_noise else None
+            raw = [torch.empty(CHUNK * per_step * 2, dtype=torch.int32, device=dev) for _ in range(2)] if use_mt else None
+            if use_mt:
+                words = CHUNK * per_step * 2
+                if self._mt is None or self._mt_words < words:
+                    if self._mt is not None:
+                        L.mb_mtstream_destroy(self._mt)
+                    self._mt = C.c_void_p()
+                    _lib.check(L.mb_mtstream_create(words, 3, C.byref(self._mt)))
+                    self._mt_words = words
+                g_state, g_left, g_next = torch_cpu_generator_position()
+                _lib.check(L.mb_mtstream_begin(self._mt, g_state.ctypes.data, g_left, g_next, steps * per_step * 2, words))
             evs = [torch.cuda.Event(), torch.cuda.Event()]
             step0 = 0
             ci = 0
-            while step0 < steps:
-                n = min(CHUNK, steps - step0)
-                nptr = None
-                if use_host_noise:
-                    slot = ci & 1
-                    if noise is not None:
-                        dbufs[slot][:n].copy_(noise[step0:step0 + n].to(torch.float32), non_blocking=True)
-                    else:
-                        if ci >= 2:
-                            evs[slot].synchronize()  # the H2D that last used this pinned buffer is done
-                        hb = bufs[slot]
-                        for j in range(n):
-                            hb[j].exponential_(1)  # same draw order as Categorical.sample(), one per step
-                        dbufs[slot][:n].copy_(hb[:n], non_blocking=True)
-                        evs[slot].record(stream)
-                    nptr = C.c_void_p(dbufs[slot].data_ptr())
-                _lib.check(L.mb_wavernn_generate(self._handle, starts_c, B, steps, step0, n, nptr, C.c_uint64(self.seed),
-                                                 C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
-                                                 C.c_void_p(stream.cuda_stream)))
-                if progress_callback is not None:
-                    gen_rate = (step0 + 1) / max(time.time() - start_t, 1e-9) * B / 1000
-                    progress_callback(step0, steps, B, gen_rate)
-                step0 += n
-                ci += 1
+            try:
+                while step0 < steps:
+                    n = min(CHUNK, steps - step0)
+                    nptr = None
+                    if use_host_noise:
+                        slot = ci & 1
+                        if noise is not None:
+                            dbufs[slot][:n].copy_(noise[step0:step0 + n].to(torch.float32), non_blocking=True)
+                        elif use_mt:
+                            _lib.check(L.mb_mtstream_next(self._mt, n * per_step, C.c_void_p(raw[slot].data_ptr()),
+                                                          C.c_void_p(dbufs[slot].data_ptr()), C.c_void_p(stream.cuda_stream)))
+                        else:
+                            if ci >= 2:
+                                evs[slot].synchronize()  # the H2D that last used this pinned buffer is done
+                            hb = bufs[slot]
+                            for j in range(n):
+                                hb[j].exponential_(1)  # same draw order as Categorical.sample(), one per step
+                            dbufs[slot][:n].copy_(hb[:n], non_blocking=True)
+                            evs[slot].record(stream)
+                        nptr = C.c_void_p(dbufs[slot].data_ptr())
+                    _lib.check(L.mb_wavernn_generate(self._handle, starts_c, B, steps, step0, n, nptr, C.c_uint64(self.seed),
+                                                     C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                     C.c_void_p(stream.cuda_stream)))
+                    if use_mt:
+                        _lib.check(L.mb_mtstream_consumed(self._mt, C.c_void_p(stream.cuda_stream)))
+                    if progress_callback is not None:
+                        gen_rate = (step0 + 1) / max(time.time() - start_t, 1e-9) * B / 1000
+                        progress_callback(step0, steps, B, gen_rate)
+                    step0 += n
+                    ci += 1
+            finally:
+                if use_mt:
+                    # the generator is left exactly where the reference's own generate() would leave it
+                    left_c, next_c = C.c_int32(), C.c_int32()
+                    _lib.check(L.mb_mtstream_finish(self._mt, g_state.ctypes.data, C.byref(left_c), C.byref(next_c)))
+                    set_torch_cpu_generator_position(g_state, left_c.value, next_c.value)
             idx = out.cpu().numpy()
         return idx
 
@@ -268,6 +318,9 @@ class WaveRNN:
 
     def __del__(self):
         try:
+            if getattr(self, "_mt", None) is not None and self._mt.value:
+                _lib.lib().mb_mtstream_destroy(self._mt)
+                self._mt = None
             if getattr(self, "_handle", None) is not None and self._handle.value:
                 _lib.lib().mb_wavernn_destroy(self._handle)
                 self._handle = C.c_void_p()
