@@ -144,6 +144,7 @@ def cpu_hifigan(batch_rows: int, passes: int, threads: int, fregan: bool = False
     """The CPU implementation (oracle port of the reference forward), batch-1 calls like
     hifigan/inference.py:66-70.  Returns (samples_per_s, seconds, samples)."""
     sys.path.insert(0, str(ROOT / "oracle"))
+    sys.path.insert(0, str(ROOT / "synth_weights"))
     import torch
     import gan_oracle as go
     import ref_init as ri
@@ -214,6 +215,8 @@ def run_ours_hifigan(args):
     import torch.distributed as dist
 
     sys.path.insert(0, str(ROOT / "oracle"))  # ref_init only: seeded random-init weights (no checkpoints exist)
+
+    sys.path.insert(0, str(ROOT / "synth_weights"))
     import ref_init as ri
     from mockingbird_b200 import _lib
     from mockingbird_b200.vocoder.fregan.models import FreGAN

@@ -36,6 +36,7 @@ def make_utterances(n_total: int):
 def cpu_oracle(n_utt: int, threads: int, frames: int = 200):
     """CPU oracles chained the same way on `n_utt` utterances with `frames` decoder frames each"""
     sys.path.insert(0, str(ROOT / "oracle"))
+    sys.path.insert(0, str(ROOT / "synth_weights"))
     import torch
     import encoder_oracle as eo
     import gan_oracle as go
@@ -96,6 +97,8 @@ def run_ours(args):
     import torch.distributed as dist
 
     sys.path.insert(0, str(ROOT / "oracle"))  # ref_init only: seeded random-init weights (no checkpoints exist)
+
+    sys.path.insert(0, str(ROOT / "synth_weights"))
     import ref_init as ri
     from bench import ClockSampler, cpu_child, host_threads, log
     from mockingbird_b200 import _lib

@@ -35,6 +35,7 @@ def make_inputs(rank=0):
 def cpu_oracle(steps: int, threads: int):
     """torch-CPU oracle (matches the reference to 1 ulp) on the cfg-4 batch with `steps` decoder frames"""
     sys.path.insert(0, str(ROOT / "oracle"))
+    sys.path.insert(0, str(ROOT / "synth_weights"))
     import torch
     import ref_init as ri
     import tacotron_oracle as to
@@ -79,6 +80,8 @@ def run_ours(args):
     import torch.distributed as dist
 
     sys.path.insert(0, str(ROOT / "oracle"))
+
+    sys.path.insert(0, str(ROOT / "synth_weights"))
     import ref_init as ri
     from bench import ClockSampler, cpu_child, host_threads, peaks
     from mockingbird_b200 import _lib

@@ -34,6 +34,7 @@ def _geometry():
 def cpu_twin(nsteps: int, threads: int):
     """CPU port (the C twin, OpenMP over the fold rows) on `nsteps` steps of the cfg-3 batch."""
     sys.path.insert(0, str(ROOT / "oracle"))
+    sys.path.insert(0, str(ROOT / "synth_weights"))
     import numpy as np
     import torch
     import ref_init as ri
@@ -80,6 +81,8 @@ def run_ours(args):
     import torch.distributed as dist
 
     sys.path.insert(0, str(ROOT / "oracle"))
+
+    sys.path.insert(0, str(ROOT / "synth_weights"))
     import ref_init as ri
     from bench import ClockSampler
     from mockingbird_b200 import _lib

@@ -174,6 +174,14 @@ int mb_wavernn_generate(mb_wavernn* h, const int32_t* fold_starts_host, int32_t 
                         int32_t step0, int32_t nsteps, const float* noise, uint64_t seed,
                         int16_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same, for a contiguous subset of an utterance's folds (fold sharding across GPUs): this call's
+ * local rows are the global folds [row0, row0+folds); `noise` holds all `noise_folds` rows per step
+ * ([steps_in_call, noise_folds, 512]) and the built-in generator is keyed by the global fold index, so the samples of
+ * a fold do not depend on how the folds are dealt to GPUs.  out_idx is local: int16 [folds, steps]. */
+int mb_wavernn_generate_rows(mb_wavernn* h, const int32_t* fold_starts_host, int32_t folds, int32_t steps,
+                             int32_t step0, int32_t nsteps, const float* noise, int32_t noise_folds, int32_t row0,
+                             uint64_t seed, int16_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
 /* debug/test hook: logits [folds, 512] fp32 of the LAST step executed by mb_wavernn_generate */
 int mb_wavernn_last_logits(mb_wavernn* h, float* logits, int32_t folds, void* workspace, void* stream);
 

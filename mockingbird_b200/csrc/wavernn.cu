@@ -177,7 +177,8 @@ struct LoopParams {
   float* f2;                // [512][Bpad]
   float* logits;            // [512][Bpad]
   float* xprev;             // [Bpad]
-  const float* noise;       // [nsteps][B][512] or nullptr
+  const float* noise;       // [nsteps][noise_B][512] or nullptr (this call's rows are noise rows row0 .. row0+B)
+  int noise_B, row0;        // row0: global fold index of local row 0 (fold sharding across GPUs)
   uint64_t seed;
   int16_t* out_idx;         // [B][steps_total]
   unsigned int* barrier;    // grid barrier counter (zeroed by the host before launch)
@@ -546,8 +547,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sample_loop(const LoopParams p)
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
           const int cls = lane + 32 * jj;
-          const float q = p.noise ? p.noise[((size_t)i * p.B + row) * NCLS + cls]
-                                  : mb_exp1_noise(p.seed, (uint32_t)gstep, (uint32_t)row, (uint32_t)cls);
+          const float q = p.noise ? p.noise[((size_t)i * p.noise_B + (size_t)(p.row0 + row)) * NCLS + cls]
+                                  : mb_exp1_noise(p.seed, (uint32_t)gstep, (uint32_t)(p.row0 + row), (uint32_t)cls);
           const float v = (e[jj] / S2) / q;
           if (v > bestv) {  // ascending class order within the lane: first maximum wins
             bestv = v;
@@ -851,7 +852,16 @@ int mb_wavernn_condition(mb_wavernn* h, const float* mel, int32_t T, void* works
 int mb_wavernn_generate(mb_wavernn* h, const int32_t* fold_starts_host, int32_t B, int32_t steps, int32_t step0,
                         int32_t nsteps, const float* noise, uint64_t seed, int16_t* out_idx, void* workspace,
                         size_t workspace_bytes, void* stream) {
+  return mb_wavernn_generate_rows(h, fold_starts_host, B, steps, step0, nsteps, noise, B, 0, seed, out_idx, workspace,
+                                  workspace_bytes, stream);
+}
+
+int mb_wavernn_generate_rows(mb_wavernn* h, const int32_t* fold_starts_host, int32_t B, int32_t steps, int32_t step0,
+                             int32_t nsteps, const float* noise, int32_t noise_folds, int32_t row0, uint64_t seed,
+                             int16_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || !fold_starts_host || !out_idx || !workspace) return fail(MB_ERR_INVALID, "mb_wavernn_generate: null argument");
+  if (row0 < 0 || (noise && row0 + B > noise_folds))
+    return fail(MB_ERR_INVALID, "mb_wavernn_generate_rows: rows [%d, %d) outside the %d noise rows", row0, row0 + B, noise_folds);
   if (!h->finalized) return fail(MB_ERR_STATE, "mb_wavernn_generate: weights not finalized");
   if (h->cond_T <= 0 || h->cond_ws != workspace)
     return fail(MB_ERR_STATE, "mb_wavernn_generate: call mb_wavernn_condition on this workspace first");
@@ -898,6 +908,8 @@ int mb_wavernn_generate(mb_wavernn* h, const int32_t* fold_starts_host, int32_t 
   p.logits = ws + L.logits;
   p.xprev = ws + L.xprev;
   p.noise = noise;
+  p.noise_B = noise_folds;
+  p.row0 = row0;
   p.seed = seed;
   p.out_idx = out_idx;
   p.barrier = reinterpret_cast<unsigned int*>(ws + L.barrier);

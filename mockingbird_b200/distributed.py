@@ -1,8 +1,8 @@
 """Multi-GPU plumbing of the vocoder / synthesizer path.
 
-The path shards by independent units (utterances; WaveRNN folds stay inside one kernel), so the only
-collective is the start-up broadcast of the packed weight arenas over NCCL/NVLink; results stay on
-their rank or are gathered by the host.  One process per GPU (torchrun), ``torch.distributed`` is
+The path shards by independent units (utterances; the folds of ONE long WaveRNN utterance, which are independent
+rows of the sample loop), so the only collectives are the start-up broadcast of the packed weight arenas over
+NCCL/NVLink and the gather of the per-rank results (int16 fold rows, ~1 MB for a 30 s utterance).  One process per GPU (torchrun), ``torch.distributed`` is
 plumbing only.  The same functions run on the ``gloo`` backend for the CPU tests.
 """
 from __future__ import annotations
@@ -52,3 +52,37 @@ def merge_sharded(results_per_rank: Sequence[Sequence], shards_per_rank: Sequenc
         for v, i in zip(res, idx):
             out[i] = v
     return out
+
+
+def fold_range(num_folds: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous folds [lo, hi) of one utterance owned by `rank` (58 folds on 8 ranks -> 8,8,7,7,7,7,7,7)."""
+    base, rem = divmod(int(num_folds), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_fold_rows(local_idx, num_folds: int, dst: int = 0, device=None):
+    """Gather the per-rank int16 [rows_r, steps] class indices of one utterance into [num_folds, steps] on `dst`
+    (None elsewhere).  NCCL: device tensors; gloo: host tensors."""
+    import numpy as np
+
+    rank, ws = world()
+    if ws == 1:
+        return local_idx
+    steps = int(local_idx.shape[1])
+    rows_max = (num_folds + ws - 1) // ws
+    use_cuda = dist.get_backend() == "nccl"
+    dev = (device or torch.device("cuda", torch.cuda.current_device())) if use_cuda else torch.device("cpu")
+    buf = torch.zeros(rows_max, steps, dtype=torch.int16, device=dev)
+    buf[: local_idx.shape[0]] = torch.from_numpy(np.ascontiguousarray(local_idx)).to(dev)
+    wire = buf.view(torch.uint8)  # neither NCCL nor gloo transports int16: ship the bytes
+    outs8 = [torch.empty_like(wire) for _ in range(ws)] if rank == dst else None
+    dist.gather(wire, outs8, dst=dst)
+    outs = [o.view(torch.int16) for o in outs8] if rank == dst else None
+    if rank != dst:
+        return None
+    full = np.empty((num_folds, steps), np.int16)
+    for r in range(ws):
+        lo, hi = fold_range(num_folds, r, ws)
+        full[lo:hi] = outs[r][: hi - lo].cpu().numpy()
+    return full

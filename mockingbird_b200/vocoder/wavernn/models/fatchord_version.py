@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import time
-from typing import Dict, Optional
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -193,8 +193,10 @@ class WaveRNN:
 
     # -- generate --------------------------------------------------------------------------------
     def generate_indices(self, mels: torch.Tensor, batched: bool, target: int, overlap: int, progress_callback=None,
-                         noise: Optional[torch.Tensor] = None) -> np.ndarray:
-        """the device part of generate(): class indices int16 [folds, steps]"""
+                         noise: Optional[torch.Tensor] = None, rows: Optional[Tuple[int, int]] = None) -> np.ndarray:
+        """the device part of generate(): class indices int16 [folds, steps].  ``rows=(lo, hi)`` runs only the folds
+        [lo, hi) of the utterance (fold sharding across GPUs): the noise stream is still the whole utterance's, each
+        fold reads its own rows, so a fold's samples do not depend on the sharding."""
         if not self._ready:
             self._upload()
         L = _lib.lib()
@@ -209,6 +211,16 @@ class WaveRNN:
             B, starts, steps = 1, np.zeros(1, dtype=np.int32), total
         if B <= 0 or steps <= 0:
             return np.zeros((max(B, 0), max(steps, 0)), np.int16)
+        B_all, row0 = B, 0  # the noise stream always covers all folds of the utterance
+        if rows is not None:
+            row0, hi = int(rows[0]), int(rows[1])
+            if not (0 <= row0 <= hi <= B_all):
+                raise ValueError(f"rows {rows} outside the {B_all} folds")
+            starts, B = starts[row0:hi], hi - row0
+            if B == 0:
+                if noise is None and self.rng in ("torch", "torch_host"):
+                    self._skip_noise(B_all, steps)
+                return np.zeros((0, steps), np.int16)
         start_t = time.time()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
@@ -229,10 +241,10 @@ class WaveRNN:
                 # (fatchord_version.py:160-161, 265-271)
                 nn.GRUCell(self.rnn_dims, self.rnn_dims)
                 nn.GRUCell(self.rnn_dims + self.aux_dims, self.rnn_dims)
-            per_step = B * self.n_classes
-            bufs = [torch.empty(CHUNK, B, self.n_classes, dtype=torch.float32).pin_memory() for _ in range(2)] \
+            per_step = B_all * self.n_classes
+            bufs = [torch.empty(CHUNK, B_all, self.n_classes, dtype=torch.float32).pin_memory() for _ in range(2)] \
                 if use_host_noise and noise is None and not use_mt else None
-            dbufs = [torch.empty(CHUNK, B, self.n_classes, dtype=torch.float32, device=dev) for _ in range(2)] \
+            dbufs = [torch.empty(CHUNK, B_all, self.n_classes, dtype=torch.float32, device=dev) for _ in range(2)] \
                 if use_host_noise else None
             raw = [torch.empty(CHUNK * per_step * 2, dtype=torch.int32, device=dev) for _ in range(2)] if use_mt else None
             if use_mt:
@@ -268,9 +280,10 @@ class WaveRNN:
                             dbufs[slot][:n].copy_(hb[:n], non_blocking=True)
                             evs[slot].record(stream)
                         nptr = C.c_void_p(dbufs[slot].data_ptr())
-                    _lib.check(L.mb_wavernn_generate(self._handle, starts_c, B, steps, step0, n, nptr, C.c_uint64(self.seed),
-                                                     C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
-                                                     C.c_void_p(stream.cuda_stream)))
+                    _lib.check(L.mb_wavernn_generate_rows(self._handle, starts_c, B, steps, step0, n, nptr, B_all, row0,
+                                                          C.c_uint64(self.seed), C.c_void_p(out.data_ptr()),
+                                                          C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                          C.c_void_p(stream.cuda_stream)))
                     if use_mt:
                         _lib.check(L.mb_mtstream_consumed(self._mt, C.c_void_p(stream.cuda_stream)))
                     if progress_callback is not None:
@@ -287,18 +300,25 @@ class WaveRNN:
             idx = out.cpu().numpy()
         return idx
 
-    def generate(self, mels, batched, target, overlap, mu_law, progress_callback=None):
-        mu_law = mu_law if self.mode == 'RAW' else False
-        progress_callback = progress_callback or self.gen_display
-        self.eval()
-        wave_len = (mels.size(-1) - 1) * self.hop_length
-        idx = self.generate_indices(mels, batched, target, overlap, progress_callback)
-        # sample = 2 * idx.float() / (n_classes - 1.) - 1.  (float32, :226) then float64 (:238)
+    def _skip_noise(self, B_all: int, steps: int) -> None:
+        """advance the global generator as a full generate() would (a rank that owns no fold of the utterance)"""
+        nn.GRUCell(self.rnn_dims, self.rnn_dims)
+        nn.GRUCell(self.rnn_dims + self.aux_dims, self.rnn_dims)
+        state, left, nxt = torch_cpu_generator_position()
+        n = steps * B_all * self.n_classes * 2
+        scratch = np.empty(1 << 20, np.uint32)
+        l, x = C.c_int32(left), C.c_int32(nxt)
+        while n > 0:
+            m = min(n, scratch.size)
+            _lib.check(_lib.lib().mb_mt19937_fill(state.ctypes.data, C.byref(l), C.byref(x), scratch.ctypes.data, m))
+            n -= m
+        set_torch_cpu_generator_position(state, l.value, x.value)
+
+    def postprocess(self, idx: np.ndarray, frames: int, batched: bool, target: int, overlap: int, mu_law: bool) -> np.ndarray:
+        """class indices [folds, steps] -> waveform, the host float64 tail of generate() (:236-253)"""
+        wave_len = (frames - 1) * self.hop_length
         output = (2 * idx.astype(np.float32) / np.float32(self.n_classes - 1.) - np.float32(1.)).astype(np.float64)
-        if batched:
-            output = xfade_and_unfold(output, target, overlap)
-        else:
-            output = output[0]
+        output = xfade_and_unfold(output, target, overlap) if batched else output[0]
         if mu_law:
             output = decode_mu_law(output, self.n_classes)
         if hp.apply_preemphasis:
@@ -306,6 +326,35 @@ class WaveRNN:
         fade_out = np.linspace(1, 0, 20 * self.hop_length)
         output = output[:wave_len]
         output[-20 * self.hop_length:] *= fade_out
+        return output
+
+    def generate_sharded(self, mels, target, overlap, mu_law, progress_callback=None, dst: int = 0):
+        """batched generate() of ONE utterance with its folds dealt contiguously across the ranks of the default process
+        group (folds are independent rows, fatchord_version.py:178-185): every rank computes the
+        (cheap) conditioning, runs its folds, the int16 indices are gathered on `dst` which cross-fades / unfolds /
+        decodes.  Returns the waveform on `dst`, None elsewhere.  Same samples as the single-GPU call."""
+        from .... import distributed as mbd
+
+        mu_law = mu_law if self.mode == 'RAW' else False
+        rank, ws = mbd.world()
+        total = int(mels.size(-1)) * self._total_scale
+        B, _ = fold_geometry(total, target, overlap)
+        lo, hi = mbd.fold_range(B, rank, ws)
+        self.eval()
+        idx = self.generate_indices(mels, True, target, overlap, progress_callback, rows=(lo, hi))
+        full = mbd.gather_fold_rows(idx, B, dst=dst, device=self._device)
+        self.train()
+        if rank != dst:
+            return None
+        return self.postprocess(full, int(mels.size(-1)), True, target, overlap, mu_law)
+
+    def generate(self, mels, batched, target, overlap, mu_law, progress_callback=None):
+        mu_law = mu_law if self.mode == 'RAW' else False
+        progress_callback = progress_callback or self.gen_display
+        self.eval()
+        idx = self.generate_indices(mels, batched, target, overlap, progress_callback)
+        # sample = 2 * idx.float() / (n_classes - 1.) - 1.  (float32, :226) then float64 (:238)
+        output = self.postprocess(idx, int(mels.size(-1)), batched, target, overlap, mu_law)
         self.train()  # side effect kept (:255)
         return output
 

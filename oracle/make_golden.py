@@ -18,6 +18,7 @@ from pathlib import Path
 os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE))
+sys.path.insert(0, str(HERE.parent / "synth_weights"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

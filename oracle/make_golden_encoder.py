@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "synth_weights"))
 import ref_harness as rh  # noqa: E402
 import ref_init as ri  # noqa: E402
 

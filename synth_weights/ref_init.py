@@ -1,5 +1,9 @@
-"""Seeded re-creation of the reference's random-init weights WITHOUT the reference tree
-(TEST INFRASTRUCTURE - used by tests/, bench.py's baseline legs and smoke() only).
+"""Seeded re-creation of the reference's random-init weights WITHOUT the reference tree.
+
+Synthetic-weight helper, NOT part of the oracle and not part of the product: the reference ships no checkpoints, so
+tests/, bench.py and smoke() need seeded random-init weights of the reference architectures (there is no network to
+fetch real ones).  Lives outside oracle/ so that bench.py / smoke() visibly import nothing from oracle/ when they build
+their inputs; contains no forward arithmetic.
 
 The reference ships no checkpoints, so every parity case uses the weights
 ``torch.manual_seed(seed); Model(...)`` would produce.  /root/reference does not exist on the GPU

@@ -121,3 +121,52 @@ def test_vocoder_on_disk_formats(tmp_path):
 
     wavs = formats.vocode_files([tmp_path / "mel-a.npy"], FakeVocoder())
     assert len(wavs) == 1 and wavs[0].shape == (1400,)
+
+
+def _fold_worker(rank, world, port, num_folds, steps, q):
+    import numpy as np
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = mbd.fold_range(num_folds, rank, world)
+        # stand-in for the device result: row g holds g*1000 + step
+        local = (np.arange(lo, hi, dtype=np.int16)[:, None] * 100 + np.arange(steps, dtype=np.int16)[None, :]).astype(np.int16)
+        full = mbd.gather_fold_rows(local, num_folds, dst=0)
+        q.put((rank, lo, hi, None if full is None else full.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fold_range_partition():
+    """58 folds over 8 ranks -> 8,8,7,... contiguous, disjoint, complete; more ranks than folds ok"""
+    for n, w in ((58, 8), (58, 1), (58, 4), (3, 8), (0, 2), (64, 2)):
+        r = [mbd.fold_range(n, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n
+        assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+        sizes = [hi - lo for lo, hi in r]
+        assert max(sizes) - min(sizes) <= 1
+    assert [hi - lo for lo, hi in (mbd.fold_range(58, k, 8) for k in range(8))] == [8, 8, 7, 7, 7, 7, 7, 7]
+
+
+def test_two_rank_fold_gather():
+    """the WaveRNN fold-sharding host logic on gloo, world_size 2: 7 folds -> 4 + 3 rows, gathered in fold order"""
+    import numpy as np
+
+    num_folds, steps = 7, 11
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fold_worker, args=(r, 2, port, num_folds, steps, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (outs[0][1], outs[0][2], outs[1][1], outs[1][2]) == (0, 4, 4, 7)
+    assert outs[1][3] is None
+    full = np.array(outs[0][3], dtype=np.int16)
+    want = (np.arange(num_folds, dtype=np.int16)[:, None] * 100 + np.arange(steps, dtype=np.int16)[None, :]).astype(np.int16)
+    assert np.array_equal(full, want)

@@ -191,3 +191,18 @@ def test_gpu_fregan_cfg2_rows(golden_dir, precision):
     e = go.rel_errors(wav[pick].cpu(), torch.from_numpy(z["wav_full"]))
     tol = 2e-5 if precision == "fp32" else 1e-3
     assert e["max_rel"] <= tol and e["rms_rel"] <= tol, e
+
+
+def test_torch_oracle_prefix_matches_reference(wsd, golden_dir):
+    """the torch-CPU restatement used as bench.py's WaveRNN CPU leg == the reference on a prefix of cfg 1 (400 draws)
+    and of cfg 3 (58 folds x 40 steps) under the same seed"""
+    import wavernn_torch_oracle as wt
+
+    z1 = np.load(golden_dir / "wavernn_cfg1.npz")
+    torch.manual_seed(1234)
+    idx, _ = wt.generate_indices(wsd, MEL1(), False, 8000, 400, max_steps=400)
+    assert np.array_equal(idx, z1["idx"][:, :400])
+    z3 = np.load(golden_dir / "wavernn_cfg3.npz")
+    torch.manual_seed(1234)
+    idx, _ = wt.generate_indices(wsd, MEL3(), True, 8000, 400, max_steps=40)
+    assert np.array_equal(idx, z3["idx"][:, :40])

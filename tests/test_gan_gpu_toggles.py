@@ -14,7 +14,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 SCRIPT = r"""
 import json, sys
-sys.path.insert(0, "oracle")
+sys.path.insert(0, "oracle"); sys.path.insert(0, "synth_weights")
 import numpy as np, torch
 import gan_oracle as go, ref_init as ri
 from mockingbird_b200.vocoder.hifigan.models import Generator

@@ -108,3 +108,24 @@ def test_inference_module_protocol(tmp_path, sd, gold):
                                          progress_callback=lambda *a: None)
     assert sr == 16000
     assert np.abs(wav - gold["wav2"]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("rng", ["torch", "device"])
+def test_fold_rows_independent_of_sharding(model, rng):
+    """the folds of one utterance are independent rows; running them as [0,3) + [3,7) (what two
+    GPUs would do) gives exactly the rows of the single call, and leaves the torch generator in the same state"""
+    mel = torch.rand(1, 80, 13, generator=torch.Generator().manual_seed(21)) * 2 - 1
+    model.rng, model.seed = rng, 31
+    try:
+        torch.manual_seed(55)
+        full = model.generate_indices(mel, True, 300, 35, None)
+        tail = torch.rand(3)
+        parts = []
+        for lo, hi in ((0, 3), (3, 7), (7, 7)):
+            torch.manual_seed(55)
+            parts.append(model.generate_indices(mel, True, 300, 35, None, rows=(lo, hi)))
+            assert torch.equal(torch.rand(3), tail) or rng == "device"
+    finally:
+        model.rng = "torch"
+    assert full.shape == (7, 370) and parts[2].shape == (0, 370)
+    assert np.array_equal(np.concatenate(parts), full)

@@ -5,6 +5,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "oracle"))
+sys.path.insert(0, str(ROOT / "synth_weights"))
 import torch  # noqa: E402
 
 import ref_init as ri  # noqa: E402

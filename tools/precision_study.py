@@ -1,7 +1,7 @@
 """CPU emulation of the f16tc rounding points of the HiFi-GAN path with per-stage knobs, to find the
 cheapest configuration that holds 1e-3 on the harder "variance preserving" init (TEST/DESIGN TOOL, uses oracle/)."""
 import itertools, sys, math
-sys.path.insert(0, "oracle")
+sys.path.insert(0, "oracle"); sys.path.insert(0, "synth_weights")
 import torch, torch.nn.functional as F
 import gan_oracle as go, ref_init as ri
 
