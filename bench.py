@@ -1,37 +1,41 @@
-#!/usr/bin/env python
-"""bench.py - headline benchmark of the B200 vocoder hot path (contract: see DESIGN.md section 6).
+"""bench.py - headline benchmark of the B200 vocoder / synthesizer hot path (contract: see DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload hifigan_cfg2|fregan_cfg2|wavernn_cfg3|tacotron_cfg4|e2e_cfg5] [--precision f16tc|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-secondary] [--no-cpu-baseline]
+                    [--workload hifigan_cfg2|fregan_cfg2|wavernn_cfg1|wavernn_cfg3|tacotron_cfg4|e2e_cfg5] [--precision ...]
 
-Default workload = BASELINE.json configs[1]: HiFi-GAN Generator forward, batch 32 random mels of
-256 frames x 80 bins, per GPU.  A "step" is one forward over one batch.  Prints ONE JSON line
-(rank 0).  Under torchrun every rank runs its own batch of the same size (weak scaling: utterance
-batches shard across GPUs with no data-path collective; NCCL only broadcasts the packed weights).
+Prints ONE JSON line (rank 0).  The headline is BASELINE.json configs[1] (the config the metric is quoted on): HiFi-GAN
+Generator forward, batch 32 random mels of 256 frames x 80 bins per GPU; a "step" is one forward over one batch; under
+torchrun every rank runs its own batch (weak scaling: utterance batches shard across GPUs, no data-path collective).
 
-  value      samples/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        same metric through the drop-in surface with HOST (pinned) buffers: H2D of the mel
-             batch and D2H of the waveforms inside the timed region
-  roofline   dominant kernel (the tcgen05 conv kernel): algorithmic FLOPs / CUDA-event time of
-             those launches (separate profiled pass) vs MEASURED_PEAKS.json bf16 peak; plus the
-             north-star's layer-granular HBM view for the whole step ("roofline_hbm_step")
-  cpu_baseline  the oracle (torch-CPU restatement, bit-identical to the reference forward) on the
-             host cores, bounded sample
---impl reference: times that CPU implementation on the same config (rank 0 only).
+  value      samples/s, inputs resident in HBM, CUDA events, max over ranks, measured AFTER a >= 2 s soak of the same
+             step ("burst" = the same K steps timed right after warm-up, reported beside it)
+  e2e        same metric through the drop-in module surface hifigan.inference.infer_waveforms() with HOST numpy mels:
+             pinned H2D of the batch and D2H of the waveforms inside the timed region, host sync every step
+  roofline   the tcgen05 conv kernel family: layer-granular algorithmic bytes / CUDA-event time of those launches
+             (separate profiled pass) vs the measured HBM copy bandwidth; roofline_tensor: FLOPs vs the measured bf16 peak
+             (burst peak for the burst figure, sustained peak for the soaked one)
+  cpu_baseline  the oracle port of the reference forward on the host cores, bounded sample (rank 0, N = 1 only)
+  secondary  every other BASELINE.json config, each with its own value / e2e / roofline / cpu_baseline:
+             wavernn_cfg1 (configs[0]), wavernn_cfg3 (configs[2]; device noise AND the reference-identical torch stream),
+             tacotron_cfg4 (configs[3]), e2e_cfg5 (configs[4], weak: 128 utterances per GPU; strong: 1024 utterances
+             over N GPUs), hifigan_fp32_equivalent (3-term split everywhere), and at N > 1 the fold-sharded cfg 3
+--impl reference: the CPU implementation (oracle port, all host threads) on the same config (rank 0 only).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+
+from bench_common import Ctx, cpu_child, host_threads, log, peaks  # noqa: E402
+
+WORKLOADS = ["hifigan_cfg2", "fregan_cfg2", "wavernn_cfg1", "wavernn_cfg3", "tacotron_cfg4", "e2e_cfg5"]
 
 
 def parse():
@@ -40,103 +44,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hifigan_cfg2", choices=["hifigan_cfg2", "fregan_cfg2", "wavernn_cfg3", "tacotron_cfg4", "e2e_cfg5"])
+    ap.add_argument("--workload", default="hifigan_cfg2", choices=WORKLOADS)
     ap.add_argument("--precision", default=os.environ.get("MOCKINGBIRD_B200_GAN_PRECISION", "f16tc"))
+    ap.add_argument("--soak-seconds", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="headline workload only")
     ap.add_argument("--cpu-child", nargs=3, default=None, help=argparse.SUPPRESS)
     return ap.parse_args()
-
-
-def host_threads() -> int:
-    """CPU threads this job may really use: affinity mask capped by the cgroup CPU quota (a container
-    on a 200-core host with an 8-core quota must not spawn 200 spinning OpenMP threads)."""
-    n = len(os.sched_getaffinity(0))
-    try:
-        txt = Path("/sys/fs/cgroup/cpu.max").read_text().split()
-        if txt[0] != "max":
-            n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
-    except Exception:
-        try:
-            q = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
-            per = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
-            if q > 0:
-                n = min(n, max(1, int(q / per + 0.5)))
-        except Exception:
-            pass
-    return max(1, min(n, 64))
-
-
-def log(msg: str) -> None:
-    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
-
-
-def cpu_child(workload: str, amount: int, threads: int, timeout: float):
-    """Run the CPU baseline in a child process with CUDA hidden and a hard
-    time limit; returns the child's JSON dict or None."""
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS=str(threads), MKL_NUM_THREADS=str(threads))
-    try:
-        out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--cpu-child", workload, str(amount), str(threads)],
-                             env=env, capture_output=True, text=True, timeout=timeout)
-        for line in reversed(out.stdout.strip().splitlines()):
-            if line.startswith("{"):
-                return json.loads(line)
-        log(f"cpu child produced no result: {out.stderr[-500:]}")
-    except subprocess.TimeoutExpired:
-        log(f"cpu child exceeded {timeout}s")
-    return None
-
-
-def peaks():
-    p = ROOT / "MEASURED_PEAKS.json"
-    if p.is_file():
-        d = json.loads(p.read_text())
-        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
-                "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
-
-
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index: int):
-        self.index = index
-        self.rows = []
-        self.proc = None
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -171,7 +85,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_threads()
-    if args.workload == "wavernn_cfg3":
+    if args.workload in ("wavernn_cfg1", "wavernn_cfg3"):
         import bench_wavernn
 
         return bench_wavernn.run_reference(args, threads)
@@ -185,24 +99,27 @@ def run_reference(args):
         return bench_e2e.run_reference(args, threads)
     per_step = []
     total = 0
+    SAMPLE = 8  # utterances of the 32-utterance batch timed per step (bounded sample; the forward is per utterance)
     for s in range(args.warmup + args.steps):
         log(f"reference step {s}")
-        v, dt, n = cpu_hifigan(32, 1, threads, fregan=(args.workload == "fregan_cfg2"))
+        v, dt, n = cpu_hifigan(SAMPLE, 1, threads, fregan=(args.workload == "fregan_cfg2"))
         if s >= args.warmup:
             per_step.append(dt)
             total += n
     secs = sum(per_step)
     value = total / secs
+    ms_full_step = 1e3 * (32 * 51200) / value
     line = {
         "impl": "reference", "metric": "vocoder audio samples/sec", "value": value, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
-        "rtf": (secs / args.steps) / (32 * 51200 / 16000.0), "higher_is_better": True, "scaling": "weak",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full_step,
+        "rtf": (ms_full_step * 1e-3) / (32 * 51200 / 16000.0), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: Generator fwd, batch 32 x 256 frames x 80 mels (batch-1 calls)",
-                   "per_gpu_batch": 32, "frames": 256},
+        "config": {"workload": f"{args.workload}: Generator fwd, batch 32 x 256 frames x 80 mels per GPU",
+                   "per_gpu_batch": 32, "frames": 256, "precision": "fp32 (torch CPU)", "parallelism": "cpu"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps x 32 utterances x 256 frames, torch-CPU oracle "
-                                   "(bit-identical to the reference forward)"},
+                         "sample": f"{args.steps} steps x {SAMPLE} of the 32 utterances x 256 frames (batch-1 calls like "
+                                   "hifigan/inference.py:66-70), torch-CPU oracle (bit-identical to the reference forward); "
+                                   "ms_per_step is scaled to the 32-utterance step"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -210,108 +127,59 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours_hifigan(args):
+# ------------------------------------------------------------------------------------------------
+def measure_hifigan(ctx: Ctx, args, workload: str, precision: str, steps: int, warmup: int, soak_s: float, cpu: bool,
+                    roofline: bool = True):
+    """HiFi-GAN / Fre-GAN generator forward on the cfg-2 batch shape; returns the JSON dict (rank 0) or None."""
+    import numpy as np
     import torch
-    import torch.distributed as dist
 
-    sys.path.insert(0, str(ROOT / "oracle"))  # ref_init only: seeded random-init weights (no checkpoints exist)
-
-    sys.path.insert(0, str(ROOT / "synth_weights"))
+    sys.path.insert(0, str(ROOT / "synth_weights"))  # seeded random-init weights (no checkpoints exist)
     import ref_init as ri
     from mockingbird_b200 import _lib
-    from mockingbird_b200.vocoder.fregan.models import FreGAN
-    from mockingbird_b200.vocoder.hifigan.models import Generator
+    from mockingbird_b200.vocoder.fregan import inference as fre_vocoder
+    from mockingbird_b200.vocoder.hifigan import inference as gan_vocoder
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
-
-    fre = args.workload == "fregan_cfg2"  # SURVEY.md row C1 on the same batch shape (not a BASELINE.json config)
+    torch, dist = ctx.torch, ctx.dist
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    fre = workload == "fregan_cfg2"  # SURVEY.md row C1 on the same batch shape (not a BASELINE.json config)
     cfg = ri.FREGAN_CONFIG if fre else ri.HIFIGAN_CONFIG_16K
-    make_sd = (lambda: ri.fregan_state_dict(cfg, 0)) if fre else (lambda: ri.hifigan_state_dict(cfg, 0))
+    sd = ri.fregan_state_dict(cfg, 0) if fre else ri.hifigan_state_dict(cfg, 0)
     B, T = 32, 256
-    g = (FreGAN(cfg, precision=args.precision) if fre else Generator(cfg, precision=args.precision)).to(dev)
-    # rank 0 builds + packs the weights, NCCL broadcasts the packed arena (the only collective)
-    if rank == 0:
-        g.load_state_dict(make_sd())
-        g.eval()
-        g.remove_weight_norm()
-    else:
-        g.load_state_dict(make_sd())  # shapes only; contents overwritten below
-        g.eval()
-        g.remove_weight_norm()
+    mod = fre_vocoder if fre else gan_vocoder
+    g = mod.load_state(sd, cfg, precision=precision)   # the module-level singleton the drop-in surface serves
     if world > 1:
-        dist.broadcast(g.packed_arena(), src=0)
+        dist.broadcast(g.packed_arena(), src=0)         # rank 0's packed weights over NCCL (the only collective)
     hop = g.hop
     mel = (torch.rand(B, 80, T, generator=torch.Generator().manual_seed(2 + rank)) * 8 - 4)
     mel_dev = mel.to(dev)
-    mel_pin = mel.pin_memory()
-    wav_pin = torch.empty(B, 1, T * hop).pin_memory()
+    mels_np = [mel[i].numpy() for i in range(B)]
     samples_per_step = B * T * hop
     lib = _lib.lib()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        barrier()
-        return float(ms.item())
+    produced = {"n": 0}
 
     def step_resident():
         g(mel_dev)
 
     def step_e2e():
-        x = mel_pin.to(dev, non_blocking=True)
-        y = g(x)
-        wav_pin.copy_(y, non_blocking=True)
+        wavs = mod.infer_waveforms(mels_np, batch_size=B)   # host numpy in, host numpy out, host sync inside
+        produced["n"] = sum(len(w) for w in wavs)
 
-    log("weights packed; warm-up")
-    for _ in range(max(3, args.warmup)):
-        step_resident()
-    torch.cuda.synchronize()
-    log("timed region (resident)")
-    sampler = ClockSampler(local)
-    sampler.start()
+    log(f"{workload}/{precision}: weights packed; resident pass")
     l0 = lib.mb_launch_count()
-    ms_total = timed(step_resident, args.steps)
-    launches = int(lib.mb_launch_count() - l0)
-    clocks = sampler.stop()
-    log(f"resident: {ms_total / args.steps:.3f} ms/step; e2e pass")
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    log("profiled pass")
-
-    value = world * samples_per_step * args.steps / (ms_total * 1e-3)
-    e2e_value = world * samples_per_step * args.steps / (ms_e2e * 1e-3)
-    ms_step = ms_total / args.steps
-
-    # ---- roofline of the dominant kernel: separate profiled pass (events around every launch)
+    r = ctx.timed(step_resident, steps, max(3, warmup), soak_s)
+    launches_total = int(lib.mb_launch_count() - l0)
+    launches = int(round(launches_total * steps / (max(3, warmup) + 2 * steps + r["soak_steps"])))
+    log(f"resident: soaked {r['ms'] / steps:.3f} ms/step, burst {r['ms_burst'] / steps:.3f}; e2e pass")
+    e = ctx.timed(step_e2e, steps, 2, min(soak_s, 1.0), host_clock=True)
+    assert produced["n"] == samples_per_step
+    ms_step = r["ms"] / steps
+    ms_burst = r["ms_burst"] / steps
+    value = world * samples_per_step / (ms_step * 1e-3)
     pk = peaks()
-    roof = None
-    roof_hbm = None
-    roof_tensor = None
-    if rank == 0:
-        n = g.num_layers()
+    roof = roof_tensor = roof_hbm = None
+    step_tf = None
+    if rank == 0 and roofline:
         acc = {}
         reps = 3
         for _ in range(reps):
@@ -328,76 +196,135 @@ def run_ours_hifigan(args):
         dom = max(acc, key=lambda k: acc[k][0])
         t_ms, flops, lbytes, cnt = acc[dom]
         tf = flops / (t_ms * 1e-3) / 1e12
-        roof_tensor = None
-        if args.precision == "f16tc":
-            peak = pk["tflops_sustained"]
-            roof_tensor = {"bound": "tensor", "kernel": f"tc_conv / tc_pair ({dom})", "achieved": tf, "peak": peak,
-                           "unit": "TFLOP/s", "frac": tf / peak, "peak_source": pk["source"] + " bf16 sustained (fp16 same rate)",
-                           "launches_timed": cnt, "flop_per_launch": flops / cnt, "ms_per_launch": t_ms / cnt,
-                           "share_of_step": (t_ms / reps) / ms_step}
-            # north-star roofline of the dominant kernel family (tcgen05 conv kernels: conv_pre, ups, resblocks):
-            # ALGORITHMIC layer-granular fp32 bytes of those layers (13 190 B per output sample over
-            # the whole generator) / their event-timed duration, vs the measured HBM copy bandwidth.  traffic =
-            # DRAM bytes the same launches really move (ncu dram__bytes_read+write, profiles/, per launch).
+        total_flops = sum(v[1] for v in acc.values()) / reps
+        if precision != "fp32":
+            mma_mult = 3.0 if precision == "f16x3" else 1.0
+            roof_tensor = {"bound": "tensor", "kernel": f"tc_conv / tc_pair ({dom})", "unit": "TFLOP/s",
+                           "achieved_soaked": total_flops / (ms_step * 1e-3) / 1e12, "peak_sustained": pk["tflops_sustained"],
+                           "frac_soaked": mma_mult * total_flops / (ms_step * 1e-3) / 1e12 / pk["tflops_sustained"],
+                           "achieved_burst": total_flops / (ms_burst * 1e-3) / 1e12, "peak_burst": pk["tflops_burst"],
+                           "frac_burst": mma_mult * total_flops / (ms_burst * 1e-3) / 1e12 / pk["tflops_burst"],
+                           "mma_flops_per_useful_flop": mma_mult, "peak_source": pk["source"] + ", bf16 (fp16 runs at the same rate)",
+                           "note": "whole-step useful FLOPs / step time; frac counts the MMA passes really issued"}
             fam = [k for k in acc if k != "conv_post"]
             fam_ms = sum(acc[k][0] for k in fam) / reps
             fam_bytes = sum(acc[k][2] for k in fam) / reps
+            fam_launches = sum(acc[k][3] for k in fam) / reps
             traffic = None
-            launches_per_fw = None
             tj = ROOT / "profiles" / "r01_hifigan_dram_traffic.json"
-            if tj.exists() and not fre:
-                tr = json.loads(tj.read_text())
-                traffic = tr["tc_dram_bytes_per_launch"]
-                launches_per_fw = tr["tc_launches_per_forward"]
+            if tj.exists() and not fre and precision == "f16tc":
+                traffic = json.loads(tj.read_text())["tc_dram_bytes_per_launch"]
             gbs = fam_bytes / (fam_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "tc_conv_kernel + tc_pair_kernel (tcgen05 tap convs; all layers but conv_post)",
                     "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": traffic,
-                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_hifigan_dram_traffic.json",
-                    "launches_per_step": launches_per_fw,
-                    "algorithmic_bytes_per_launch": (fam_bytes / launches_per_fw) if launches_per_fw else None,
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/)",
+                    "plan_ops_per_step": fam_launches, "algorithmic_bytes_per_op": fam_bytes / max(fam_launches, 1),
                     "algorithmic_bytes_per_step": fam_bytes, "ms_per_step_in_kernel": fam_ms,
-                    "share_of_step": fam_ms / ms_step, "peak_source": pk["source"] + " HBM copy bandwidth",
-                    "definition": "layer-granular fp32 bytes (inputs + outputs of every conv layer + weights once) / time"}
+                    "share_of_step": fam_ms / ms_step, "peak_source": pk["source"] + ", HBM copy bandwidth",
+                    "definition": "layer-granular fp32 bytes (inputs + outputs of every conv layer + weights once, SURVEY.md 8d) / "
+                                  "event-timed duration of those launches (profiled pass, no PDL overlap)"}
         else:
             peak = 72.0  # 148 SM x 128 lanes x 2 x ~1.9 GHz FP32 FFMA, nominal
             roof = {"bound": "tensor", "kernel": f"tapconv_f32 ({dom})", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                     "frac": tf / peak, "traffic": None, "peak_source": "nominal fp32 FFMA (parity-anchor path)",
                     "launches_timed": cnt, "share_of_step": (t_ms / reps) / ms_step}
-        # north-star view: layer-granular fp32 bytes of the whole step / step time vs measured HBM copy BW
         step_bytes = sum(v[2] for v in acc.values()) / reps + (68_926_660 if fre else 51_902_980)  # + fp32 weights once
         gbs = step_bytes / (ms_step * 1e-3) / 1e9
         roof_hbm = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                    "bytes_per_step": step_bytes, "definition": "layer-granular fp32 bytes (SURVEY.md 8d) / step time"}
-        step_tf = sum(v[1] for v in acc.values()) / reps / (ms_step * 1e-3) / 1e12
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+                    "achieved_burst": step_bytes / (ms_burst * 1e-3) / 1e9, "bytes_per_step": step_bytes,
+                    "definition": "layer-granular fp32 bytes of the whole step (SURVEY.md 8d: 21.61 GB) / step time"}
+        step_tf = total_flops / (ms_step * 1e-3) / 1e12
+    cpu_d = None
+    if rank == 0 and cpu:
         threads = host_threads()
         log(f"cpu baseline on {threads} threads")
-        r = cpu_child(args.workload, 4, threads, 240.0)
-        if r is not None:
-            cpu = {"value": r["value"], "unit": "samples/s", "cores": threads, "kind": "port",
-                   "sample": f"4 passes x 32 utterances x 256 frames ({r['seconds']:.1f} s), torch-CPU oracle "
-                             "(bit-identical to the reference forward), batch-1 calls like hifigan/inference.py"}
-    if rank == 0:
-        line = {
-            "metric": "vocoder audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
-            "rtf": (ms_step * 1e-3) / (samples_per_step / 16000.0), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate + f32 residual" if args.precision == "f16tc" else "f32",
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload}: Generator fwd, batch 32 x 256 frames x 80 mels per GPU",
-                       "per_gpu_batch": B, "frames": T, "precision": args.precision, "parallelism": f"dp{world}",
-                       "l2": "per-step working set (2.9 GB of activations) >> 126 MB L2; no explicit flush",
-                       "weights": "random init, torch.manual_seed(0) order of the reference constructor"},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": mel_pin.numel() * 4,
-                    "d2h_bytes_per_step": wav_pin.numel() * 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tensor,
-            "roofline_hbm_step": roof_hbm,
-            "step_tflops": step_tf, "cpu_baseline": cpu,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        rc = cpu_child(workload, 2, threads, 240.0)
+        if rc is not None:
+            cpu_d = {"value": rc["value"], "unit": "samples/s", "cores": threads, "kind": "port",
+                     "sample": f"2 passes x 32 utterances x 256 frames ({rc['seconds']:.1f} s), torch-CPU oracle "
+                               "(bit-identical to the reference forward), batch-1 calls like hifigan/inference.py:66-70"}
+    if rank != 0:
+        return None
+    dtype = {"f16tc": "f16 operands / f32 accumulate (3-term-split serial layers), f32 residual in the full-rate stage",
+             "f16x3": "3-term f16 split on tensor cores (FP32-equivalent) / f32 accumulate", "fp32": "f32"}.get(precision, precision)
+    return {
+        "metric": "vocoder audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": steps, "warmup": max(3, warmup), "ms_per_step": ms_step,
+        "rtf": (ms_step * 1e-3) / (samples_per_step / 16000.0), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": f"{workload}: Generator fwd, batch 32 x 256 frames x 80 mels per GPU",
+                   "per_gpu_batch": B, "frames": T, "precision": precision, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (2.9 GB of activations) >> 126 MB L2; no explicit flush",
+                   "weights": "random init, torch.manual_seed(0) order of the reference constructor"},
+        "burst": {"value": world * samples_per_step / (ms_burst * 1e-3), "ms_per_step": ms_burst, "clocks": r["clocks_burst"]},
+        "soak": {"seconds": r["soak_s"], "steps": r["soak_steps"], "clocks": r["clocks_soak"]},
+        "e2e": {"value": world * samples_per_step * steps / (e["ms"] * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": B * 80 * T * 4 + B * 4, "d2h_bytes_per_step": samples_per_step * 4,
+                "ms_per_step": e["ms"] / steps, "burst_value": world * samples_per_step * steps / (e["ms_burst"] * 1e-3),
+                "surface": "vocoder.hifigan.inference.infer_waveforms(list of host numpy mels) -> list of host numpy waveforms"},
+        "gpu_launches": launches, "clocks": r["clocks"], "roofline": roof, "roofline_tensor": roof_tensor,
+        "roofline_hbm_step": roof_hbm, "step_tflops": step_tf, "cpu_baseline": cpu_d,
+    }
+
+
+def _short(d, keys=("value", "unit", "ms_per_step", "burst", "e2e", "roofline", "cpu_baseline", "config", "dtype", "gpu_launches",
+                    "steps", "scaling", "n_gpus")):
+    """secondary entries keep the contract's keys, drop the bulk"""
+    return None if d is None else {k: d[k] for k in d if k in keys or k.startswith(("value_", "e2e_", "raw_", "mel_", "utter", "stage", "rtf", "us_", "note"))}
+
+
+def run_ours(args):
+    ctx = Ctx()
+    try:
+        cpu = (not args.no_cpu_baseline) and ctx.world == 1
+        if args.workload in ("hifigan_cfg2", "fregan_cfg2"):
+            line = measure_hifigan(ctx, args, args.workload, args.precision, args.steps, args.warmup, args.soak_seconds, cpu)
+            secondary = {}
+            if args.workload == "hifigan_cfg2" and not args.no_secondary:
+                import bench_e2e
+                import bench_tacotron
+                import bench_wavernn
+
+                def sec(name, fn):
+                    try:
+                        t0 = time.perf_counter()
+                        d = fn()
+                        if ctx.rank == 0:
+                            secondary[name] = _short(d)
+                            log(f"secondary {name}: {time.perf_counter() - t0:.1f} s")
+                    except Exception as ex:  # a secondary must never cost the headline line
+                        log(f"secondary {name} failed: {ex!r}")
+                        if ctx.rank == 0:
+                            secondary[name] = {"error": repr(ex)[:300]}
+
+                if ctx.world == 1:
+                    sec("hifigan_fp32_equivalent", lambda: measure_hifigan(ctx, args, "hifigan_cfg2", "f16x3", max(3, args.steps // 4),
+                                                                         2, 0.5, False, roofline=True))
+                    sec("wavernn_cfg1", lambda: bench_wavernn.measure_cfg1(ctx, args, cpu))
+                sec("wavernn_cfg3", lambda: bench_wavernn.measure_cfg3(ctx, args, cpu))
+                if ctx.world > 1:
+                    sec("wavernn_cfg3_fold_sharded", lambda: bench_wavernn.measure_cfg3_sharded(ctx, args))
+                sec("tacotron_cfg4", lambda: bench_tacotron.measure(ctx, args, cpu, steps=3))
+                sec("e2e_cfg5", lambda: bench_e2e.measure(ctx, args, cpu, steps=2))
+                sec("e2e_cfg5_strong_1024", lambda: bench_e2e.measure(ctx, args, False, steps=1, strong_total=1024))
+            if ctx.rank == 0:
+                if secondary:
+                    line["secondary"] = secondary
+                print(json.dumps(line), flush=True)
+        else:
+            import bench_e2e
+            import bench_tacotron
+            import bench_wavernn
+
+            fn = {"wavernn_cfg1": lambda: bench_wavernn.measure_cfg1(ctx, args, cpu),
+                  "wavernn_cfg3": lambda: bench_wavernn.measure_cfg3(ctx, args, cpu, steps=max(3, min(args.steps, 5))),
+                  "tacotron_cfg4": lambda: bench_tacotron.measure(ctx, args, cpu, steps=max(1, min(args.steps, 10))),
+                  "e2e_cfg5": lambda: bench_e2e.measure(ctx, args, cpu, steps=max(1, min(args.steps, 5)))}[args.workload]
+            line = fn()
+            if ctx.rank == 0:
+                print(json.dumps(line), flush=True)
+    finally:
+        ctx.close()
 
 
 def main():
@@ -417,24 +344,12 @@ def main():
         else:
             import bench_wavernn
 
-            v, dt = bench_wavernn.cpu_twin(amount, threads)
+            v, dt = bench_wavernn.cpu_torch_oracle(workload, amount, threads)
         print(json.dumps({"value": v, "seconds": dt}))
         return
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload in ("hifigan_cfg2", "fregan_cfg2"):
-        return run_ours_hifigan(args)
-    if args.workload == "tacotron_cfg4":
-        import bench_tacotron
-
-        return bench_tacotron.run_ours(args)
-    if args.workload == "e2e_cfg5":
-        import bench_e2e
-
-        return bench_e2e.run_ours(args)
-    import bench_wavernn
-
-    return bench_wavernn.run_ours(args)
+    return run_ours(args)
 
 
 if __name__ == "__main__":

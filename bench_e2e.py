@@ -72,7 +72,7 @@ def cpu_oracle(n_utt: int, threads: int, frames: int = 200):
 
 def run_reference(args, threads):
     per = []
-    n_utt, frames = 32, 200
+    n_utt, frames = 8, 200  # bounded sample per step
     for s in range(args.warmup + args.steps):
         v, dt = cpu_oracle(n_utt, threads, frames)
         if s >= args.warmup:
@@ -84,23 +84,23 @@ def run_reference(args, threads):
         "utterances_per_s": v / 80000.0, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "e2e_cfg5: encoder -> Tacotron -> HiFi-GAN (sample: 32 utterances x 200 frames per step)"},
+        "config": {"workload": "e2e_cfg5: encoder -> Tacotron(steps=400, r=2) -> HiFi-GAN, 128 utterances per GPU"},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": "32 utterances x 200 of 400 decoder frames per step, torch-CPU oracles chained"},
+                         "sample": "8 utterances x 200 of 400 decoder frames per step, torch-CPU oracles chained"},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
-def run_ours(args):
+def measure(ctx, args, cpu: bool, steps: int = 2, strong_total: int = 0):
+    """weak scaling (default): 128 utterances per GPU.  strong_total=1024: the FIXED 1024-utterance job of BASELINE.json
+    configs[4] dealt over however many GPUs there are (N = 1 holds all 1024) - the driver's N = 1,2,4,8 runs give
+    the strong-scaling curve."""
     import numpy as np
     import torch
-    import torch.distributed as dist
 
-    sys.path.insert(0, str(ROOT / "oracle"))  # ref_init only: seeded random-init weights (no checkpoints exist)
-
-    sys.path.insert(0, str(ROOT / "synth_weights"))
+    sys.path.insert(0, str(ROOT / "synth_weights"))  # seeded random-init weights (no checkpoints exist)
     import ref_init as ri
-    from bench import ClockSampler, cpu_child, host_threads, log
+    from bench_common import cpu_child, host_threads, log
     from mockingbird_b200 import _lib
     from mockingbird_b200.distributed import shard_utterances
     from mockingbird_b200.encoder import inference as enc_inf
@@ -109,16 +109,7 @@ def run_ours(args):
     from mockingbird_b200.synthesizer.inference import Synthesizer
     from mockingbird_b200.vocoder.hifigan import inference as gan_vocoder
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
     # models: every rank builds the objects, rank 0's packed weights are broadcast over NCCL
     enc = SpeakerEncoder(dev)
     enc.load_state_dict(ri.encoder_state_dict(0))
@@ -131,22 +122,23 @@ def run_ours(args):
     gen = gan_vocoder.load_state(ri.hifigan_state_dict(cfg, 0), cfg)
     if world > 1:
         for m in (enc, taco, gen):
-            dist.broadcast(m.packed_arena(), src=0)
+            ctx.dist.broadcast(m.packed_arena(), src=0)
+    old_bs = shp.synthesis_batch_size
     shp.synthesis_batch_size = TBATCH
 
-    n_total = UTT_PER_GPU * world
+    n_total = strong_total if strong_total else UTT_PER_GPU * world
     lens, chars = make_utterances(n_total)
     mine = shard_utterances(lens.tolist(), rank, world)
-    assert len(mine) == UTT_PER_GPU
+    n_mine = len(mine)
     seqs = [chars[i, : int(lens[i])].tolist() for i in mine]  # sorted longest first -> little padding per batch
     parts = [(torch.rand(PARTIALS, PFRAMES, 40, generator=torch.Generator().manual_seed(1000 + i)) * 0.2).numpy() for i in mine]
     parts_dev = torch.from_numpy(np.concatenate(parts)).to(dev)
-    offsets = list(range(0, UTT_PER_GPU * PARTIALS + 1, PARTIALS))
+    offsets = list(range(0, n_mine * PARTIALS + 1, PARTIALS))
     chars_dev = []
-    for s in range(0, UTT_PER_GPU, TBATCH):
-        tc = max(len(q) for q in seqs[s:s + TBATCH])
-        c = torch.zeros(min(TBATCH, UTT_PER_GPU - s), tc, dtype=torch.int32)
-        for b, q in enumerate(seqs[s:s + TBATCH]):
+    for s0 in range(0, n_mine, TBATCH):
+        tc = max(len(q) for q in seqs[s0:s0 + TBATCH])
+        c = torch.zeros(min(TBATCH, n_mine - s0), tc, dtype=torch.int32)
+        for b, q in enumerate(seqs[s0:s0 + TBATCH]):
             c[b, : len(q)] = torch.tensor(q, dtype=torch.int32)
         chars_dev.append(c.to(dev))
     lib = _lib.lib()
@@ -167,89 +159,71 @@ def run_ours(args):
         wavs = gan_vocoder.infer_waveforms(specs, batch_size=VBATCH)
         produced["samples"] = sum(len(w) for w in wavs)
 
-    def barrier():
+    try:
+        l0 = lib.mb_launch_count()
+        r = ctx.timed(step_resident, steps, 1, 0.0, host_clock=True)
+        launches = int(lib.mb_launch_count() - l0) * steps // (1 + 2 * steps)
+        n_res = produced["samples"]
+        # stage split of one resident step (events between stages)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        ev[0].record()
+        emb = enc.reduce_partials(enc.forward(parts_dev), offsets)
+        ev[1].record()
+        lins = [taco.generate(c, emb[bi * TBATCH: bi * TBATCH + c.shape[0]], steps=STEPS, style_idx=-1, min_stop_token=10)[1]
+                for bi, c in enumerate(chars_dev)]
+        ev[2].record()
+        for lin in lins:
+            for v in range(0, lin.shape[0], VBATCH):
+                gen(lin[v:v + VBATCH].contiguous())
+        ev[3].record()
         torch.cuda.synchronize()
-
-    def timed(fn, k):
-        barrier()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        barrier()
-        return float(ms.item())
-
-    log("e2e_cfg5: warm-up")
-    for _ in range(max(1, min(args.warmup, 3))):
-        step_resident()
-    sampler = ClockSampler(local)
-    sampler.start()
-    l0 = lib.mb_launch_count()
-    k = max(1, args.steps)
-    ms = timed(step_resident, k)
-    launches = int(lib.mb_launch_count() - l0)
-    clocks = sampler.stop()
-    n_res = produced["samples"]
-    # stage split of one resident step (events between stages)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    torch.cuda.synchronize()
-    ev[0].record()
-    emb = enc.reduce_partials(enc.forward(parts_dev), offsets)
-    ev[1].record()
-    lins = [taco.generate(c, emb[bi * TBATCH: bi * TBATCH + c.shape[0]], steps=STEPS, style_idx=-1, min_stop_token=10)[1]
-            for bi, c in enumerate(chars_dev)]
-    ev[2].record()
-    for lin in lins:
-        for v in range(0, lin.shape[0], VBATCH):
-            gen(lin[v:v + VBATCH].contiguous())
-    ev[3].record()
-    torch.cuda.synchronize()
-    split = {"encoder_ms": ev[0].elapsed_time(ev[1]), "tacotron_ms": ev[1].elapsed_time(ev[2]),
-             "hifigan_ms": ev[2].elapsed_time(ev[3])}
-    log(f"resident {ms / k:.1f} ms/step {split}; e2e pass")
-    step_e2e()
-    ms_e2e = timed(step_e2e, k)
-    n_e2e = produced["samples"]
-    if rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline:
-            threads = host_threads()
-            r = cpu_child("e2e_cfg5", 64, threads, 300.0)
-            if r:
-                cpu = {"value": r["value"], "unit": "samples/s", "cores": threads, "kind": "port",
-                       "sample": f"64 utterances x 200 of 400 decoder frames ({r['seconds']:.1f} s), torch-CPU oracles chained"}
-        value = world * n_res * k / (ms * 1e-3)
-        h2d = sum(p.nbytes for p in parts) + sum(len(q) for q in seqs) * 8 + UTT_PER_GPU * 256 * 4 + UTT_PER_GPU * 80 * STEPS * 4
-        d2h = UTT_PER_GPU * 256 * 4 + UTT_PER_GPU * 80 * STEPS * 4 + n_e2e * 4
-        # dominant stage = Tacotron (FP32 FFMA): its FLOPs over its share of the step
-        flops = 2.0 * UTT_PER_GPU * (20.99e6 * (STEPS // R) + 8.03e6 * STEPS + 3.2e6 * 70)
-        taco_s = split["tacotron_ms"] * 1e-3
-        print(json.dumps({
-            "metric": "vocoder audio samples/sec", "value": value, "unit": "samples/s",
-            "utterances_per_s": value / (STEPS * 200), "n_gpus": world, "steps": k, "warmup": max(1, min(args.warmup, 3)),
-            "ms_per_step": ms / k, "rtf": (ms / k * 1e-3) / (n_res / 16000.0), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (encoder, Tacotron) / f16 operands + f32 accumulate (HiFi-GAN)", "data": "synthetic",
-            "config": {"workload": "e2e_cfg5: encoder -> Tacotron(steps=400, r=2) -> HiFi-GAN, 128 utterances per GPU "
-                                   f"({n_total} total), length-sorted round-robin shards", "parallelism": f"dp{world}",
-                       "l2": "per-step working set (activations of 128 utterances) exceeds L2"},
-            "stage_split_ms": split,
-            "e2e": {"value": world * n_e2e * k / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / k},
-            "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"bound": "latency", "kernel": "Tacotron stage (FP32 FFMA GEMMs; 200 dependent decoder steps per batch of 64)",
-                         "achieved": flops / taco_s / 1e12, "peak": 72.0, "unit": "TFLOP/s",
-                         "frac": flops / taco_s / 1e12 / 72.0, "traffic": None,
-                         "note": "pipeline of three models; per-stage times in stage_split_ms; the HiFi-GAN stage has its own "
-                                 "roofline line under --workload hifigan_cfg2"},
-            "cpu_baseline": cpu}))
+        split = {"encoder_ms": ev[0].elapsed_time(ev[1]), "tacotron_ms": ev[1].elapsed_time(ev[2]),
+                 "hifigan_ms": ev[2].elapsed_time(ev[3])}
+        del lins
+        e = ctx.timed(step_e2e, steps, 1, 0.0, host_clock=True)
+        n_e2e = produced["samples"]
+    finally:
+        shp.synthesis_batch_size = old_bs
+    # totals over ranks (shards differ by at most one utterance)
+    tot = torch.tensor([float(n_res), float(n_e2e)], device=dev)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.all_reduce(tot)
+    if rank != 0:
+        return None
+    ms = r["ms"] / steps
+    cpu_d = None
+    if cpu:
+        threads = host_threads()
+        rc = cpu_child("e2e_cfg5", 16, threads, 300.0)
+        if rc:
+            cpu_d = {"value": rc["value"], "unit": "samples/s", "cores": threads, "kind": "port",
+                     "sample": f"16 utterances x 200 of 400 decoder frames ({rc['seconds']:.1f} s), torch-CPU oracles chained"}
+    value = float(tot[0]) / (ms * 1e-3)
+    h2d = sum(p.nbytes for p in parts) + sum(len(q) for q in seqs) * 8 + n_mine * 256 * 4 + n_mine * 80 * STEPS * 4
+    d2h = n_mine * 256 * 4 + n_mine * 80 * STEPS * 4 + n_e2e * 4
+    flops = 2.0 * n_mine * (20.99e6 * (STEPS // R) + 8.03e6 * STEPS + 3.2e6 * 70)
+    taco_s = split["tacotron_ms"] * 1e-3
+    name = (f"e2e_cfg5 strong: encoder -> Tacotron(steps=400, r=2) -> HiFi-GAN on a FIXED {n_total} utterances dealt over {world} GPU(s)"
+            if strong_total else
+            f"e2e_cfg5: encoder -> Tacotron(steps=400, r=2) -> HiFi-GAN, 128 utterances per GPU ({n_total} total), length-sorted round-robin shards")
+    return {
+        "metric": "vocoder audio samples/sec", "value": value, "unit": "samples/s",
+        "utterances_per_s": value / (STEPS * 200), "n_gpus": world, "steps": steps,
+        "ms_per_step": ms, "rtf": (ms * 1e-3) / (float(tot[0]) / world / 16000.0), "higher_is_better": True,
+        "scaling": "strong" if strong_total else "weak",
+        "dtype": "f32-equivalent (encoder, Tacotron: 3-term f16 split) / f16 operands + f32 accumulate (HiFi-GAN)",
+        "config": {"workload": name, "utterances_total": n_total, "utterances_this_rank": n_mine, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (activations of >= 128 utterances) exceeds L2"},
+        "stage_split_ms": split,
+        "burst": {"value": float(tot[0]) * steps / (r["ms_burst"] * 1e-3)},
+        "e2e": {"value": float(tot[1]) * steps / (e["ms"] * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e["ms"] / steps,
+                "surface": "encoder.inference.embed_utterances_frames -> Synthesizer.synthesize_from_sequences -> "
+                           "hifigan.inference.infer_waveforms (host numpy between the stages, like the reference's callers)"},
+        "gpu_launches": launches, "clocks": r["clocks"],
+        "roofline": {"bound": "latency", "kernel": "Tacotron stage (200 dependent decoder steps per batch of 64)",
+                     "achieved": flops / taco_s / 1e12, "peak": 72.0, "unit": "TFLOP/s",
+                     "frac": flops / taco_s / 1e12 / 72.0, "traffic": None,
+                     "note": "pipeline of three models; per-stage times in stage_split_ms; the HiFi-GAN stage has its own roofline in the headline"},
+        "cpu_baseline": cpu_d}

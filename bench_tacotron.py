@@ -1,21 +1,22 @@
-"""Tacotron workload of bench.py (--workload tacotron_cfg4): BASELINE.json configs[3],
+"""Tacotron workload of bench.py (tacotron_cfg4): BASELINE.json configs[3],
 Tacotron generate + postnet, batch 64 random token sequences of length <= 120, steps=400, r=2,
 min_stop_token=10 (early stop disabled), style_idx=-1.
 
 A "step" is one whole generate() of the batch (25,600 mel frames).  value is reported in the bench
 metric's unit (audio samples/s at the vocoders' 200 samples per frame); mel frames/s is given beside it.
-e2e: host numpy token ids / embeddings in, host numpy spectrograms out (Synthesizer surface after the
+e2e: host token ids / embeddings in, host numpy spectrograms out (Synthesizer surface after the
 text front-end).  Under torchrun every rank synthesises its own batch (weak scaling)."""
 from __future__ import annotations
 
 import json
-import os
 import sys
 import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 B, TC, STEPS, R = 64, 120, 400, 2
+WORKLOAD = ("tacotron_cfg4: Tacotron generate + postnet, B=64, len<=120, steps=400, r=2, min_stop_token=10, "
+            "style_idx=-1 per GPU")
 
 
 def make_inputs(rank=0):
@@ -65,68 +66,36 @@ def run_reference(args, threads):
     print(json.dumps({
         "impl": "reference", "metric": "vocoder audio samples/sec", "value": fps * 200, "unit": "samples/s",
         "mel_frames_per_s": fps, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "tacotron_cfg4: generate B=64, len<=120, r=2 + postnet (sample: 80 of 400 frames per step)"},
+        "ms_per_step": 1e3 * B * STEPS / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": fps * 200, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": "80 of 400 decoder frames per step, torch-CPU oracle (1 ulp from the reference)"},
+                         "sample": "80 of 400 decoder frames per step, torch-CPU oracle (1 ulp from the reference); ms_per_step scaled to 400"},
         "e2e": {"value": fps * 200, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
-def run_ours(args):
-    import numpy as np
+def measure(ctx, args, cpu: bool, steps: int = 3):
     import torch
-    import torch.distributed as dist
-
-    sys.path.insert(0, str(ROOT / "oracle"))
 
     sys.path.insert(0, str(ROOT / "synth_weights"))
     import ref_init as ri
-    from bench import ClockSampler, cpu_child, host_threads, peaks
+    from bench_common import cpu_child, host_threads, peaks
     from mockingbird_b200 import _lib
+    from mockingbird_b200.synthesizer.hparams import hparams as shp
     from mockingbird_b200.synthesizer.inference import Synthesizer
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
     syn = Synthesizer("unused.pt", verbose=False)
     model = syn.load_state(ri.tacotron_state_dict(0, r=R, randomize_bn=True))
     if world > 1:
-        dist.broadcast(model.packed_arena(), src=0)
+        ctx.dist.broadcast(model.packed_arena(), src=0)
     chars, emb, lens = make_inputs(rank)
     chars_dev, emb_dev = chars.to(dev), emb.to(dev)
     seqs = [chars[b, : int(lens[b])].tolist() for b in range(B)]
     embs = [emb[b].numpy() for b in range(B)]
     lib = _lib.lib()
-    from mockingbird_b200.synthesizer.hparams import hparams as shp
-
+    old_bs = shp.synthesis_batch_size
     shp.synthesis_batch_size = B  # one padded batch of 64 like the config (the reference default is 16)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, k):
-        barrier()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(k):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        barrier()
-        return float(ms.item())
 
     def step_resident():
         model.generate(chars_dev, emb_dev, steps=STEPS, style_idx=-1, min_stop_token=10)
@@ -134,47 +103,42 @@ def run_ours(args):
     def step_e2e():
         syn.synthesize_from_sequences(seqs, embs, False, -1, 10, STEPS)
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        step_resident()
-    sampler = ClockSampler(local)
-    sampler.start()
-    l0 = lib.mb_launch_count()
-    k = max(1, args.steps)
-    ms = timed(step_resident, k)
-    launches = int(lib.mb_launch_count() - l0)
-    clocks = sampler.stop()
-    ms_e2e = timed(step_e2e, k)
+    try:
+        l0 = lib.mb_launch_count()
+        r = ctx.timed(step_resident, steps, 2, min(args.soak_seconds, 1.0), host_clock=True)
+        launches = int(lib.mb_launch_count() - l0) * steps // (2 + 2 * steps + max(r["soak_steps"], 0))
+        e = ctx.timed(step_e2e, steps, 1, 0.0, host_clock=True)
+    finally:
+        shp.synthesis_batch_size = old_bs
+    if rank != 0:
+        return None
     frames = B * STEPS
-    fps = world * frames * k / (ms * 1e-3)
-    if rank == 0:
-        cpu = None
-        if not args.no_cpu_baseline:
-            threads = host_threads()
-            r = cpu_child("tacotron_cfg4", 400, threads, 240.0)
-            if r:
-                cpu = {"value": r["value"] * 200, "unit": "samples/s", "mel_frames_per_s": r["value"], "cores": threads,
-                       "kind": "port", "sample": f"400 of 400 decoder frames, B=64 ({r['seconds']:.1f} s), torch-CPU oracle"}
-        flops = 2.0 * (20.99e6 * 200 * B + 8.03e6 * STEPS * B + 3.2e6 * TC * B)
-        pk = peaks()
-        print(json.dumps({
-            "metric": "vocoder audio samples/sec", "value": fps * 200, "unit": "samples/s", "mel_frames_per_s": fps,
-            "n_gpus": world, "steps": k, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms / k,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "tacotron_cfg4: Tacotron generate + postnet, B=64, len<=120, steps=400, r=2, "
-                                   "min_stop_token=10, style_idx=-1 per GPU", "parallelism": f"dp{world}",
-                       "l2": "decoder weights (162 MB of hi/lo fp16 images) stream from L2/HBM every step; no flush applicable"},
-            "e2e": {"value": world * frames * k / (ms_e2e * 1e-3) * 200, "unit": "samples/s",
-                    "h2d_bytes_per_step": int(B * TC * 8 + B * 256 * 4), "d2h_bytes_per_step": int(frames * 80 * 4),
-                    "ms_per_step": ms_e2e / k},
-            "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "tc_skinny / tc_gru / tc_big (tcgen05 GEMMs, 3-term fp16 split = 3 MMA flops per "
-                                                       "useful flop, FP32-equivalent)",
-                         "achieved": flops / (ms / k * 1e-3) / 1e12, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": 3.0 * flops / (ms / k * 1e-3) / 1e12 / pk["tflops_sustained"], "traffic": None,
-                         "peak_source": pk["source"] + " bf16 sustained (fp16 same rate)",
-                         "note": "achieved = useful (FP32-equivalent) FLOPs of the whole generate / time; frac counts the 3 MMA passes. "
-                                 "The path is bound by 200 dependent decoder steps (~150 us each, 22 launches replayed from a CUDA graph), "
-                                 "not by the tensor pipe; per-kernel times in profiles/r01_ncu_launches_tacotron_v4_summary.txt"},
-            "cpu_baseline": cpu}))
-    if world > 1:
-        dist.destroy_process_group()
+    ms = r["ms"] / steps
+    fps = world * frames / (ms * 1e-3)
+    cpu_d = None
+    if cpu:
+        threads = host_threads()
+        rc = cpu_child("tacotron_cfg4", 80, threads, 240.0)
+        if rc:
+            cpu_d = {"value": rc["value"] * 200, "unit": "samples/s", "mel_frames_per_s": rc["value"], "cores": threads,
+                     "kind": "port", "sample": f"80 of 400 decoder frames, B=64 ({rc['seconds']:.1f} s), torch-CPU oracle"}
+    flops = 2.0 * (20.99e6 * 200 * B + 8.03e6 * STEPS * B + 3.2e6 * TC * B)
+    pk = peaks()
+    return {
+        "metric": "vocoder audio samples/sec", "value": fps * 200, "unit": "samples/s", "mel_frames_per_s": fps,
+        "n_gpus": world, "steps": steps, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "dtype": "f32 (3-term f16 split on tensor cores, FP32-equivalent)",
+        "config": {"workload": WORKLOAD, "parallelism": f"dp{world}",
+                   "l2": "decoder weights (162 MB of hi/lo fp16 images) stream from L2/HBM every step; no flush applicable"},
+        "burst": {"value": world * frames * steps / (r["ms_burst"] * 1e-3) * 200},
+        "e2e": {"value": world * frames * steps / (e["ms"] * 1e-3) * 200, "unit": "samples/s",
+                "h2d_bytes_per_step": int(B * TC * 8 + B * 256 * 4), "d2h_bytes_per_step": int(frames * 80 * 4),
+                "ms_per_step": e["ms"] / steps, "surface": "Synthesizer.synthesize_from_sequences (host ids / embeds -> host numpy mels)"},
+        "gpu_launches": launches, "clocks": r["clocks"],
+        "roofline": {"bound": "tensor", "kernel": "tc_skinny / tc_gru / tc_big (tcgen05 GEMMs, 3-term fp16 split = 3 MMA flops per "
+                                                   "useful flop, FP32-equivalent)",
+                     "achieved": flops / (ms * 1e-3) / 1e12, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": 3.0 * flops / (ms * 1e-3) / 1e12 / pk["tflops_sustained"], "traffic": None,
+                     "peak_source": pk["source"] + ", bf16 sustained (fp16 same rate)",
+                     "note": "achieved = useful (FP32-equivalent) FLOPs of the whole generate / time; frac counts the 3 MMA passes. "
+                             "The path is bound by 200 dependent decoder steps, not by the tensor pipe"},
+        "cpu_baseline": cpu_d}
