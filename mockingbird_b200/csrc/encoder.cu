@@ -182,6 +182,7 @@ int mb_encoder_create(const mb_encoder_config* cfg, mb_encoder** out) {
   mb_encoder* h = new mb_encoder();
   h->cfg = c;
   const size_t H = c.hidden_size;
+  slot(h, "scratch.absmax.bias_sum", 64);  // device scratch of the weight-image packers (derived: no cudaMalloc after create)
   for (int l = 0; l < c.num_layers; ++l) {
     const size_t in = l == 0 ? c.mel_n_channels : H;
     const std::string s = std::to_string(l);
@@ -209,6 +210,8 @@ int mb_encoder_set_arena(mb_encoder* h, void* arena, size_t bytes) {
   if (bytes < mb_encoder_arena_bytes(h)) return fail(MB_ERR_WORKSPACE, "mb_encoder_set_arena: arena too small");
   if (((uintptr_t)arena & 255) != 0) return fail(MB_ERR_INVALID, "mb_encoder_set_arena: arena must be 256-byte aligned");
   h->arena = (float*)arena;
+  for (bool& b : h->big_packed) b = false;  // a new arena holds none of the lazily packed images
+  h->finalized = false;
   return MB_OK;
 }
 
@@ -227,6 +230,7 @@ int mb_encoder_set_weight(mb_encoder* h, const char* name, const float* w, const
   MB_CUDA_CHECK(cudaMemcpyAsync(h->arena + it->second.off, w, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   it->second.set = true;
   h->finalized = false;
+  for (bool& b : h->big_packed) b = false;  // images packed from the previous weights are stale
   return MB_OK;
 }
 
@@ -247,15 +251,13 @@ int mb_encoder_finalize(mb_encoder* h, void* stream) {
   if (enc_use_tc(h->cfg)) {
     // tensor-core images of every W_hh (power-of-two scale from max |w|, see tacotron.cu tc_prepare)
     const int H = h->cfg.hidden_size;
-    unsigned int* dmax = nullptr;
-    MB_CUDA_CHECK(cudaMalloc(&dmax, 8 * sizeof(unsigned int)));
+    unsigned int* dmax = reinterpret_cast<unsigned int*>(P(h, "scratch.absmax.bias_sum"));
     MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, 8 * sizeof(unsigned int), st));
     for (int l = 0; l < h->cfg.num_layers; ++l)
       TK(tc_skinny_absmax(P(h, "lstm.weight_hh_l" + std::to_string(l)), (size_t)4 * H * H, dmax + l, st));
     unsigned int hmax[8] = {0};
     MB_CUDA_CHECK(cudaMemcpyAsync(hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
     MB_CUDA_CHECK(cudaStreamSynchronize(st));
-    MB_CUDA_CHECK(cudaFree(dmax));
     for (int l = 0; l < h->cfg.num_layers; ++l) {
       float mx;
       memcpy(&mx, &hmax[l], sizeof(float));
@@ -301,14 +303,12 @@ int mb_encoder_embed_frames(mb_encoder* h, const float* frames, int32_t rows, in
       __half* wimg = reinterpret_cast<__half*>(P(h, "lstm.ih_bigw_l" + s));
       const int KBs = (in_dim + 63) / 64;
       if (!h->big_packed[l]) {
-        unsigned int* dmax = nullptr;
-        MB_CUDA_CHECK(cudaMalloc(&dmax, sizeof(unsigned int)));
+        unsigned int* dmax = reinterpret_cast<unsigned int*>(P(h, "scratch.absmax.bias_sum"));
         MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, sizeof(unsigned int), st));
         TK(tc_skinny_absmax(P(h, "lstm.weight_ih_l" + s), (size_t)4 * H * in_dim, dmax, st));
         unsigned int hmax = 0;
         MB_CUDA_CHECK(cudaMemcpyAsync(&hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
         MB_CUDA_CHECK(cudaStreamSynchronize(st));
-        MB_CUDA_CHECK(cudaFree(dmax));
         float mx;
         memcpy(&mx, &hmax, sizeof(float));
         int e = 0;

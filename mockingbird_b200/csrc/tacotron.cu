@@ -491,14 +491,12 @@ int cbhg_gemm(mb_tacotron* h, const std::string& key, const GemmArgs& a, cudaStr
   const int KBs = (K + 63) / 64;
   __half* wimg = reinterpret_cast<__half*>(P(h, key + ".bigw"));
   if (!h->big_packed.count(key)) {
-    unsigned int* dmax = nullptr;
-    MB_CUDA_CHECK(cudaMalloc(&dmax, sizeof(unsigned int)));
+    unsigned int* dmax = reinterpret_cast<unsigned int*>(P(h, "scratch.absmax.tcb"));
     MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, sizeof(unsigned int), st));
     TK(tc_skinny_absmax(a.W, (size_t)a.N * a.ldw, dmax, st));
     unsigned int hmax = 0;
     MB_CUDA_CHECK(cudaMemcpyAsync(&hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
     MB_CUDA_CHECK(cudaStreamSynchronize(st));
-    MB_CUDA_CHECK(cudaFree(dmax));
     float mx;
     memcpy(&mx, &hmax, sizeof(float));
     int e = 0;
@@ -716,15 +714,13 @@ int run_cbhg(mb_tacotron* h, const std::string& p, int K, int cin, int ch, int p
 // subnormal range) -> hi/lo tile images "<name>.tcw" + tile-order bias "<name>.tcb".  Synchronises the stream.
 int tc_prepare(mb_tacotron* h, const std::string& name, const float* w0, int K0, const float* w1, int K1, const float* b0,
                const float* b1, int N, int lstm_H, cudaStream_t st) {
-  unsigned int* dmax = nullptr;
-  MB_CUDA_CHECK(cudaMalloc(&dmax, sizeof(unsigned int)));
+  unsigned int* dmax = reinterpret_cast<unsigned int*>(P(h, "scratch.absmax.tcb"));
   MB_CUDA_CHECK(cudaMemsetAsync(dmax, 0, sizeof(unsigned int), st));
   TK(tc_skinny_absmax(w0, (size_t)N * K0, dmax, st));
   if (w1) TK(tc_skinny_absmax(w1, (size_t)N * K1, dmax, st));
   unsigned int hmax = 0;
   MB_CUDA_CHECK(cudaMemcpyAsync(&hmax, dmax, sizeof(hmax), cudaMemcpyDeviceToHost, st));
   MB_CUDA_CHECK(cudaStreamSynchronize(st));
-  MB_CUDA_CHECK(cudaFree(dmax));
   float mx;
   memcpy(&mx, &hmax, sizeof(float));
   int e = 0;
@@ -749,6 +745,7 @@ int mb_tacotron_create(const mb_tacotron_config* cfg, mb_tacotron** out) {
   mb_tacotron* h = new mb_tacotron();
   h->cfg = c;
   const int E = c.encoder_dims, D = c.decoder_dims, proj_dims = E + c.speaker_embedding_size + c.gst_E;
+  slot(h, "scratch.absmax.tcb", 64);  // device scratch of the weight-image packers (derived slot: no cudaMalloc after create)
   slot(h, "encoder.embedding.weight", (size_t)c.num_chars * c.embed_dims);
   slot(h, "encoder.pre_net.fc1.weight", (size_t)E * c.embed_dims);
   slot(h, "encoder.pre_net.fc1.bias", E);
@@ -823,6 +820,11 @@ int mb_tacotron_set_arena(mb_tacotron* h, void* arena, size_t bytes) {
   if (bytes < mb_tacotron_arena_bytes(h)) return fail(MB_ERR_WORKSPACE, "mb_tacotron_set_arena: arena too small");
   if (((uintptr_t)arena & 255) != 0) return fail(MB_ERR_INVALID, "mb_tacotron_set_arena: arena must be 256-byte aligned");
   h->arena = (float*)arena;
+  // a new arena holds none of the derived images: forget every lazily packed tensor-core image and its scale
+  h->big_packed.clear();
+  h->tc_inv_scale.clear();
+  h->packed_r = 0;
+  h->finalized = false;
   return MB_OK;
 }
 
@@ -839,12 +841,15 @@ int mb_tacotron_set_weight(mb_tacotron* h, const char* name, const float* w, con
   MB_CUDA_CHECK(cudaMemcpyAsync(h->arena + it->second.off, w, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   it->second.set = true;
   h->finalized = false;
+  h->big_packed.clear();  // images packed from the previous weights are stale
+  h->packed_r = 0;
   return MB_OK;
 }
 
 int mb_tacotron_finalize(mb_tacotron* h, void* stream) {
   if (!h) return fail(MB_ERR_INVALID, "mb_tacotron_finalize: null handle");
   cudaStream_t st = (cudaStream_t)stream;
+  h->big_packed.clear();  // re-packed from the current weights at first use
   const mb_tacotron_config& c = h->cfg;
   auto derived = [](const std::string& n) {
     return n.find(".bn_scale") != std::string::npos || n.find(".bn_shift") != std::string::npos ||

@@ -15,9 +15,18 @@ from .. import _lib
 from .model import SpeakerEncoder
 from .params_data import *  # noqa: F401,F403  (the reference re-exports these, inference.py:1)
 from .params_data import mel_window_step, partials_n_frames, sampling_rate
+from ..synthesizer import audio_host as _audio_host
 
 _model = None  # type: SpeakerEncoder
 _device = None  # type: torch.device
+
+
+def preprocess_wav(fpath_or_wav, source_sr=None, normalize=True, trim_silence=True):
+    """re-exported like the reference does from models/encoder/audio.py:19-53 (host utility: load / resample / volume
+    normalisation / optional webrtcvad trim)"""
+    from .params_data import audio_norm_target_dBFS
+
+    return _audio_host.preprocess_wav(fpath_or_wav, source_sr, normalize, trim_silence, sampling_rate, audio_norm_target_dBFS)
 
 
 def load_model(weights_fpath: Path, device=None):

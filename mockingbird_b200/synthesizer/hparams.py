@@ -37,7 +37,7 @@ hparams = HParams(
     ref_level_db=20, max_abs_value=4., preemphasis=0.97, preemphasize=True,
     # mel front-end (models/synthesizer/hparams.py:16-70)
     frame_shift_ms=None, fmax=7600, signal_normalization=True, allow_clipping_in_normalization=True, symmetric_mels=True,
-    use_lws=False, rescale=True, rescaling_max=0.9,
+    use_lws=False, rescale=True, rescaling_max=0.9, power=1.5, griffin_lim_iters=60,
     tts_embed_dims=512, tts_encoder_dims=256, tts_decoder_dims=128, tts_postnet_dims=512, tts_encoder_K=5,
     tts_lstm_dims=1024, tts_postnet_K=5, tts_num_highways=4, tts_dropout=0.5, tts_cleaner_names=["basic_cleaners"],
     tts_stop_threshold=-3.4, synthesis_batch_size=16, speaker_embedding_size=256, use_gst=True, use_ser_for_gst=True,

@@ -80,6 +80,42 @@ class Synthesizer:
         inputs = [text_to_sequence(text, hparams.tts_cleaner_names) for text in texts]
         return self.synthesize_from_sequences(inputs, embeddings, return_alignments, style_idx, min_stop_token, steps)
 
+    @staticmethod
+    def load_preprocess_wav(fpath):
+        """inference.py:143-158 (host utility): load at the synthesizer rate and rescale.  The reference additionally
+        runs the third-party `logmmse` denoiser when the clip is longer than 0.4 s; it is applied here only when that
+        optional package is importable."""
+        from . import audio_host
+
+        wav = audio_host.load_wav(fpath, hparams.sample_rate)[0]
+        if hparams.rescale:
+            wav = wav / np.abs(wav).max() * hparams.rescaling_max
+        if len(wav) > hparams.sample_rate * (0.3 + 0.1):
+            try:
+                import logmmse
+
+                noise_wav = np.concatenate([wav[:int(hparams.sample_rate * 0.15)], wav[-int(hparams.sample_rate * 0.15):]])
+                wav = logmmse.denoise(wav, logmmse.profile_noise(noise_wav, hparams.sample_rate))
+            except ImportError:
+                pass
+        return wav
+
+    @staticmethod
+    def make_spectrogram(fpath_or_wav):
+        """inference.py:160-172: mel spectrogram [80, M] as fed to the synthesizer in training (GPU front-end,
+        synthesizer/audio.py)"""
+        from . import audio
+
+        wav = Synthesizer.load_preprocess_wav(fpath_or_wav) if isinstance(fpath_or_wav, (str, Path)) else fpath_or_wav
+        return audio.melspectrogram(wav, hparams).astype(np.float32)
+
+    @staticmethod
+    def griffin_lim(mel):
+        """inference.py:174-180: invert a mel spectrogram with Griffin-Lim (host, numpy/torch-CPU)"""
+        from . import audio_host
+
+        return audio_host.inv_mel_spectrogram(mel, hparams)
+
     def synthesize_from_sequences(self, inputs, embeddings, return_alignments=False, style_idx=0, min_stop_token=5,
                                   steps=2000, dropout_masks=None):
         """the part of synthesize_spectrograms after the text front-end (inference.py:104-142)"""

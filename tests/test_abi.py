@@ -166,3 +166,32 @@ def test_gan_plan_structure_on_cpu():
     assert not any(s.startswith("add x+=") for s in info32)
     assert any(s.startswith("conv resblocks.12.convs1.0 cin=16 cout=16") for s in info32)
     assert len(info32) == len(info) - 3
+
+
+def test_drop_in_surface_names_present():
+    """INTEGRATION.md's import switch: every attribute the reference's callers use on these modules / classes exists
+    (gen_voice.py:41, control/toolbox/__init__.py:215,283-344, control/mkgui/app.py:125)"""
+    import numpy as np
+
+    from mockingbird_b200.encoder import inference as enc
+    from mockingbird_b200.synthesizer.inference import Synthesizer
+    from mockingbird_b200.vocoder.fregan import inference as fre
+    from mockingbird_b200.vocoder.hifigan import inference as gan
+    from mockingbird_b200.vocoder.wavernn import inference as rnn
+
+    for name in ("load_model", "is_loaded", "embed_utterance", "embed_frames_batch", "compute_partial_slices", "preprocess_wav"):
+        assert callable(getattr(enc, name)), name
+    for name in ("synthesize_spectrograms", "load_preprocess_wav", "make_spectrogram", "griffin_lim", "is_loaded", "load"):
+        assert callable(getattr(Synthesizer, name)), name
+    assert Synthesizer.sample_rate == 16000 and hasattr(Synthesizer, "hparams")
+    for mod in (gan, fre, rnn):
+        for name in ("load_model", "is_loaded", "infer_waveform"):
+            assert callable(getattr(mod, name)), (mod.__name__, name)
+    # host utilities run without a GPU
+    wav = (np.sin(np.arange(16000) * 0.05) * 0.01).astype(np.float32)
+    out = enc.preprocess_wav(wav, source_sr=16000, trim_silence=False)
+    assert abs(10 * np.log10(np.mean(out ** 2)) - (-30)) < 1e-3       # normalised up to -30 dBFS
+    assert enc.preprocess_wav(wav, source_sr=32000, normalize=False, trim_silence=False).shape[0] == 8000
+    mel = np.random.RandomState(0).rand(80, 20).astype(np.float32) * 8 - 4
+    y = Synthesizer.griffin_lim(mel)
+    assert y.ndim == 1 and abs(len(y) - 19 * 256) <= 256 and np.isfinite(y).all()

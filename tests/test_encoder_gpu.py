@@ -69,3 +69,23 @@ def test_not_loaded_error():
             enc_inf.embed_frames_batch(np.zeros((1, 160, 40), np.float32))
     finally:
         enc_inf._model = saved
+
+
+def test_reupload_invalidates_lazily_packed_images():
+    """the whole-sequence input-projection images (packed at first use with >= 512 rows) must be re-packed
+    after .to() / a second load_state_dict"""
+    from mockingbird_b200.encoder.model import SpeakerEncoder
+
+    sd = ri.encoder_state_dict(0)
+    frames = torch.rand(8, 160, 40, generator=torch.Generator().manual_seed(3)) * 0.3
+    m = SpeakerEncoder()
+    m.load_state_dict(sd)
+    a = m.forward(frames).cpu()
+    m.to(torch.device("cuda", torch.cuda.current_device()))
+    b = m.forward(frames).cpu()
+    assert torch.equal(a, b)
+    sd2 = {k: (v * 1.25 if "weight_ih" in k else v) for k, v in sd.items()}
+    m.load_state_dict(sd2)
+    c = m.forward(frames).cpu()
+    ref = eo.embed_frames(sd2, frames)
+    assert float((c - ref).abs().max()) < TOL and not torch.equal(a, c)

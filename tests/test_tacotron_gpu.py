@@ -122,3 +122,29 @@ def test_synthesizer_surface(tmp_path, sd):
     assert all(m.shape[0] == 80 and m.shape[1] <= 6 and m.dtype == np.float32 for m in specs)
     specs2, align = s.synthesize_spectrograms(texts[:2], embeds[:2], return_alignments=True, steps=6, min_stop_token=10)
     assert len(specs2) == 2 and align.shape[0] == 2
+
+
+def test_reupload_invalidates_lazily_packed_images(sd):
+    """after one large-M generate (CBHG tensor-core images packed on first use) a re-upload - .to(device) or a
+    second load_state_dict with DIFFERENT weights - must not reuse the stale images / scales"""
+    from mockingbird_b200.synthesizer.inference import Synthesizer
+
+    g = torch.Generator().manual_seed(77)
+    B, Tc, steps = 12, 48, 64
+    chars = torch.randint(2, 75, (B, Tc), generator=g)
+    emb = torch.rand(B, 256, generator=g)
+    emb = emb / emb.norm(dim=1, keepdim=True)
+    nst = steps // 2
+    enc = (torch.rand(2, B, Tc, 256, generator=g) < 0.5)
+    dec = (torch.rand(nst, 2, B, 256, generator=g) < 0.5)
+    m = Synthesizer("unused.pt", verbose=False).load_state(sd)
+    a = m.generate(chars, emb, steps=steps, style_idx=-1, min_stop_token=10, dropout_masks=(enc, dec))[1].cpu()
+    m.to(torch.device("cuda", torch.cuda.current_device()))  # forces a fresh arena
+    b = m.generate(chars, emb, steps=steps, style_idx=-1, min_stop_token=10, dropout_masks=(enc, dec))[1].cpu()
+    assert torch.equal(a, b)
+    sd2 = {k: (v * 1.5 if k.endswith("conv.weight") and v.dtype == torch.float32 else v) for k, v in sd.items()}
+    m.load_state_dict(sd2)
+    c = m.generate(chars, emb, steps=steps, style_idx=-1, min_stop_token=10, dropout_masks=(enc, dec))[1].cpu()
+    fresh = Synthesizer("unused.pt", verbose=False).load_state(sd2)
+    d = fresh.generate(chars, emb, steps=steps, style_idx=-1, min_stop_token=10, dropout_masks=(enc, dec))[1].cpu()
+    assert torch.equal(c, d) and not torch.equal(a, c)
