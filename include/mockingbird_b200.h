@@ -53,6 +53,9 @@ uint64_t mb_launch_count(void);
 #define MB_PREC_FP32 0      /* FP32 FFMA everywhere (parity anchor, ~1e-6 of the reference)     */
 #define MB_PREC_F16TC 1     /* tcgen05 tensor cores: fp16 operands, fp32 accumulate, fp32
                                residual stream; conv_post in fp32 (tolerance 1e-3) */
+#define MB_PREC_F16X3 2     /* tcgen05 tensor cores with the 3-term fp16 split on EVERY layer
+                               (x*w = hi*hi + lo*hi + hi*lo, fp32 accumulate): FP32-equivalent results
+                               (~1e-5 of the reference) at 3x the MMA work of MB_PREC_F16TC            */
 
 typedef struct mb_gan_config {
   int32_t kind;                 /* MB_GAN_HIFIGAN | MB_GAN_FREGAN                                  */

@@ -16,8 +16,9 @@ MB_GAN_HIFIGAN = 0
 MB_GAN_FREGAN = 1
 MB_PREC_FP32 = 0
 MB_PREC_F16TC = 1
+MB_PREC_F16X3 = 2
 
-PRECISIONS = {"fp32": MB_PREC_FP32, "f16tc": MB_PREC_F16TC}
+PRECISIONS = {"fp32": MB_PREC_FP32, "f16tc": MB_PREC_F16TC, "f16x3": MB_PREC_F16X3}
 
 
 class MbError(RuntimeError):

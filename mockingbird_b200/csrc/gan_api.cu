@@ -127,7 +127,7 @@ int pad_channels(const mb_gan* h, int c) {
     const char* e = getenv("MB_GAN_PAD16");
     return e ? atoi(e) != 0 : true;
   }();
-  return (env && h->cfg.precision == MB_PREC_F16TC && c > 1 && c < 32) ? 32 : c;
+  return (env && h->cfg.precision != MB_PREC_FP32 && c > 1 && c < 32) ? 32 : c;
 }
 
 // run-time switches of the Fre-GAN lowering on the tensor-core path (A/B measurements):
@@ -266,7 +266,7 @@ int build_plan(mb_gan* h) {
         const int dstc = (cond == CA) ? CB : CA;
         Layer& cu = add_conv(h, "cond_up." + std::to_string(j), cond_ch, ch, k, 1, u, true, 1, 1.f, cond, dstc,
                              BUF_NONE, cond_rate);
-        const bool split = c.precision == MB_PREC_F16TC && j > 0 && env_flag("MB_FREGAN_SPLIT", true);
+        const bool split = c.precision != MB_PREC_FP32 && j > 0 && env_flag("MB_FREGAN_SPLIT", true);
         if (!split) cu.dst2 = S;  // x += mel  (generator.py:143-144) fused as a second destination
         cond = dstc;
         cond_ch = ch;
@@ -403,12 +403,12 @@ extern "C" {
 
 int mb_gan_create(const mb_gan_config* cfg, mb_gan** out) {
   if (!cfg || !out) return fail(MB_ERR_INVALID, "mb_gan_create: null argument");
-  if (cfg->precision != MB_PREC_FP32 && cfg->precision != MB_PREC_F16TC)
+  if (cfg->precision != MB_PREC_FP32 && cfg->precision != MB_PREC_F16TC && cfg->precision != MB_PREC_F16X3)
     return fail(MB_ERR_INVALID, "mb_gan_create: unknown precision %d", cfg->precision);
   mb_gan* h = new mb_gan();
   h->cfg = *cfg;
   int rc = build_plan(h);
-  if (rc == MB_OK && cfg->precision == MB_PREC_F16TC) {
+  if (rc == MB_OK && cfg->precision != MB_PREC_FP32) {
     std::vector<TcLayerDesc> descs;
     for (Layer& L : h->layers) {
       TcLayerDesc d{};
@@ -416,6 +416,10 @@ int mb_gan_create(const mb_gan_config* cfg, mb_gan** out) {
       // (res_output reads its source un-activated while ups reads the same buffer through leaky-relu: one fp16 plane
       //  cannot serve both, so the nearest-upsample layers stay on the FP32 kernel unless explicitly requested)
       d.force_f32 = (L.dst2 != BUF_NONE) || (L.nearest > 1 && !env_flag("MB_GAN_NEAREST_TC", false));
+      // 3-term split (FP32-equivalent operands): every layer in MB_PREC_F16X3; in MB_PREC_F16TC the serial layers nothing
+      // downstream averages out - the transposed convs `ups.*` / `cond_up.*` (MB_TC_UPS_X3=0 disables)
+      d.want_x3 = cfg->precision == MB_PREC_F16X3 ||
+                  (env_flag("MB_TC_UPS_X3", true) && (L.name.rfind("ups.", 0) == 0 || L.name.rfind("cond_up.", 0) == 0));
       d.taps = &L.taps;
       d.k = L.k;
       d.tc = &L.tc;
@@ -474,7 +478,7 @@ int mb_gan_set_weight(mb_gan* h, const char* name, const float* w, const int64_t
       cudaError_t e = launch_pack_slabs_f32(w, h->arena + L.w_off, L.cout_w, L.cin_w, L.k, L.transposed, st, L.cout, L.cin);
       if (e != cudaSuccess) return fail(MB_ERR_CUDA, "pack_slabs: %s", cudaGetErrorString(e));
       count_launch();
-      if (h->cfg.precision == MB_PREC_F16TC) {
+      if (h->cfg.precision != MB_PREC_FP32) {
         char* tcbase = (char*)h->arena + align_up(h->f32_floats * sizeof(float), 256);
         int rc = tc_pack_weights(L.tc, L.taps, h->arena + L.w_off, tcbase, st);
         if (rc != MB_OK) return rc;
@@ -503,7 +507,7 @@ int32_t mb_gan_hop(const mb_gan* h) { return h ? h->hop : 0; }
 
 size_t mb_gan_workspace_bytes(const mb_gan* h, int32_t batch, int32_t frames) {
   if (!h || batch <= 0 || frames <= 0) return 0;
-  if (h->cfg.precision == MB_PREC_F16TC) {
+  if (h->cfg.precision != MB_PREC_FP32) {
     std::vector<TcBufReq> req;
     for (size_t i = 0; i < h->buf_cr.size(); ++i) req.push_back({h->buf_cr[i]});
     return tc_workspace_bytes(req, batch, frames, h->cfg.num_mels, h->hop);
@@ -522,7 +526,7 @@ static int gan_forward_impl(mb_gan* h, const float* mel, const int32_t* lengths,
   if (workspace_bytes < need)
     return fail(MB_ERR_WORKSPACE, "mb_gan_forward: workspace %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->cfg.precision == MB_PREC_F16TC) {
+  if (h->cfg.precision != MB_PREC_FP32) {
     std::vector<TcOp> ops;
     for (const Layer& L : h->layers) {
       TcOp o{};
@@ -630,7 +634,7 @@ int mb_gan_debug_layer(mb_gan* h, int32_t i, const float* x, const float* residu
   L.mode = EPI_STORE;
   L.taps.mode = EPI_STORE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->cfg.precision == MB_PREC_F16TC) {
+  if (h->cfg.precision != MB_PREC_FP32) {
     TcOp o{};
     o.is_conv = true;
     o.taps = L.taps;

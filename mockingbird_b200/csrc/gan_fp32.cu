@@ -25,8 +25,13 @@ __device__ __forceinline__ float tload(const TRef& t, int b, int c, int l) {
 
 __device__ __forceinline__ void tstore(const TRef& t, int b, int c, int l, float v) {
   const size_t i = tref_index(t, b, c, l);
-  if (t.layout == LAYOUT_F16B) reinterpret_cast<__half*>(t.p)[i] = __float2half_rn(v);
-  else reinterpret_cast<float*>(t.p)[i] = v;
+  if (t.layout == LAYOUT_F16B) {
+    const __half h = __float2half_rn(v);
+    reinterpret_cast<__half*>(t.p)[i] = h;
+    if (t.hilo) reinterpret_cast<__half*>(t.p)[tref_index(t, b, c + (t.C >> 1), l)] = __float2half_rn(v - __half2float(h));
+  } else {
+    reinterpret_cast<float*>(t.p)[i] = v;
+  }
 }
 
 // shared epilogue of both FP32 kernels

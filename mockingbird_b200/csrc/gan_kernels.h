@@ -59,6 +59,9 @@ struct TRef {
   void* p = nullptr;
   int layout = LAYOUT_NONE;
   int C = 0, L = 0;
+  // F16B planes only: 1 = "hi/lo" operand plane of a 3-term-split consumer.  The plane has C = 2 x logical channels:
+  // channel c holds hi = fp16(v), channel c + C/2 holds lo = fp16(v - hi); writers store both, readers see 2C channels.
+  int hilo = 0;
 };
 
 __host__ __device__ inline int f16_cw(int C) { return C >= 64 ? 64 : C; }

@@ -72,7 +72,11 @@ struct TcParams {
   float* y32;
   __half* y16;
   int y_Lp;
-  int y_nchunks, y_chunk0;             // fp16 destination plane: row chunks per utterance / first chunk this launch writes
+  int y_nchunks, y_cw, y_c0;           // fp16 destination plane: row chunks per utterance, channels per row chunk, first channel
+                                       // this launch writes
+  int y_lo_c;                          // >= 0: hi/lo destination plane - lo = fp16(v - fp16(v)) goes to channel + y_lo_c
+  int x_pchunks;                       // 64-channel chunks of the INPUT plane per utterance (K-chunk c reads chunk c % x_pchunks)
+  float acc_scale;                     // accumulator -> value (1, or 1/kX3WScale for 3-term-split layers)
   float out_slope;
   int mode;
   float div;
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
           const uint32_t bytes = (uint32_t)(p.W * p.row_bytes);
           mbar_expect_tx(&a_full[a_stage], bytes);
           const int row0 = (kPadRows + wi.m0 + p.omin) & ~7;  // multiple of 8: swizzle phases line up
-          const __half* src = p.x16 + (((size_t)wi.b * p.n_cchunks + c) * p.x_Lp + (size_t)row0) * p.cw;
+          const __half* src = p.x16 + (((size_t)wi.b * p.x_pchunks + (c % p.x_pchunks)) * p.x_Lp + (size_t)row0) * p.cw;
           bulk_g2s(smem_u32(a_base + (size_t)a_stage * p.a_stage_bytes), src, bytes, &a_full[a_stage]);
           if (++a_stage == kAStages) { a_stage = 0; a_phase ^= 1; }
           for (int t = 0; t < p.ntaps[wi.r]; ++t) {
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         if (!inb) continue;
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) + bias_s[col0 + i];
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.acc_scale + bias_s[col0 + i];
         if (p.res32) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -343,22 +347,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                 make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
         }
         if (p.y16) {
+          const int rr = kPadRows + lo;
+          const int ysw = f16_swz(p.y_cw, rr);
+          const int ycw8 = p.y_cw >> 3;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            __half2 h0 = __floats2half2_rn(lrelu(v[8 * g + 0], p.out_slope), lrelu(v[8 * g + 1], p.out_slope));
-            __half2 h1 = __floats2half2_rn(lrelu(v[8 * g + 2], p.out_slope), lrelu(v[8 * g + 3], p.out_slope));
-            __half2 h2 = __floats2half2_rn(lrelu(v[8 * g + 4], p.out_slope), lrelu(v[8 * g + 5], p.out_slope));
-            __half2 h3 = __floats2half2_rn(lrelu(v[8 * g + 6], p.out_slope), lrelu(v[8 * g + 7], p.out_slope));
+            float a[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] = lrelu(v[8 * g + e], p.out_slope);
+            __half2 h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
             uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0);
-            pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2);
-            pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            const int rr = kPadRows + lo;
-            const int cc = (col0 & (ocw - 1)) + 8 * g;  // channel within the row chunk
-            const size_t i16 = (((size_t)wi.b * p.y_nchunks + p.y_chunk0 + col0 / ocw) * p.y_Lp + rr) * (size_t)(ocw >> 3) +
-                               (size_t)((cc >> 3) ^ f16_swz(ocw, rr));
+            pk.x = *reinterpret_cast<uint32_t*>(&h[0]);
+            pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
+            pk.z = *reinterpret_cast<uint32_t*>(&h[2]);
+            pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
+            const int ct = p.y_c0 + col0 + 8 * g;  // channel of the (hi) block
+            const int chunk = ct / p.y_cw, cc = ct - chunk * p.y_cw;
+            const size_t i16 = (((size_t)wi.b * p.y_nchunks + chunk) * p.y_Lp + rr) * (size_t)ycw8 + (size_t)((cc >> 3) ^ ysw);
             reinterpret_cast<uint4*>(p.y16)[i16] = pk;
+            if (p.y_lo_c >= 0) {
+              __half2 l2[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 hf = __half22float2(h[e]);
+                l2[e] = __floats2half2_rn(a[2 * e] - hf.x, a[2 * e + 1] - hf.y);
+              }
+              uint4 pl;
+              pl.x = *reinterpret_cast<uint32_t*>(&l2[0]);
+              pl.y = *reinterpret_cast<uint32_t*>(&l2[1]);
+              pl.z = *reinterpret_cast<uint32_t*>(&l2[2]);
+              pl.w = *reinterpret_cast<uint32_t*>(&l2[3]);
+              const int ctl = ct + p.y_lo_c;
+              const int chl = ctl / p.y_cw, ccl = ctl - chl * p.y_cw;
+              const size_t j16 = (((size_t)wi.b * p.y_nchunks + chl) * p.y_Lp + rr) * (size_t)ycw8 + (size_t)((ccl >> 3) ^ ysw);
+              reinterpret_cast<uint4*>(p.y16)[j16] = pl;
+            }
           }
         }
       }
@@ -395,6 +420,38 @@ __global__ void pack_w16_kernel(const float* __restrict__ w32, __half* __restric
   const size_t img = ((size_t)k * nch + c) * (size_t)Cout * cw;
   const size_t off = (size_t)co * cw + (size_t)((((cc >> 3) ^ f16_swz(cw, co)) << 3) + (cc & 7));
   dst[img + off] = __float2half_rn(w32[i]);
+}
+
+// 3-term-split layer over an internal hi/lo plane: K-chunks [hi | lo | hi] x images [hi(w) | hi(w) | lo(w)] (Cin >= 64), or for
+// Cin == 32 the single 64-channel plane chunk [hi32 | lo32] twice: images [hi(w) | hi(w)] and [lo(w) | 0].  w is pre-scaled by
+// kX3WScale (power of two; the epilogue multiplies the accumulator by its inverse) so that lo(w) is a normal fp16.
+__global__ void pack_w16_x3_kernel(const float* __restrict__ w32, __half* __restrict__ dst, int K, int Cin, int Cout, float wscale) {
+  const int nK = Cin >= 64 ? 3 * (Cin / 64) : 2;
+  const size_t n = (size_t)K * nK * Cout * 64;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cc = (int)(i & 63);
+  const int co = (int)((i >> 6) % Cout);
+  const int j = (int)((i / ((size_t)64 * Cout)) % nK);
+  const int k = (int)(i / ((size_t)64 * Cout * nK));
+  int ci, part;  // part 0: hi(w), 1: lo(w), 2: zero
+  if (Cin >= 64) {
+    const int nc = Cin / 64;
+    part = j < 2 * nc ? 0 : 1;
+    ci = (j % nc) * 64 + cc;
+  } else {
+    ci = cc & 31;
+    part = j == 0 ? 0 : (cc < 32 ? 1 : 2);
+  }
+  __half v = __float2half_rn(0.f);
+  if (part < 2) {
+    const float w = w32[((size_t)k * Cin + ci) * Cout + co] * wscale;
+    const __half hi = __float2half_rn(w);
+    v = part == 0 ? hi : __float2half_rn(w - __half2float(hi));
+  }
+  const size_t img = ((size_t)k * nK + j) * (size_t)Cout * 64;
+  const size_t off = (size_t)co * 64 + (size_t)((((cc >> 3) ^ f16_swz(64, co)) << 3) + (cc & 7));
+  dst[img + off] = v;
 }
 
 // ---- 3-term split of an fp32 layer (conv_pre) --------------------------------------------------------
@@ -459,6 +516,13 @@ int pick_kc(int Cin) {
   if (Cin % 64 == 0) return 64;
   if (Cin == 32) return 32;
   return 0;
+}
+
+// shapes the 3-term-split variant of tc_conv_kernel covers (operand rows are always 64 channels wide)
+bool x3_capable(const TapConv& t) {
+  if (t.Cout != 32 && t.Cout != 64 && t.Cout != 128 && t.Cout != 256) return false;
+  if (t.Cin != 32 && t.Cin % 64 != 0) return false;
+  return !t.act_tanh;
 }
 
 bool tc_capable(const TapConv& t) {
@@ -568,7 +632,7 @@ int tc_baseoff_mode() {
 
 size_t f16_plane_bytes(size_t B, size_t T, size_t cr) {
   // rows are padded to Lp = ceil8(L + 2*kPadRows) <= L + 2*kPadRows + 7 for at most 512 channels
-  return align_up(2 * B * T * cr + 2 * B * 512 * (2 * kPadRows + 7) + kPlaneSlack, 1024);
+  return align_up(2 * B * T * cr + 2 * B * 1024 * (2 * kPadRows + 7) + kPlaneSlack, 1024);  // pad rows of <= 1024 channels (hi/lo of 512)
 }
 size_t f32_plane_bytes(size_t B, size_t T, size_t cr) { return align_up(4 * B * T * cr + 256, 1024); }
 
@@ -611,6 +675,11 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.bar_off = sp.bar_off;
   p.x16 = reinterpret_cast<const __half*>(x16.p);
   p.x_Lp = f16_lp(x16.L);
+  p.x_pchunks = op.tc.x3 ? op.tc.x_pchunks : op.tc.n_cchunks;
+  p.acc_scale = op.tc.x3 ? 1.f / kX3WScale : 1.f;
+  if (op.tc.x3 && (!x16.hilo || x16.C != 64 * op.tc.x_pchunks))
+    return fail(MB_ERR_INVALID, "tc_conv(%s): 3-term-split layer needs a hi/lo input plane", op.name);
+  if (!op.tc.x3 && !op.tc.split3 && x16.hilo) return fail(MB_ERR_INVALID, "tc_conv(%s): plain layer fed a hi/lo plane", op.name);
   p.w16 = reinterpret_cast<const __half*>(tc_arena + op.tc.w16_off);
   p.bias = bias_override ? bias_override : op.b32;
   p.res32 = reinterpret_cast<const float*>(res32.p);
@@ -620,13 +689,16 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.y32 = reinterpret_cast<float*>(y32.p);
   p.y16 = reinterpret_cast<__half*>(y16.p);
   p.y_Lp = f16_lp(y16.L);
-  p.y_nchunks = (y16.p ? y16.C : t.Cout) / f16_cw(t.Cout);
-  p.y_chunk0 = y_c0 / f16_cw(t.Cout);
+  p.y_cw = f16_cw(y16.p ? y16.C : t.Cout);
+  p.y_nchunks = (y16.p ? y16.C : t.Cout) / p.y_cw;
+  p.y_c0 = y_c0;
+  p.y_lo_c = (y16.p && y16.hilo) ? (y16.C >> 1) : -1;
   p.out_slope = out_slope;
   p.mode = t.mode;
   p.div = t.div;
   p.lengths = lengths;
   p.len_mul_out = t.len_mul_out;
+  if (res16.p && (res16.hilo || res16.C != t.Cout)) return fail(MB_ERR_INVALID, "tc_conv(%s): fp16 residual plane must be a plain plane", op.name);
   if (y_c0 != 0 && (p.y32 || p.res32 || p.res16)) return fail(MB_ERR_INVALID, "tc_conv(%s): channel-offset launch supports the fp16 plane only", op.name);
   if (p.mode != EPI_STORE && !p.y32) return fail(MB_ERR_INVALID, "tc_conv(%s): accumulate mode without fp32 plane", op.name);
   void (*kern)(const TcParams) = nullptr;
@@ -693,9 +765,18 @@ int tc_plan_layers(std::vector<TcLayerDesc>& layers, size_t* tc_arena_bytes) {
       off += align_up((size_t)(t.Cout / 256) * d.k * 4 * tc.slab_bytes, 256);
       continue;  // use_tc stays 0: every generic decision treats the layer as an FP32-input layer
     }
-    if (d.force_f32 || !tc_capable(t)) continue;
-    tc.kc = pick_kc(t.Cin);
-    tc.n_cchunks = t.Cin / tc.kc;
+    const bool x3 = d.want_x3 && !d.force_f32 && x3_capable(t);
+    if (d.force_f32 || (!x3 && !tc_capable(t))) continue;
+    if (x3) {
+      tc.x3 = 1;
+      tc.kc = 64;
+      tc.n_cchunks = t.Cin >= 64 ? 3 * (t.Cin / 64) : 2;
+      tc.x_pchunks = t.Cin >= 64 ? 2 * (t.Cin / 64) : 1;
+    } else {
+      tc.kc = pick_kc(t.Cin);
+      tc.n_cchunks = t.Cin / tc.kc;
+      tc.x_pchunks = tc.n_cchunks;
+    }
     tc.slab_bytes = (size_t)tc.kc * t.Cout * 2;
     SmemPlan sp;
     bool ok = false;
@@ -733,6 +814,14 @@ int tc_pack_weights(const TcLayer& tc, const TapConv& taps, const float* w32_sla
     return MB_OK;
   }
   if (!tc.use_tc) return MB_OK;
+  if (tc.x3) {
+    const int K = kernel_count(taps);
+    const size_t n = (size_t)K * tc.n_cchunks * taps.Cout * 64;
+    pack_w16_x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w32_slabs, reinterpret_cast<__half*>(tc_arena + tc.w16_off), K,
+                                                                      taps.Cin, taps.Cout, kX3WScale);
+    MB_LAUNCH_CHECK("pack_w16_x3_kernel");
+    return MB_OK;
+  }
   const int K = kernel_count(taps);
   const size_t n = (size_t)K * taps.Cin * taps.Cout;
   pack_w16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
@@ -745,7 +834,7 @@ size_t tc_workspace_bytes(const std::vector<TcBufReq>& bufs, int B, int T, int n
   (void)num_mels;
   (void)hop;
   size_t total = 2048;
-  for (const TcBufReq& b : bufs) total += f16_plane_bytes(B, T, b.cr) + f32_plane_bytes(B, T, b.cr);
+  for (const TcBufReq& b : bufs) total += f16_plane_bytes(B, T, 2 * b.cr) + f32_plane_bytes(B, T, b.cr);  // 2x: hi/lo planes
   return total;
 }
 
@@ -761,7 +850,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
   char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
   for (int i = 0; i < nb; ++i) {
     p16[i] = ws;
-    ws += f16_plane_bytes(B, T, bufs[i].cr);
+    ws += f16_plane_bytes(B, T, 2 * bufs[i].cr);
     p32[i] = ws;
     ws += f32_plane_bytes(B, T, bufs[i].cr);
   }
@@ -778,8 +867,17 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
   for (const TcOp& o : ops) full_rate = std::max(full_rate, o.rate_out);
   // residual taken from the activated fp16 plane (no fp32 residual plane) in every stage but the full-rate one
   auto res16_ok = [&](const TcOp& c) {
-    return tc_res16_enabled() && c.is_conv && c.tc.use_tc && c.res >= 0 && c.res < nb && c.taps.stride == 1 &&
+    return tc_res16_enabled() && c.is_conv && c.tc.use_tc && !c.tc.x3 && c.res >= 0 && c.res < nb && c.taps.stride == 1 &&
            c.rate_out < full_rate;
+  };
+  // does a 3-term-split layer consume buffer `buf` (scanning forward from op `from` until the buffer is overwritten)?
+  auto wants_hilo = [&](int buf, int from) {
+    for (int j = from; j < n; ++j) {
+      const TcOp& c = ops[j];
+      if (c.is_conv && c.src == buf && c.tc.use_tc && c.tc.x3) return true;
+      if (c.is_conv && c.dst == buf && c.taps.mode == EPI_STORE) break;
+    }
+    return false;
   };
   // ---- pre-pass: which (c1, c2) op pairs run as ONE fused kernel (gan_tc_pair.cu)?
   //   kind 1: fp16-plane input;  kind 2: fp32-plane input (full-rate stage, residual = the pair's input)
@@ -789,6 +887,8 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
     memset(&pair_plan[i], 0, sizeof(TcPairParams));
     const TcOp& op = ops[i];
     if (!tc_fuse_enabled() || !op.is_conv || !op.tc.use_tc || !ops[i + 1].is_conv || !ops[i + 1].tc.use_tc) continue;
+    if (op.tc.x3 || ops[i + 1].tc.x3) continue;                 // 3-term-split layers run unfused (tc_conv_kernel)
+    if (wants_hilo(ops[i + 1].dst, i + 2)) continue;            // the pair kernel's epilogue writes plain planes only
     const TcOp& c2 = ops[i + 1];
     const TapConv& t1 = op.taps;
     const TapConv& t2 = c2.taps;
@@ -829,8 +929,18 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       }
       TRef d32 = make_ref(p32[map32[op.dst]], LAYOUT_F32B, op.cout, Lout);
       TRef s32 = make_ref(p32[map32[op.src]], LAYOUT_F32B, op.cout, Lout);
-      TRef d16 = need16 ? make_ref(p16[map16[op.dst]], LAYOUT_F16B, op.cout, Lout) : TRef{};
-      if (need16) plane_slope[map16[op.dst]] = slope16;
+      const bool add_hilo = need16 && wants_hilo(op.dst, i + 1);
+      TRef d16 = need16 ? make_ref(p16[map16[op.dst]], LAYOUT_F16B, op.cout * (add_hilo ? 2 : 1), Lout) : TRef{};
+      d16.hilo = add_hilo ? 1 : 0;
+      if (need16) {
+        plane_slope[map16[op.dst]] = slope16;
+        if (cur16[map16[op.dst]].C != d16.C || cur16[map16[op.dst]].L != Lout || cur16[map16[op.dst]].hilo != d16.hilo) {
+          cudaError_t ez = launch_zero_pads_f16(d16, B, st);
+          if (ez != cudaSuccess) return fail(MB_ERR_CUDA, "zero_pads: %s", cudaGetErrorString(ez));
+          count_launch();
+          cur16[map16[op.dst]] = d16;
+        }
+      }
       cudaError_t e = launch_add_inplace_f32(d32, s32, d16, slope16, B, st);
       if (e != cudaSuccess) return fail(MB_ERR_CUDA, "add kernel: %s", cudaGetErrorString(e));
       count_launch();
@@ -895,8 +1005,10 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       if (oop.taps.mode != EPI_STORE) need32 = true;
       if (need32) y32 = make_ref(p32[map32[oop.dst]], LAYOUT_F32B, oop.cout, Lout);
       if (need16) {
-        y16 = make_ref(p16[map16[oop.dst]], LAYOUT_F16B, oop.cout, Lout);
-        if (cur16[map16[oop.dst]].C != oop.cout || cur16[map16[oop.dst]].L != Lout) {
+        const bool hl = wants_hilo(oop.dst, scan_from);
+        y16 = make_ref(p16[map16[oop.dst]], LAYOUT_F16B, oop.cout * (hl ? 2 : 1), Lout);
+        y16.hilo = hl ? 1 : 0;
+        if (cur16[map16[oop.dst]].C != y16.C || cur16[map16[oop.dst]].L != Lout || cur16[map16[oop.dst]].hilo != y16.hilo) {
           cudaError_t e = launch_zero_pads_f16(y16, B, st);
           if (e != cudaSuccess) return fail(MB_ERR_CUDA, "zero_pads: %s", cudaGetErrorString(e));
           count_launch();
@@ -912,7 +1024,9 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       if (rc != MB_OK) return rc;
       y2_32 = make_ref(p32[map32[oop.dst2]], LAYOUT_F32B, oop.cout, Lout);
       if (n16) {
-        y2_16 = make_ref(p16[map16[oop.dst2]], LAYOUT_F16B, oop.cout, Lout);
+        const bool hl = wants_hilo(oop.dst2, scan_from);
+        y2_16 = make_ref(p16[map16[oop.dst2]], LAYOUT_F16B, oop.cout * (hl ? 2 : 1), Lout);
+        y2_16.hilo = hl ? 1 : 0;
         plane_slope[map16[oop.dst2]] = y2_slope;
       }
     }
@@ -953,7 +1067,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       int sidx = -1;
       const size_t need = (size_t)B * 256 * f16_lp(Lin) * 2;
       for (int j = 0; j < nb && sidx < 0; ++j)
-        if (j != map16[op.dst] && f16_plane_bytes(B, T, bufs[j].cr) >= need + kPlaneSlack) sidx = j;
+        if (j != map16[op.dst] && f16_plane_bytes(B, T, 2 * bufs[j].cr) >= need + kPlaneSlack) sidx = j;
       if (sidx < 0) return fail(MB_ERR_WORKSPACE, "tc_forward: no scratch plane for %s", op.name);
       TRef xs = make_ref(p16[sidx], LAYOUT_F16B, 256, Lin);
       if (cur16[sidx].C != 256 || cur16[sidx].L != Lin) {
@@ -978,7 +1092,10 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       }
     } else if (op.tc.use_tc) {
       if (op.src < 0 || op.src >= nb) return fail(MB_ERR_INVALID, "tc_forward: tensor-core layer %s reads an external buffer", op.name);
-      TRef x16 = make_ref(p16[map16[op.src]], LAYOUT_F16B, op.cin, Lin);
+      TRef x16 = make_ref(p16[map16[op.src]], LAYOUT_F16B, op.tc.x3 ? 64 * op.tc.x_pchunks : op.cin, Lin);
+      x16.hilo = op.tc.x3;
+      if (cur16[map16[op.src]].hilo != x16.hilo)
+        return fail(MB_ERR_INVALID, "tc_forward: %s expects a %s input plane", op.name, x16.hilo ? "hi/lo" : "plain");
       int rc = launch_tc(op, tc_arena, x16, res32, res16, res_slope, y32, y16, slope16, lengths, B, Lin, st);
       if (rc != MB_OK) return rc;
     } else {
@@ -1031,11 +1148,13 @@ int tc_debug_layer(const TcOp& op, const char* tc_arena, const float* x, const f
     return MB_OK;
   }
   // planes: x16 (activated), res32, y32
-  const size_t b_x16 = align_up((size_t)B * t.Cin * f16_lp(Lin) * 2 + kPlaneSlack, 1024);
+  const int xC = op.tc.x3 ? 64 * op.tc.x_pchunks : t.Cin;  // hi/lo plane: twice the channels
+  const size_t b_x16 = align_up((size_t)B * xC * f16_lp(Lin) * 2 + kPlaneSlack, 1024);
   const size_t b_r32 = align_up((size_t)B * t.Cout * Lout * 4, 1024);
   if (workspace_bytes < b_x16 + 2 * b_r32 + 2048) return fail(MB_ERR_WORKSPACE, "tc_debug_layer: workspace too small");
   char* ws = (char*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
-  TRef x16 = make_ref(ws, LAYOUT_F16B, t.Cin, Lin);
+  TRef x16 = make_ref(ws, LAYOUT_F16B, xC, Lin);
+  x16.hilo = op.tc.x3;
   TRef r32 = residual ? make_ref(ws + b_x16, LAYOUT_F32B, t.Cout, Lout) : TRef{};
   TRef y32 = make_ref(ws + b_x16 + b_r32, LAYOUT_F32B, t.Cout, Lout);
   MB_CUDA_CHECK(cudaMemsetAsync(ws, 0, b_x16, st));

@@ -18,12 +18,19 @@ struct TcLayer {
   int mt = 1;            // 128-row accumulator tiles per work item
   size_t slab_bytes = 0; // one (kernel index, chunk) weight image: [kc/8][Cout][8] fp16
   size_t w16_off = 0;    // byte offset of this layer's images in the tensor-core arena section
+  int x3 = 0;            // 1: FP32-equivalent 3-term fp16 split of a layer whose input is an internal "hi/lo" plane
+                         //    (TRef::hilo): K-chunks [hi | lo | hi] of the plane x weight images [hi(w) | hi(w) | lo(w)], weights
+                         //    pre-scaled by kX3WScale (a power of two) so that lo(w) stays a normal fp16; n_cchunks counts K-chunks
+  int x_pchunks = 0;     //    64-channel chunks of the input plane per utterance (x3: 2*Cin/64, or 1 when Cin == 32)
   int split3 = 0;        // 1: fp32-accurate 3-term fp16 split (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo) of a layer whose
                          //    input is the external fp32 tensor (conv_pre): K = 3*Cin padded to 256 channels
 };
 
+constexpr float kX3WScale = 256.f;
+
 struct TcLayerDesc {
   bool is_conv;
+  bool want_x3 = false;  // run the layer with the 3-term split if the tensor-core kernel covers its shape
   bool force_f32;  // layer shapes the tensor-core kernel does not cover (second destination, nearest-upsample)
   const TapConv* taps;
   int k;

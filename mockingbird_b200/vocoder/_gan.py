@@ -44,7 +44,7 @@ class GanGenerator:
 
     KIND = _lib.MB_GAN_HIFIGAN
 
-    def __init__(self, h, precision: str = "f16tc", top_k: int = 4):
+    def __init__(self, h, precision: str = "auto", top_k: int = 4):
         self.h = h
         if _cfg_get(h, "sampling_rate", 16000) == 24000 and self.KIND == _lib.MB_GAN_HIFIGAN:
             raise NotImplementedError("the 24 kHz InterpolationBlock variant (hifigan/models.py:105-117) "
@@ -71,10 +71,15 @@ class GanGenerator:
                 cfg.resblock_dilation_sizes[j][m] = int(dd)
         cfg.resblock_type = 1 if str(_cfg_get(h, "resblock")) == "1" else 2
         cfg.fregan_top_k = int(top_k)
-        if precision not in _lib.PRECISIONS:
-            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
-        cfg.precision = _lib.PRECISIONS[precision]
-        self.precision = precision
+        if precision != "auto" and precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be 'auto' or one of {sorted(_lib.PRECISIONS)}")
+        # "auto" (the drop-in default): the fast tensor-core mode (f16tc) is used only if, for THIS checkpoint, it stays within
+        # half the 1e-3 parity tolerance of the FP32-equivalent tensor-core mode (f16x3) on a probe batch; otherwise f16x3 is
+        # kept.  Decided once when the weights are uploaded (see _calibrate); `precision` then names the selected mode.
+        self.requested_precision = precision
+        self.calibration: Optional[Dict[str, float]] = None
+        self.precision = "f16tc" if precision == "auto" else precision
+        cfg.precision = _lib.PRECISIONS[self.precision]
         self._cfg = cfg
         self.num_kernels = len(rks)
         self.num_upsamples = len(rates)
@@ -124,7 +129,50 @@ class GanGenerator:
         return self
 
     # -- weights ---------------------------------------------------------------------------------
+    AUTO_TOLERANCE = 5e-4  # half the north-star's 1e-3: f16tc is selected only with a 2x margin on the probe
+
+    def _set_precision(self, precision: str) -> None:
+        """re-create the library handle for another precision (weights must be uploaded again)"""
+        L = _lib.lib()
+        if self._handle.value:
+            L.mb_gan_destroy(self._handle)
+        self.precision = precision
+        self._cfg.precision = _lib.PRECISIONS[precision]
+        self._handle = C.c_void_p()
+        _lib.check(L.mb_gan_create(C.byref(self._cfg), C.byref(self._handle)))
+        self._workspace = None
+        self._ready = False
+
+    def _calibrate(self) -> None:
+        """precision='auto': run a seeded probe batch (mel ~ U[-4, 4], the synthesizer's range; private generator, the global
+        RNG is not touched) through f16x3 and f16tc and keep f16tc only if max- and rms-relative deviation <= AUTO_TOLERANCE"""
+        dev = self._device
+        probe = (torch.rand(2, 80, 64, generator=torch.Generator().manual_seed(20260922)) * 8 - 4).to(dev)
+        self._set_precision("f16x3")
+        self._upload_weights()
+        ref = self.forward(probe).double()
+        self._set_precision("f16tc")
+        self._upload_weights()
+        got = self.forward(probe).double()
+        d = got - ref
+        scale = float(ref.abs().max())
+        rms = float(ref.pow(2).mean().sqrt())
+        max_rel = float(d.abs().max()) / scale if scale > 0 else 0.0
+        rms_rel = float(d.pow(2).mean().sqrt()) / rms if rms > 0 else 0.0
+        ok = max_rel <= self.AUTO_TOLERANCE and rms_rel <= self.AUTO_TOLERANCE
+        self.calibration = {"max_rel": max_rel, "rms_rel": rms_rel, "tolerance": self.AUTO_TOLERANCE, "selected": "f16tc" if ok else "f16x3"}
+        if not ok:
+            self._set_precision("f16x3")
+            self._upload_weights()
+
     def _upload(self):
+        if self.requested_precision == "auto":
+            self._device = self._device or _lib.require_cuda()
+            self._calibrate()
+        else:
+            self._upload_weights()
+
+    def _upload_weights(self):
         dev = self._device or _lib.require_cuda()
         self._device = dev
         L = _lib.lib()
@@ -231,7 +279,7 @@ class GanGenerator:
         cout = int(info.split("cout=")[1].split()[0])
         y = torch.zeros(B, cout, out_rows, dtype=torch.float32, device=x.device)
         cin = x.shape[1]
-        need = B * cin * (L + 96) * 2 + 2 * B * cout * out_rows * 4 + (1 << 20)
+        need = 2 * B * max(cin, 64) * (L + 96) * 2 + 2 * B * cout * out_rows * 4 + (1 << 20)  # hi/lo planes: 2x channels
         ws = torch.empty(need, dtype=torch.uint8, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         rp = C.c_void_p(residual.contiguous().data_ptr()) if residual is not None else None

@@ -22,13 +22,14 @@ from .models import DEFAULT_CONFIG as DEFAULT_CONFIG_16K, FreGAN as Generator
 generator = None  # type: Optional[Generator]
 output_sample_rate = None
 _device = None
-_precision = os.environ.get("MOCKINGBIRD_B200_GAN_PRECISION", "f16tc")
+_precision = os.environ.get("MOCKINGBIRD_B200_GAN_PRECISION", "auto")  # auto | f16tc | f16x3 | fp32 (see vocoder/_gan.py)
 
 
 def set_precision(precision: str) -> None:
-    """'f16tc' (default) or 'fp32'; takes effect at the next load_model."""
+    """'auto' (default: f16tc if a load-time probe shows it within 5e-4 of f16x3 for the checkpoint, else f16x3), 'f16tc',
+    'f16x3' or 'fp32'; takes effect at the next load_model."""
     global _precision
-    if precision not in _lib.PRECISIONS:
+    if precision != "auto" and precision not in _lib.PRECISIONS:
         raise ValueError(precision)
     _precision = precision
 

@@ -24,5 +24,5 @@ class FreGAN(GanGenerator):
 
     KIND = _lib.MB_GAN_FREGAN
 
-    def __init__(self, h, top_k: int = 4, precision: str = "f16tc"):
+    def __init__(self, h, top_k: int = 4, precision: str = "auto"):
         super().__init__(h, precision=precision, top_k=top_k)

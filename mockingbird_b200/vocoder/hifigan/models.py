@@ -24,7 +24,8 @@ DEFAULT_CONFIG_16K = {
 class Generator(GanGenerator):
     """``Generator(h)``; ``forward(mel[B,80,T]) -> wav[B,1,200*T]`` (models.py:134-150).
 
-    ``precision``: "f16tc" (tcgen05 tensor cores, fp16 operands / fp32 accumulate, <=1e-3 of the
-    reference) or "fp32" (FFMA everywhere, ~1e-6)."""
+    ``precision``: "auto" (default; picks "f16tc" when a load-time probe shows it within 5e-4 of "f16x3" for this
+    checkpoint, else "f16x3"), "f16tc" (tcgen05, fp16 operands / fp32 accumulate, 3-term split on the serial layers),
+    "f16x3" (tcgen05, 3-term fp16 split everywhere: FP32-equivalent) or "fp32" (FFMA everywhere, ~1e-6)."""
 
     KIND = _lib.MB_GAN_HIFIGAN

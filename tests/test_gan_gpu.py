@@ -4,7 +4,10 @@ surfaces) vs the CPU oracle and the committed golden vectors.
 Tolerances (BASELINE.json north_star: "within 1e-3 relative for HiFi-GAN float waveforms"):
   both  max_rel = |y - ref|_inf / |ref|_inf   and   rms_rel = rms(y - ref) / rms(ref)
   fp32  path : <= 2e-5   (FFMA, differs from the oracle only by summation order)
-  f16tc path : <= 1e-3   on the reference's own initialisation (the configs BASELINE.json names)
+  f16tc path : <= 1e-3   fp16 operands in the resblocks, 3-term split on the serial layers
+  f16x3 path : <= 1e-4   3-term fp16 split on every layer (FP32-equivalent on the tensor cores)
+  auto       : <= 1e-3   the drop-in default: f16tc when a load-time probe shows it within 5e-4 of f16x3, else f16x3
+No assertion in this file is looser than the north star's 1e-3.
 """
 import numpy as np
 import pytest
@@ -15,8 +18,8 @@ import ref_init as ri
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-5, "f16tc": 1e-3}
-PRECISIONS = ["fp32", "f16tc"]
+TOL = {"fp32": 2e-5, "f16tc": 1e-3, "f16x3": 1e-4, "auto": 1e-3}
+PRECISIONS = ["fp32", "f16tc", "f16x3"]
 
 
 def _hifigan(precision, sd=None, cfg=None):
@@ -97,10 +100,11 @@ def test_hifigan_empty_batch(sd0):
     assert g(torch.zeros(2, 80, 0).cuda()).shape == (2, 1, 0)
 
 
-@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "auto"])
 def test_hifigan_rescaled_init(precision):
-    """second, harder initialisation (activations O(1) through the stack).  The f16tc path keeps
-    rms_rel <= 1e-3; its max_rel bound is 3e-3 there (see DESIGN.md error budget)."""
+    """second, harder initialisation (activations O(1) through the stack, like a trained checkpoint).  fp16 operand
+    rounding alone does not hold 1e-3 there (2.4e-3 max), so: the FP32-equivalent tensor-core mode must,
+    and the drop-in default (`auto`) must DETECT the case at load time and select it."""
     sd = ri.rescale_variance_preserving(ri.hifigan_state_dict(ri.HIFIGAN_CONFIG_16K, 0), 1.0)
     g = _hifigan(precision, sd)
     mel = torch.rand(2, 80, 64, generator=torch.Generator().manual_seed(9)) * 8 - 4
@@ -110,7 +114,19 @@ def test_hifigan_rescaled_init(precision):
     if precision == "fp32":
         assert e["max_rel"] <= 5e-5 and e["rms_rel"] <= 2e-5, e
     else:
-        assert e["rms_rel"] <= 1e-3 and e["max_rel"] <= 3e-3, e
+        assert e["max_rel"] <= TOL[precision] and e["rms_rel"] <= TOL[precision], e
+    if precision == "auto":
+        assert g.precision == "f16x3" and g.calibration["max_rel"] > g.AUTO_TOLERANCE, g.calibration
+
+
+def test_auto_precision_selects_fast_mode_on_reference_init(sd0):
+    """on the reference's own initialisation (the BASELINE configs) the probe shows f16tc well inside the tolerance: the
+    drop-in default runs the fast mode; the global torch RNG is not consumed by the calibration"""
+    torch.manual_seed(123)
+    g = _hifigan("auto", sd0)
+    assert g.precision == "f16tc" and g.calibration["selected"] == "f16tc", g.calibration
+    assert g.calibration["max_rel"] <= g.AUTO_TOLERANCE and g.calibration["rms_rel"] <= g.AUTO_TOLERANCE
+    assert torch.equal(torch.rand(3), torch.rand(3, generator=torch.Generator().manual_seed(123)))
 
 
 def test_hifigan_resblock2_variant():
@@ -193,4 +209,4 @@ def test_fregan_vs_golden_and_oracle(golden_dir, precision):
     g.remove_weight_norm()
     wav = g(torch.from_numpy(z["mel"]).cuda()).cpu()
     e = go.rel_errors(wav, torch.from_numpy(z["wav"]))
-    assert e["max_rel"] <= TOL[precision] * (1.5 if precision == "f16tc" else 1) and e["rms_rel"] <= TOL[precision], e
+    assert e["max_rel"] <= TOL[precision] and e["rms_rel"] <= TOL[precision], e

@@ -1,5 +1,5 @@
 """The f16tc path has run-time switches for A/B measurements (MB_TC_FUSE, MB_TC_RES16, MB_TC_PAIR32,
-MB_TC_SPLIT3; read once per process).  Every combination a user can select must stay inside the 1e-3
+MB_TC_SPLIT3, MB_TC_UPS_X3; read once per process).  Every combination a user can select must stay inside the 1e-3
 tolerance: each setting runs the golden comparison in a fresh interpreter."""
 import json
 import os
@@ -43,7 +43,7 @@ out["tail"] = tail
 print(json.dumps(out))
 """
 
-ENVS = [{}, {"MB_TC_FUSE": "0"}, {"MB_TC_RES16": "0"}, {"MB_TC_PAIR32": "0"}, {"MB_TC_SPLIT3": "0"},
+ENVS = [{}, {"MB_TC_UPS_X3": "0", "MB_TC_RES16": "0"}, {"MB_TC_FUSE": "0"}, {"MB_TC_RES16": "0"}, {"MB_TC_PAIR32": "0"}, {"MB_TC_SPLIT3": "0"},
         {"MB_TC_RES16": "0", "MB_TC_PAIR32": "0", "MB_TC_FUSE": "0"}]
 
 
@@ -55,5 +55,5 @@ def test_hifigan_f16tc_switches_within_tolerance(env):
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["small"]["max_rel"] <= 1e-3 and out["small"]["rms_rel"] <= 1e-3, out
-    assert out["ragged_worst"] <= 1.5e-3, out
+    assert out["ragged_worst"] <= 1e-3, out
     assert out["tail"] == 0.0, out  # samples past an utterance's length are exactly zero
