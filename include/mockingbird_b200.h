@@ -185,6 +185,17 @@ int mb_wavernn_generate_rows(mb_wavernn* h, const int32_t* fold_starts_host, int
                              int32_t step0, int32_t nsteps, const float* noise, int32_t noise_folds, int32_t row0,
                              uint64_t seed, int16_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The float64 tail of WaveRNN.generate on the device (fatchord_version.py:236-253, :340-402; wavernn/audio.py:92-107):
+ * class indices int16 [folds, steps] (device) -> sample = 2*idx/(n_classes-1) - 1 -> equal-power cross-fade + unfold
+ * (batched) -> mu-law decode -> de-emphasis y[n] = x[n] + preemphasis*y[n-1] (0 = off) -> out[:wave_len] ->
+ * linear fade-out over the last fade_len samples.  `out` (device, float64) must hold
+ * min(wave_len, folds*(target+overlap)+overlap | steps) samples; *n_out receives that count. */
+size_t mb_wavernn_postprocess_workspace_bytes(int32_t folds, int32_t steps, int32_t batched, int32_t target, int32_t overlap);
+int mb_wavernn_postprocess(const int16_t* idx, int32_t folds, int32_t steps, int32_t batched, int32_t target,
+                           int32_t overlap, int32_t n_classes, int32_t mu_law, double preemphasis, int64_t wave_len,
+                           int32_t fade_len, double* out, int64_t* n_out, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
 /* debug/test hook: logits [folds, 512] fp32 of the LAST step executed by mb_wavernn_generate */
 int mb_wavernn_last_logits(mb_wavernn* h, float* logits, int32_t folds, void* workspace, void* stream);
 

@@ -123,6 +123,7 @@ class WaveRNN:
         self._ready = False
         self.training = True
         self.rng = "torch"
+        self.post = "device"     # "device": mb_wavernn_postprocess (float64 kernels); "host": the numpy restatement
         self.seed = 0
         self.step = torch.zeros(1).long()
 
@@ -194,6 +195,12 @@ class WaveRNN:
     # -- generate --------------------------------------------------------------------------------
     def generate_indices(self, mels: torch.Tensor, batched: bool, target: int, overlap: int, progress_callback=None,
                          noise: Optional[torch.Tensor] = None, rows: Optional[Tuple[int, int]] = None) -> np.ndarray:
+        """host copy of generate_indices_device()"""
+        out = self.generate_indices_device(mels, batched, target, overlap, progress_callback, noise, rows)
+        return out if isinstance(out, np.ndarray) else out.cpu().numpy()
+
+    def generate_indices_device(self, mels: torch.Tensor, batched: bool, target: int, overlap: int, progress_callback=None,
+                                noise: Optional[torch.Tensor] = None, rows: Optional[Tuple[int, int]] = None):
         """the device part of generate(): class indices int16 [folds, steps].  ``rows=(lo, hi)`` runs only the folds
         [lo, hi) of the utterance (fold sharding across GPUs): the noise stream is still the whole utterance's, each
         fold reads its own rows, so a fold's samples do not depend on the sharding."""
@@ -297,8 +304,7 @@ class WaveRNN:
                     left_c, next_c = C.c_int32(), C.c_int32()
                     _lib.check(L.mb_mtstream_finish(self._mt, g_state.ctypes.data, C.byref(left_c), C.byref(next_c)))
                     set_torch_cpu_generator_position(g_state, left_c.value, next_c.value)
-            idx = out.cpu().numpy()
-        return idx
+        return out
 
     def _skip_noise(self, B_all: int, steps: int) -> None:
         """advance the global generator as a full generate() would (a rank that owns no fold of the utterance)"""
@@ -328,6 +334,28 @@ class WaveRNN:
         output[-20 * self.hop_length:] *= fade_out
         return output
 
+    def postprocess_device(self, idx: torch.Tensor, frames: int, batched: bool, target: int, overlap: int, mu_law: bool) -> np.ndarray:
+        """the same tail on the device (csrc/wavernn_post.cu): int16 [folds, steps] (cuda) -> host float64 waveform"""
+        L = _lib.lib()
+        folds, steps = int(idx.shape[0]), int(idx.shape[1])
+        dev = idx.device
+        total = folds * (target + overlap) + overlap if batched else steps
+        wave_len = (frames - 1) * self.hop_length
+        fade_len = 20 * self.hop_length
+        if min(total, wave_len) < fade_len:  # the reference's `output[-fade:] *= fade_out` raises on such short outputs too
+            return self.postprocess(idx.cpu().numpy(), frames, batched, target, overlap, mu_law)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            need = int(L.mb_wavernn_postprocess_workspace_bytes(folds, steps, int(batched), target, overlap))
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            out = torch.empty(min(total, max(wave_len, 0)), dtype=torch.float64, device=dev)
+            n_out = C.c_int64()
+            _lib.check(L.mb_wavernn_postprocess(C.c_void_p(idx.data_ptr()), folds, steps, int(batched), target, overlap,
+                                                self.n_classes, int(bool(mu_law)), float(hp.preemphasis) if hp.apply_preemphasis else 0.0,
+                                                wave_len, fade_len, C.c_void_p(out.data_ptr()), C.byref(n_out), C.c_void_p(ws.data_ptr()),
+                                                ws.numel(), C.c_void_p(stream.cuda_stream)))
+            return out[: n_out.value].cpu().numpy()
+
     def generate_sharded(self, mels, target, overlap, mu_law, progress_callback=None, dst: int = 0):
         """batched generate() of ONE utterance with its folds dealt contiguously across the ranks of the default process
         group (folds are independent rows, fatchord_version.py:178-185): every rank computes the
@@ -352,9 +380,13 @@ class WaveRNN:
         mu_law = mu_law if self.mode == 'RAW' else False
         progress_callback = progress_callback or self.gen_display
         self.eval()
-        idx = self.generate_indices(mels, batched, target, overlap, progress_callback)
+        idx = self.generate_indices_device(mels, batched, target, overlap, progress_callback)
         # sample = 2 * idx.float() / (n_classes - 1.) - 1.  (float32, :226) then float64 (:238)
-        output = self.postprocess(idx, int(mels.size(-1)), batched, target, overlap, mu_law)
+        if self.post == "device" and not isinstance(idx, np.ndarray) and idx.numel() > 0:
+            output = self.postprocess_device(idx, int(mels.size(-1)), batched, target, overlap, mu_law)
+        else:
+            idx = idx if isinstance(idx, np.ndarray) else idx.cpu().numpy()
+            output = self.postprocess(idx, int(mels.size(-1)), batched, target, overlap, mu_law)
         self.train()  # side effect kept (:255)
         return output
 

@@ -129,3 +129,23 @@ def test_fold_rows_independent_of_sharding(model, rng):
         model.rng = "torch"
     assert full.shape == (7, 370) and parts[2].shape == (0, 370)
     assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_device_postprocess_matches_reference(model, gold, golden_dir):
+    """mb_wavernn_postprocess (float64 kernels: unfold + cross-fade, mu-law, parallel de-emphasis, fade) on the reference's own
+    integer samples == the reference's float64 waveform, <= 1e-12 (the host numpy path holds the same bound)"""
+    import json
+
+    w1 = model.postprocess_device(torch.from_numpy(gold["idx1"]).cuda(), 27, False, 8000, 400, True)
+    assert w1.dtype == np.float64 and w1.shape == gold["wav1"].shape and np.abs(w1 - gold["wav1"]).max() <= 1e-12
+    w2 = model.postprocess_device(torch.from_numpy(gold["idx2"]).cuda(), 30, True, 1000, 100, True)
+    assert w2.shape == gold["wav2"].shape and np.abs(w2 - gold["wav2"]).max() <= 1e-12
+    z = np.load(golden_dir / "wavernn_cfg3.npz")
+    w3 = model.postprocess_device(torch.from_numpy(z["idx"]).cuda(), 2400, True, 8000, 400, True)
+    st = int(json.loads(str(z["meta"]))["wav_stride"])
+    assert len(w3) == int(z["wav_len"])
+    assert np.abs(w3[::st] - z["wav_strided"]).max() <= 1e-12
+    assert np.abs(w3[:4096] - z["wav_head"]).max() <= 1e-12 and np.abs(w3[-8192:] - z["wav_tail"]).max() <= 1e-12
+    # and against the host restatement on every sample
+    host = model.postprocess(z["idx"], 2400, True, 8000, 400, True)
+    assert np.abs(w3 - host).max() <= 1e-13
