@@ -203,3 +203,29 @@ def build_encoder(seed: int = 0):
     m = SpeakerEncoder(torch.device("cpu"), torch.device("cpu"))
     m.eval()
     return m
+
+
+def load_deepmind():
+    """Import the UNMODIFIED models/vocoder/wavernn/models/deepmind_version.py.  As shipped it star-imports two modules
+    that do not exist in the tree (`utils.display`, `utils.dsp`) for the names time / np / stream / combine_signal, and
+    calls `.cuda()` unconditionally: provide those names through stub modules and make `.cuda()` a CPU no-op while the
+    returned class is in use (harness only; the reference file itself is untouched)."""
+    install()
+    import time as _time
+
+    import numpy as _np
+    import torch
+
+    disp = types.ModuleType("utils.display")
+    disp.time, disp.np, disp.stream = _time, _np, (lambda *a, **k: None)
+    dsp = types.ModuleType("utils.dsp")
+    dsp.combine_signal = lambda coarse, fine: coarse * 256 + fine - 2 ** 15  # wavernn/audio.py:34-35
+    dsp.np = _np
+    sys.modules["utils.display"], sys.modules["utils.dsp"] = disp, dsp
+    import utils as _u
+
+    _u.display, _u.dsp = disp, dsp
+    torch.Tensor.cuda = lambda self, *a, **k: self  # type: ignore[assignment]
+    from models.vocoder.wavernn.models.deepmind_version import WaveRNN
+
+    return WaveRNN

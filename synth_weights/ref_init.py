@@ -371,3 +371,26 @@ def encoder_state_dict(seed: int = 0) -> Dict[str, torch.Tensor]:
     sd["similarity_weight"] = torch.tensor([10.0])
     sd["similarity_bias"] = torch.tensor([-5.0])
     return sd
+
+
+# ---- DeepMind-style dual-softmax WaveRNN (models/vocoder/wavernn/models/deepmind_version.py:8-34) ----------------
+def deepmind_state_dict(seed: int = 0, bias_scale: float = 0.1) -> Dict[str, torch.Tensor]:
+    """``torch.manual_seed(seed); WaveRNN(hidden_size=896, quantisation=256)`` state_dict in the constructor's order
+    (R, O1..O4, I_coarse, I_fine, then zero gate biases).  ``bias_scale`` > 0 additionally draws the three gate biases
+    (zeros in a fresh module) from N(0, bias_scale) AFTER everything else, so that the fixtures exercise them."""
+    torch.manual_seed(seed)
+    nn = torch.nn
+    H, S, Q = 896, 448, 256
+    sd: Dict[str, torch.Tensor] = {}
+    sd["R.weight"] = nn.Linear(H, 3 * H, bias=False).weight.detach()
+    for name, (i, o) in (("O1", (S, S)), ("O2", (S, Q)), ("O3", (S, S)), ("O4", (S, Q))):
+        m = nn.Linear(i, o)
+        sd[name + ".weight"], sd[name + ".bias"] = m.weight.detach(), m.bias.detach()
+    sd["I_coarse.weight"] = nn.Linear(2, 3 * S, bias=False).weight.detach()
+    sd["I_fine.weight"] = nn.Linear(3, 3 * S, bias=False).weight.detach()
+    for b in ("bias_u", "bias_r", "bias_e"):
+        sd[b] = torch.zeros(H)
+    if bias_scale > 0:
+        for b in ("bias_u", "bias_r", "bias_e"):
+            sd[b] = torch.randn(H) * bias_scale
+    return sd

@@ -208,3 +208,41 @@ def test_melspec_oracle_stft_matches_torch_and_mel_basis_matches_transformers():
             theirs = z[key]
             assert ours.shape == theirs.shape
             assert np.abs(ours - theirs).max() < 1e-6 * max(1.0, float(np.abs(theirs).max()))
+
+
+@pytest.mark.reference
+def test_deepmind_oracle_matches_reference(golden_dir):
+    """N3: the unimportable-as-shipped deepmind_version.py runs UNMODIFIED behind the harness stubs; ref_init reproduces its
+    constructor bit for bit, the torch restatement reproduces its integer coarse / fine samples, the committed golden
+    re-generates identically"""
+    import deepmind_oracle as do
+
+    if not rh.reference_available():
+        pytest.skip("reference tree not present")
+    W = rh.load_deepmind()
+    torch.manual_seed(0)
+    m = W()
+    fresh = ri.deepmind_state_dict(0, bias_scale=0.0)
+    ref_sd = m.state_dict()
+    assert sorted(ref_sd) == sorted(fresh) and all(torch.equal(ref_sd[k], fresh[k]) for k in fresh)
+    sd = ri.deepmind_state_dict(0)
+    m.load_state_dict(sd)
+    torch.manual_seed(1234)
+    out, c, f = m.generate(600)
+    torch.manual_seed(1234)
+    out2, c2, f2 = do.generate(sd, 600)
+    assert np.array_equal(c, c2) and np.array_equal(f, f2) and np.array_equal(out, out2)
+    z = np.load(golden_dir / "deepmind_seed0.npz")
+    assert np.array_equal(z["coarse"][:600], c) and np.array_equal(z["fine"][:600], f)
+
+
+def test_deepmind_oracle_matches_golden(golden_dir):
+    """runs everywhere (no reference tree needed): the restatement reproduces the committed reference samples"""
+    import deepmind_oracle as do
+
+    z = np.load(golden_dir / "deepmind_seed0.npz")
+    sd = ri.deepmind_state_dict(0)
+    torch.manual_seed(1234)
+    out, c, f = do.generate(sd, 1000)
+    assert np.array_equal(c, z["coarse"][:1000]) and np.array_equal(f, z["fine"][:1000])
+    assert np.array_equal(out, z["output"][:1000]) and out.min() >= -2 ** 15 and out.max() < 2 ** 15
