@@ -200,6 +200,26 @@ int mb_wavernn_postprocess(const int16_t* idx, int32_t folds, int32_t steps, int
 int mb_wavernn_last_logits(mb_wavernn* h, float* logits, int32_t folds, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * DeepMind-style dual-softmax WaveRNN (csrc/deepmind.cu)
+ *   replaces  models/vocoder/wavernn/models/deepmind_version.py:75-162 (WaveRNN.generate: one unconditioned row, per sample a
+ *             coarse and a dependent fine 256-way draw) and :8-34 (the parameters, reference names: R.weight [2688,896],
+ *             O1..O4.{weight,bias}, I_coarse.weight [1344,2], I_fine.weight [1344,3], bias_u/r/e [896])
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mb_deepmind mb_deepmind;
+int mb_deepmind_create(int32_t hidden_size, int32_t quantisation, mb_deepmind** out);
+void mb_deepmind_destroy(mb_deepmind* h);
+size_t mb_deepmind_arena_bytes(const mb_deepmind* h);
+int mb_deepmind_set_arena(mb_deepmind* h, void* arena, size_t bytes);
+int mb_deepmind_set_weight(mb_deepmind* h, const char* name, const float* w, const int64_t* dims, int32_t ndim, void* stream);
+int mb_deepmind_finalize(mb_deepmind* h, void* stream);
+size_t mb_deepmind_workspace_bytes(const mb_deepmind* h);
+/* samples [step0, step0+nsteps) of one generate(seq_len = steps); step0 == 0 resets hidden state / previous outputs to zero.
+ * noise: Exp(1) draws fp32 [nsteps][2][256] (coarse then fine, the order Categorical.sample() consumes the torch generator)
+ * or NULL (built-in counter-based generator, `seed`).  coarse / fine: int16 [steps] class ids (device). */
+int mb_deepmind_generate(mb_deepmind* h, int32_t steps, int32_t step0, int32_t nsteps, const float* noise, uint64_t seed,
+                         int16_t* coarse, int16_t* fine, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Reference-identical sampling noise (mt_stream.cu)
  *   replaces  the per-step `Categorical(...).sample()` draw of fatchord_version.py:223-226, i.e. ATen's CPU
  *             `exponential_` on the global torch generator: serial MT19937, two 32-bit draws per element,
