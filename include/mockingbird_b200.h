@@ -200,6 +200,15 @@ int mb_wavernn_postprocess(const int16_t* idx, int32_t folds, int32_t steps, int
 int mb_wavernn_last_logits(mb_wavernn* h, float* logits, int32_t folds, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * monotonic alignment search (csrc/monotonic.cu)
+ *   replaces  monotonic_align/core.pyx:7-42 (maximum_path_c) + the host round trip of monotonic_align/__init__.py:6-19
+ *   values float32 [b, T_y, T_x] (device, updated in place like the reference), paths int32 [b, T_y, T_x] (device),
+ *   t_ys / t_xs int32 [b] (device): valid lengths per item.
+ * ------------------------------------------------------------------------------------------- */
+int mb_monotonic_path(float* values, int32_t* paths, const int32_t* t_ys, const int32_t* t_xs, int32_t batch, int32_t T_y,
+                      int32_t T_x, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * DeepMind-style dual-softmax WaveRNN (csrc/deepmind.cu)
  *   replaces  models/vocoder/wavernn/models/deepmind_version.py:75-162 (WaveRNN.generate: one unconditioned row, per sample a
  *             coarse and a dependent fine 256-way draw) and :8-34 (the parameters, reference names: R.weight [2688,896],

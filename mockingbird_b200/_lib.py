@@ -120,6 +120,7 @@ SIGNATURES = {
                                          C.c_double, C.c_int64, C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_size_t,
                                          C.c_void_p]),
     "mb_wavernn_last_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mb_monotonic_path": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mb_deepmind_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "mb_deepmind_destroy": (None, [C.c_void_p]),
     "mb_deepmind_arena_bytes": (C.c_size_t, [C.c_void_p]),

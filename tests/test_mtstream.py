@@ -83,7 +83,7 @@ def test_device_conversion_equals_aten():
 @pytest.mark.gpu
 def test_generate_fast_torch_rng_equals_host_replay():
     """rng='torch' (MT19937 stream in the library) == rng='torch_host' (ATen exponential_ per step): same integer
-    samples, and the global generator ends in the same state (ragged: 7 folds, last chunk partial)"""
+    samples, and the global generator ends in the same state (ragged: 8 folds, last chunk partial)"""
     import ref_init as ri
     from mockingbird_b200.vocoder.wavernn import inference as rnn_vocoder
 
@@ -96,6 +96,6 @@ def test_generate_fast_torch_rng_equals_host_replay():
         outs.append(model.generate_indices(mel, True, 300, 35, None))
         tails.append(torch.rand(5))
     model.rng = "torch"
-    assert outs[0].shape == (7, 370)
+    assert outs[0].shape == (8, 370)  # 13 frames -> 2600 samples -> 7 full folds of 335 + a remainder fold
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[1], outs[2])
     assert torch.equal(tails[0], tails[1]) and torch.equal(tails[1], tails[2])

@@ -112,7 +112,7 @@ def test_inference_module_protocol(tmp_path, sd, gold):
 
 @pytest.mark.parametrize("rng", ["torch", "device"])
 def test_fold_rows_independent_of_sharding(model, rng):
-    """the folds of one utterance are independent rows; running them as [0,3) + [3,7) (what two
+    """the folds of one utterance are independent rows; running them as [0,3) + [3,8) (what two
     GPUs would do) gives exactly the rows of the single call, and leaves the torch generator in the same state"""
     mel = torch.rand(1, 80, 13, generator=torch.Generator().manual_seed(21)) * 2 - 1
     model.rng, model.seed = rng, 31
@@ -121,13 +121,13 @@ def test_fold_rows_independent_of_sharding(model, rng):
         full = model.generate_indices(mel, True, 300, 35, None)
         tail = torch.rand(3)
         parts = []
-        for lo, hi in ((0, 3), (3, 7), (7, 7)):
+        for lo, hi in ((0, 3), (3, 8), (8, 8)):
             torch.manual_seed(55)
             parts.append(model.generate_indices(mel, True, 300, 35, None, rows=(lo, hi)))
             assert torch.equal(torch.rand(3), tail) or rng == "device"
     finally:
         model.rng = "torch"
-    assert full.shape == (7, 370) and parts[2].shape == (0, 370)
+    assert full.shape == (8, 370) and parts[2].shape == (0, 370)
     assert np.array_equal(np.concatenate(parts), full)
 
 

@@ -2,7 +2,7 @@
 import sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle")); sys.path.insert(0, str(ROOT / "synth_weights"))
 import numpy as np, torch
 import ref_init as ri
 from mockingbird_b200.vocoder.wavernn import inference as rnn_vocoder
