@@ -4,6 +4,8 @@
 // 4x4 per thread, input window and weight slabs staged through shared memory in chunks of 8
 // input channels.  Reference semantics: hifigan/models.py:35-42, :134-150;
 // fregan/generator.py:137-166.
+#include <cstdlib>
+
 #include "gan_kernels.h"
 
 namespace mb {
@@ -135,8 +137,10 @@ __global__ void __launch_bounds__(256) tapconv_f32_kernel(TapConv p, TapConvIO i
   }
 }
 
-// Cout == 1 (conv_post): weights [taps][Cin] in shared memory; a thread produces 4 consecutive output
-// rows so that every input row it loads is reused by up to 4 outputs.
+// Cout == 1 (conv_post): weights [taps][Cin] in shared memory; a thread produces R consecutive output rows.  R = 1: every
+// load of a warp is 32 consecutive 16-byte quads (fully coalesced; the k-fold re-reads of a row by neighbouring threads are L1
+// hits); R = 4 (round 1): fewer L1 reads but a 64-byte lane stride.  Per-output accumulation order is the same for every R.
+template <int R>
 __global__ void __launch_bounds__(256) tapconv_cout1_kernel(TapConv p, TapConvIO io, const float* __restrict__ w,
                                                             const float* __restrict__ bias) {
   extern __shared__ float wsm[];  // [ntaps][Cin]
@@ -147,12 +151,14 @@ __global__ void __launch_bounds__(256) tapconv_cout1_kernel(TapConv p, TapConvIO
     wsm[i] = w[((size_t)p.slab[0][t] * p.Cin + ci) * p.Cout];
   }
   __syncthreads();
-  const int l0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int l0 = (blockIdx.x * blockDim.x + threadIdx.x) * R;
   if (l0 >= p.Lin) return;
   const int valid_in = p.lengths ? min(p.Lin, p.lengths[b] * p.len_mul_in) : p.Lin;
   const int valid_out = p.lengths ? min(p.Lout, p.lengths[b] * p.len_mul_out) : p.Lout;
   const float in_slope = (io.x.layout == LAYOUT_F16B) ? 1.f : p.in_slope;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) acc[i] = 0.f;
   // contiguous tap offsets off[t] = t - pad (dilation 1) let us walk input rows once
   const int o0 = p.off[0][0];
   bool contiguous = true;
@@ -161,13 +167,13 @@ __global__ void __launch_bounds__(256) tapconv_cout1_kernel(TapConv p, TapConvIO
     const float4* xp = reinterpret_cast<const float4*>(io.x.p);
     for (int c4 = 0; c4 < (p.Cin >> 2); ++c4) {
       const float4* run = xp + ((size_t)b * (p.Cin >> 2) + c4) * p.Lin;
-      for (int j = 0; j < nt + 3; ++j) {   // input row l0 + o0 + j feeds output i with tap t = j - i
+      for (int j = 0; j < nt + R - 1; ++j) {   // input row l0 + o0 + j feeds output i with tap t = j - i
         const int li = l0 + o0 + j;
         if (li < 0 || li >= valid_in) continue;
         float4 v = run[li];
         v.x = lrelu(v.x, in_slope); v.y = lrelu(v.y, in_slope); v.z = lrelu(v.z, in_slope); v.w = lrelu(v.w, in_slope);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < R; ++i) {
           const int t = j - i;
           if (t < 0 || t >= nt) continue;
           const float* wt = &wsm[t * p.Cin + c4 * 4];
@@ -181,13 +187,13 @@ __global__ void __launch_bounds__(256) tapconv_cout1_kernel(TapConv p, TapConvIO
   } else {
     for (int ci = 0; ci < p.Cin; ++ci)
       for (int t = 0; t < nt; ++t)
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < R; ++i) {
           const int li = l0 + i + p.off[0][t];
           if (li < 0 || li >= valid_in) continue;
           acc[i] = fmaf(wsm[t * p.Cin + ci], lrelu(tload(io.x, b, ci, li), in_slope), acc[i]);
         }
   }
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < R; ++i)
     if (l0 + i < p.Lin) epilogue_store(p, io, b, 0, l0 + i, valid_out, acc[i] + (bias ? bias[0] : 0.f));
 }
 
@@ -274,9 +280,16 @@ cudaError_t launch_tapconv_f32(const TapConv& p, const TapConvIO& io, const floa
 cudaError_t launch_tapconv_cout1_f32(const TapConv& p, const TapConvIO& io, const float* w, const float* bias,
                                      cudaStream_t stream) {
   if (p.Cout != 1 || p.stride != 1) return cudaErrorInvalidValue;
-  dim3 grid((p.Lin + 1023) / 1024, p.B);
+  static const int rows = [] {
+    const char* e = getenv("MB_POST_ROWS");  // A/B switch: 1 (default), 2 or 4 output rows per thread
+    const int r = e ? atoi(e) : 1;
+    return (r == 2 || r == 4) ? r : 1;
+  }();
+  dim3 grid((p.Lin + 256 * rows - 1) / (256 * rows), p.B);
   const size_t smem = sizeof(float) * p.ntaps[0] * p.Cin;
-  tapconv_cout1_kernel<<<grid, 256, smem, stream>>>(p, io, w, bias);
+  if (rows == 4) tapconv_cout1_kernel<4><<<grid, 256, smem, stream>>>(p, io, w, bias);
+  else if (rows == 2) tapconv_cout1_kernel<2><<<grid, 256, smem, stream>>>(p, io, w, bias);
+  else tapconv_cout1_kernel<1><<<grid, 256, smem, stream>>>(p, io, w, bias);
   return cudaGetLastError();
 }
 

@@ -888,7 +888,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
     const TcOp& op = ops[i];
     if (!tc_fuse_enabled() || !op.is_conv || !op.tc.use_tc || !ops[i + 1].is_conv || !ops[i + 1].tc.use_tc) continue;
     if (op.tc.x3 || ops[i + 1].tc.x3) continue;                 // 3-term-split layers run unfused (tc_conv_kernel)
-    if (wants_hilo(ops[i + 1].dst, i + 2)) continue;            // the pair kernel's epilogue writes plain planes only
+    if (wants_hilo(ops[i + 1].dst, i + 2) && op.cout != 64) continue;  // the pair kernel writes hi/lo planes for C = 64 only
     const TcOp& c2 = ops[i + 1];
     const TapConv& t1 = op.taps;
     const TapConv& t2 = c2.taps;
@@ -1049,6 +1049,8 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
       pp.y32 = reinterpret_cast<float*>(y32.p);
       pp.y16 = reinterpret_cast<__half*>(y16.p);
       pp.y_Lp = f16_lp(Lout);
+      pp.y_hilo = y16.hilo;
+      if (y16.hilo && c2.cout != 64) return fail(MB_ERR_INVALID, "tc_pair(%s): hi/lo output needs C = 64", c2.name);
       pp.out_slope = slope16;
       pp.mode = c2.taps.mode;
       pp.div = c2.taps.div;

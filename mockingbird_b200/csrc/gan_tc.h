@@ -90,6 +90,7 @@ struct TcPairParams {
   float* y32;
   __half* y16;
   int y_Lp;
+  int y_hilo;                // 1: y16 is a hi/lo plane (C == 64 only: chunk 0 = hi, chunk 1 = lo = fp16(v - hi))
   float out_slope;
   int mode;
   float div;

@@ -406,8 +406,23 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
             pk.z = *reinterpret_cast<uint32_t*>(&h2);
             pk.w = *reinterpret_cast<uint32_t*>(&h3);
             const int cc = (col0 >> 3) + g;
-            const size_t i16 = ((size_t)b * p.y_Lp + rr) * (size_t)(OCW >> 3) + (size_t)(cc ^ sw);
+            // plain plane: one row chunk per utterance; hi/lo plane (N == 64 only): chunk 0 = hi, chunk 1 = lo
+            const size_t cstride = (size_t)p.y_Lp * (size_t)(OCW >> 3);
+            const size_t i16 = (size_t)b * (p.y_hilo ? 2 : 1) * cstride + (size_t)rr * (size_t)(OCW >> 3) + (size_t)(cc ^ sw);
             reinterpret_cast<uint4*>(p.y16)[i16] = pk;
+            if (p.y_hilo) {
+              const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+              __half2 l0 = __floats2half2_rn(lrelu(v[8 * g + 0], p.out_slope) - f0.x, lrelu(v[8 * g + 1], p.out_slope) - f0.y);
+              __half2 l1 = __floats2half2_rn(lrelu(v[8 * g + 2], p.out_slope) - f1.x, lrelu(v[8 * g + 3], p.out_slope) - f1.y);
+              __half2 l2 = __floats2half2_rn(lrelu(v[8 * g + 4], p.out_slope) - f2.x, lrelu(v[8 * g + 5], p.out_slope) - f2.y);
+              __half2 l3 = __floats2half2_rn(lrelu(v[8 * g + 6], p.out_slope) - f3.x, lrelu(v[8 * g + 7], p.out_slope) - f3.y);
+              uint4 pl;
+              pl.x = *reinterpret_cast<uint32_t*>(&l0);
+              pl.y = *reinterpret_cast<uint32_t*>(&l1);
+              pl.z = *reinterpret_cast<uint32_t*>(&l2);
+              pl.w = *reinterpret_cast<uint32_t*>(&l3);
+              reinterpret_cast<uint4*>(p.y16)[i16 + cstride] = pl;
+            }
           }
         }
       }
