@@ -875,7 +875,7 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
     for (int j = from; j < n; ++j) {
       const TcOp& c = ops[j];
       if (c.is_conv && c.src == buf && c.tc.use_tc && c.tc.x3) return true;
-      if (c.is_conv && c.dst == buf && c.taps.mode == EPI_STORE) break;
+      if (c.is_conv && c.dst == buf) break;  // the next writer (store or accumulate) produces the plane its own consumers need
     }
     return false;
   };

@@ -2,6 +2,8 @@
 // Bit-compatible with std::mt19937 / at::mt19937 (aten/src/ATen/core/MT19937RNGEngine.h): same recurrence, same tempering.
 #include "mt19937_host.h"
 
+#include <cstring>
+
 namespace mb {
 namespace {
 constexpr int kN = 624, kM = 397;
@@ -40,7 +42,7 @@ __attribute__((target_clones("avx512f", "avx2", "default"))) void mt_temper(cons
 
 }  // namespace
 
-void mt_fill(MtPos& g, uint32_t* out, size_t n) {
+void mt_fill(MtPos& g, uint32_t* out, size_t n, bool temper) {
   while (n > 0) {
     if (g.avail == 0) {
       mt_twist(g.s);
@@ -48,7 +50,8 @@ void mt_fill(MtPos& g, uint32_t* out, size_t n) {
       g.avail = kN;
     }
     const int m = (size_t)g.avail < n ? g.avail : (int)n;
-    mt_temper(g.s + g.idx, out, m);
+    if (temper) mt_temper(g.s + g.idx, out, m);
+    else memcpy(out, g.s + g.idx, sizeof(uint32_t) * (size_t)m);
     g.idx += m;
     g.avail -= m;
     out += m;

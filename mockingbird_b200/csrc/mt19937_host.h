@@ -11,7 +11,8 @@ struct MtPos {
   int avail;  // outputs left in the current block (at::mt19937: left_ - 1)
 };
 
-// n tempered 32-bit outputs continuing from g (g is advanced)
-void mt_fill(MtPos& g, uint32_t* out, size_t n);
+// n 32-bit outputs continuing from g (g is advanced).  temper = false stores the UNTEMPERED state words (the caller applies
+// the tempering - mt_stream.cu does it on the device, which halves the host work per draw)
+void mt_fill(MtPos& g, uint32_t* out, size_t n, bool temper = true);
 
 }  // namespace mb

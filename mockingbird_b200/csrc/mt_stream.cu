@@ -8,7 +8,8 @@
 //
 // This component reproduces that stream bit for bit without the host bottleneck:
 //   * a host worker thread runs MT19937 from the generator's exact state (624 words + position) with a
-//     vectorisable block twist / tempering (~1.5-3 G draws/s) into a ring of pinned host buffers,
+//     vectorisable block twist (AVX2 / AVX-512 clones) and ships the UNTEMPERED state words into a ring of pinned host buffers
+//     (the tempering is elementwise and moves to the device: half the host work per draw),
 //   * each chunk's raw draws are copied H2D on a side stream and converted on the device
 //     (mt_to_exp_kernel: the same double-precision formula) into the fp32 noise tensor the sample kernel
 //     consumes, overlapped with the sample kernel of the previous chunk,
@@ -34,10 +35,24 @@ using mb::mt_fill;
 
 // raw draws (hi, lo) -> q = (float)(-log1p(-u)), u = ((hi<<32|lo) & (2^53-1)) * 2^-53   (ATen: uniform_real_distribution<double>
 // + transformation::exponential, aten/src/ATen/core/TransformationHelper.h, CPU branch)
+__device__ __forceinline__ uint32_t mt_temper_dev(uint32_t y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+
+// TEMPER: the host sent untempered MT19937 state words (mb_mtstream path); otherwise finished 32-bit outputs
+template <bool TEMPER>
 __global__ void mt_to_exp_kernel(const uint2* __restrict__ raw, float* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint2 r = raw[i];
+  uint2 r = raw[i];
+  if (TEMPER) {
+    r.x = mt_temper_dev(r.x);
+    r.y = mt_temper_dev(r.y);
+  }
   const unsigned long long r64 = ((unsigned long long)r.x << 32) | (unsigned long long)r.y;
   const double u = (double)(r64 & ((1ULL << 53) - 1ULL)) * 1.1102230246251565e-16;  // 2^-53
   out[i] = (float)(-log1p(-u));
@@ -83,7 +98,7 @@ void worker_main(mb_mtstream* ms) {
     }
     const uint64_t done = c * ms->words_per_chunk;
     const uint64_t n = ms->total_words - done < ms->words_per_chunk ? ms->total_words - done : ms->words_per_chunk;
-    mt_fill(ms->gen, ms->slots[slot], (size_t)n);
+    mt_fill(ms->gen, ms->slots[slot], (size_t)n, /*temper=*/false);  // tempering happens in mt_to_exp_kernel<true>
     {
       std::lock_guard<std::mutex> lk(ms->mu);
       ms->produced = c + 1;
@@ -195,8 +210,8 @@ int mb_mtstream_next(mb_mtstream* ms, uint64_t n_elems, void* dev_raw, float* de
   MB_CUDA_CHECK(cudaMemcpyAsync(dev_raw, ms->slots[slot], words * 4, cudaMemcpyHostToDevice, ms->side));
   MB_CUDA_CHECK(cudaEventRecord(ms->copied[slot], ms->side));
   ms->copy_pending[slot] = 1;
-  mt_to_exp_kernel<<<(unsigned)((n_elems + 255) / 256), 256, 0, ms->side>>>(reinterpret_cast<const uint2*>(dev_raw), dev_noise,
-                                                                            (size_t)n_elems);
+  mt_to_exp_kernel<true><<<(unsigned)((n_elems + 255) / 256), 256, 0, ms->side>>>(reinterpret_cast<const uint2*>(dev_raw), dev_noise,
+                                                                                  (size_t)n_elems);
   MB_LAUNCH_CHECK("mt_to_exp_kernel");
   MB_CUDA_CHECK(cudaEventRecord(ms->ready[par], ms->side));
   MB_CUDA_CHECK(cudaStreamWaitEvent(st, ms->ready[par], 0));
@@ -253,8 +268,8 @@ int mb_mt19937_fill(uint32_t* state624, int32_t* left, int32_t* next, uint32_t* 
 int mb_mt_to_exp(const void* dev_raw, float* dev_noise, uint64_t n_elems, void* stream) {
   if (!dev_raw || !dev_noise) return mb::fail(MB_ERR_INVALID, "mb_mt_to_exp: null argument");
   if (n_elems == 0) return MB_OK;
-  mt_to_exp_kernel<<<(unsigned)((n_elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(dev_raw),
-                                                                                       dev_noise, (size_t)n_elems);
+  mt_to_exp_kernel<false><<<(unsigned)((n_elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint2*>(dev_raw),
+                                                                                              dev_noise, (size_t)n_elems);
   MB_LAUNCH_CHECK("mt_to_exp_kernel");
   return MB_OK;
 }

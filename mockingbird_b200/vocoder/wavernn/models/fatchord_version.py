@@ -337,6 +337,7 @@ class WaveRNN:
     def postprocess_device(self, idx: torch.Tensor, frames: int, batched: bool, target: int, overlap: int, mu_law: bool) -> np.ndarray:
         """the same tail on the device (csrc/wavernn_post.cu): int16 [folds, steps] (cuda) -> host float64 waveform"""
         L = _lib.lib()
+        idx = idx.to(torch.int16).contiguous()  # row-major [folds, steps] (a numpy view may arrive transposed)
         folds, steps = int(idx.shape[0]), int(idx.shape[1])
         dev = idx.device
         total = folds * (target + overlap) + overlap if batched else steps

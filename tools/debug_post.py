@@ -8,7 +8,7 @@ import wavernn_oracle as wo
 from mockingbird_b200 import _lib
 z = np.load(ROOT / "tests/golden/wavernn_seed0.npz"); idx = z["idx2"]; folds, steps = idx.shape; target, overlap = 1000, 100
 L = _lib.lib()
-d_idx = torch.from_numpy(idx).cuda()
+d_idx = torch.from_numpy(np.ascontiguousarray(idx)).cuda()
 total = folds * (target + overlap) + overlap
 def run(mu, pre, fade_len, wave_len):
     ws = torch.empty(int(L.mb_wavernn_postprocess_workspace_bytes(folds, steps, 1, target, overlap)), dtype=torch.uint8, device="cuda")
