@@ -13,8 +13,18 @@
  *   - all tensor arguments are caller-owned DEVICE pointers unless the name ends in _host.
  *   - no hidden device allocation after *_create: packed weights live in a caller-provided arena
  *     (mb_*_arena_bytes), temporaries in a caller-provided workspace (mb_*_workspace_bytes).
+ *     Derived weight images are (re)packed inside that arena at finalize, or - for the large-M GEMMs of the Tacotron CBHG
+ *     stacks and the encoder's input projections - at the first use of a layer after any set_arena / set_weight (no
+ *     cudaMalloc: the packers' scratch is a slot of the arena).  Exceptions, allocated at create: mb_tacotron owns one
+ *     stream and two events, mb_mtstream its pinned host ring, a side stream and events.
  *   - every launch goes to the cudaStream_t passed as `stream` (void* here so that the header
  *     needs no CUDA include); functions are asynchronous with respect to the host unless stated.
+ *   - multi-GPU: the library links no communication library and has no global state.  The packed arena of every model
+ *     is ONE contiguous device buffer precisely so that the host layer can ship it with a single collective of whatever
+ *     it already uses - torch.distributed.broadcast(model.packed_arena(), src=0) over NCCL/NVLink in this repo
+ *     (SURVEY.md 8b listed an `mb_nccl_broadcast_weights` entry point; it would only wrap that one call and force an NCCL
+ *     link dependency on single-GPU users, so the contract is: arena = broadcast unit, collective = the host's).  Every
+ *     rank still loads the checkpoint itself (host-side pack scales are per handle), see INTEGRATION.md section 4.
  */
 #ifndef MOCKINGBIRD_B200_H
 #define MOCKINGBIRD_B200_H
