@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="hifigan_cfg2", choices=WORKLOADS)
-    ap.add_argument("--precision", default=os.environ.get("MOCKINGBIRD_B200_GAN_PRECISION", "f16tc"))
+    ap.add_argument("--precision", default=os.environ.get("MOCKINGBIRD_B200_GAN_PRECISION", "auto"),
+                    help="auto (drop-in default: load-time calibration picks f16tc or f16x3) | f16tc | f16x3 | fp32")
     ap.add_argument("--soak-seconds", type=float, default=2.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="headline workload only")
@@ -151,6 +152,7 @@ def measure_hifigan(ctx: Ctx, args, workload: str, precision: str, steps: int, w
     if world > 1:
         dist.broadcast(g.packed_arena(), src=0)         # rank 0's packed weights over NCCL (the only collective)
     hop = g.hop
+    requested, precision = precision, g.precision  # "auto" resolves at load time (vocoder/_gan.py: _calibrate)
     mel = (torch.rand(B, 80, T, generator=torch.Generator().manual_seed(2 + rank)) * 8 - 4)
     mel_dev = mel.to(dev)
     mels_np = [mel[i].numpy() for i in range(B)]
@@ -253,7 +255,8 @@ def measure_hifigan(ctx: Ctx, args, workload: str, precision: str, steps: int, w
         "rtf": (ms_step * 1e-3) / (samples_per_step / 16000.0), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {"workload": f"{workload}: Generator fwd, batch 32 x 256 frames x 80 mels per GPU",
-                   "per_gpu_batch": B, "frames": T, "precision": precision, "parallelism": f"dp{world}",
+                   "per_gpu_batch": B, "frames": T, "precision": precision, "precision_requested": requested,
+                   "precision_calibration": g.calibration, "parallelism": f"dp{world}",
                    "l2": "per-step working set (2.9 GB of activations) >> 126 MB L2; no explicit flush",
                    "weights": "random init, torch.manual_seed(0) order of the reference constructor"},
         "burst": {"value": world * samples_per_step / (ms_burst * 1e-3), "ms_per_step": ms_burst, "clocks": r["clocks_burst"]},
