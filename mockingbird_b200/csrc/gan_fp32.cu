@@ -281,8 +281,8 @@ cudaError_t launch_tapconv_cout1_f32(const TapConv& p, const TapConvIO& io, cons
                                      cudaStream_t stream) {
   if (p.Cout != 1 || p.stride != 1) return cudaErrorInvalidValue;
   static const int rows = [] {
-    const char* e = getenv("MB_POST_ROWS");  // A/B switch: 1 (default), 2 or 4 output rows per thread
-    const int r = e ? atoi(e) : 1;
+    const char* e = getenv("MB_POST_ROWS");  // A/B switch: 1, 2 (default: measured fastest, 0.099 vs 0.127 / 0.122 ms) or 4 output rows per thread
+    const int r = e ? atoi(e) : 2;
     return (r == 2 || r == 4) ? r : 1;
   }();
   dim3 grid((p.Lin + 256 * rows - 1) / (256 * rows), p.B);
