@@ -328,6 +328,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sample_loop(const LoopParams p)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    // built-in generator: the same 512 values, one per thread, computed here instead of inside the sampling phase
+    if (!p.noise && cta < p.B && tid < NCLS) qsm[tid] = mb_exp1_noise(p.seed, (uint32_t)gstep, (uint32_t)(p.row0 + cta), (uint32_t)tid);
 
     // ================= phase A: rnn1 =================
     for (int rb = 0; rb < nrb; ++rb) {
@@ -559,8 +561,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_sample_loop(const LoopParams p)
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
           const int cls = lane + 32 * jj;
-          const float q = p.noise ? (row == cta ? qsm[cls] : p.noise[((size_t)i * p.noise_B + (size_t)(p.row0 + row)) * NCLS + cls])
-                                  : mb_exp1_noise(p.seed, (uint32_t)gstep, (uint32_t)(p.row0 + row), (uint32_t)cls);
+          const float q = (row == cta) ? qsm[cls]
+                          : (p.noise ? p.noise[((size_t)i * p.noise_B + (size_t)(p.row0 + row)) * NCLS + cls]
+                                     : mb_exp1_noise(p.seed, (uint32_t)gstep, (uint32_t)(p.row0 + row), (uint32_t)cls));
           const float v = (e[jj] / S2) / q;
           if (v > bestv) {  // ascending class order within the lane: first maximum wins
             bestv = v;
