@@ -1,4 +1,5 @@
-"""Minimal driver for ncu: N forwards of the cfg-2 HiFi-GAN batch (default 2)."""
+"""Minimal driver for ncu: N forwards of the cfg-2 HiFi-GAN batch (default 2) inside a cudaProfilerStart/Stop range
+(run ncu with --profile-from-start off so that weight packing and the warm-up forward are not captured)."""
 import sys
 from pathlib import Path
 
@@ -19,6 +20,10 @@ g.load_state_dict(ri.hifigan_state_dict(cfg, 0))
 g.eval()
 g.remove_weight_norm()
 mel = (torch.rand(32, 80, 256, generator=torch.Generator().manual_seed(2)) * 8 - 4).cuda()
+g(mel)  # warm-up (outside the profiled range)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()  # ncu --profile-from-start off: only the forwards below are captured
 for _ in range(n):
     g(mel)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
