@@ -144,12 +144,13 @@ def infer_waveforms(mels: Sequence[np.ndarray], batch_size: int = 32) -> List[np
         wav = generator(dev, lengths=lens.to(_device))
         host_out[o_out:o_out + len(idx) * tmax * hop].view(len(idx), 1, tmax * hop).copy_(wav, non_blocking=True)
     torch.cuda.current_stream(_device).synchronize()
+    block = np.array(host_out[:n_out].numpy(), copy=True)  # ONE copy out of the reused pinned staging; results are views of it
     for idx, tmax, o_in, o_out in batches:
         if tmax == 0:
             for i in idx:
                 out[i] = np.zeros(0, np.float32)
             continue
-        wav = host_out[o_out:o_out + len(idx) * tmax * hop].view(len(idx), tmax * hop).numpy()
+        wav = block[o_out:o_out + len(idx) * tmax * hop].reshape(len(idx), tmax * hop)
         for r, i in enumerate(idx):
-            out[i] = wav[r, : mels[i].shape[1] * hop].copy()
+            out[i] = wav[r, : mels[i].shape[1] * hop]
     return out  # type: ignore[return-value]
