@@ -5,7 +5,7 @@ Run in the build container only (needs /root/reference):
     CUDA_VISIBLE_DEVICES="" python oracle/make_golden.py
 
 Every fixture stores the seeds, torch version and CPU capability it was made with (SURVEY.md
-appendix C item 6).  Weights are never stored: tests rebuild them with oracle/ref_init.py, which
+appendix C item 6).  Weights are never stored: tests rebuild them with synth_weights/ref_init.py, which
 tests/test_oracle_pinned.py proves bit-identical to the reference constructors.
 """
 from __future__ import annotations

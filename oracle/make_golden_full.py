@@ -12,7 +12,7 @@
          4 full rows of mel / postnet / attention + float64 row sums of every row
   fregan FreGAN.forward on the cfg-2 shape (mel rand(32,80,256;seed 2)*8-4), rows 0 and 31
 
-SURVEY.md section 8(d) names these inputs.  Weights: oracle/ref_init.py seeded state dicts (pinned
+SURVEY.md section 8(d) names these inputs.  Weights: synth_weights/ref_init.py seeded state dicts (pinned
 bit-identical to the reference constructors by tests/test_oracle_pinned.py).
 """
 from __future__ import annotations
