@@ -213,7 +213,7 @@ def measure_hifigan(ctx: Ctx, args, workload: str, precision: str, steps: int, w
             fam_bytes = sum(acc[k][2] for k in fam) / reps
             fam_launches = sum(acc[k][3] for k in fam) / reps
             traffic = None
-            tj = ROOT / "profiles" / "r01_hifigan_dram_traffic.json"
+            tj = ROOT / "profiles" / "r02_hifigan_dram_traffic.json"
             if tj.exists() and not fre and precision == "f16tc":
                 traffic = json.loads(tj.read_text())["tc_dram_bytes_per_launch"]
             gbs = fam_bytes / (fam_ms * 1e-3) / 1e9
