@@ -148,3 +148,23 @@ def test_reupload_invalidates_lazily_packed_images(sd):
     fresh = Synthesizer("unused.pt", verbose=False).load_state(sd2)
     d = fresh.generate(chars, emb, steps=steps, style_idx=-1, min_stop_token=10, dropout_masks=(enc, dec))[1].cpu()
     assert torch.equal(c, d) and not torch.equal(a, c)
+
+
+def test_batch_128_rows(sd, model):
+    """B = 128 (the full 128-row tensor-core tile; the cfg-5 pipeline batches 128 utterances per generate): same tolerance vs
+    the oracle on a short run"""
+    g = torch.Generator().manual_seed(4242)
+    B, Tc, steps = 128, 24, 12
+    chars = torch.randint(2, 75, (B, Tc), generator=g)
+    for b in range(0, B, 3):
+        chars[b, 8 + (b % 11):] = 0
+    emb = torch.rand(B, 256, generator=g)
+    emb = emb / emb.norm(dim=1, keepdim=True)
+    nst = steps // 2
+    enc = (torch.rand(2, B, Tc, 256, generator=g) < 0.5)
+    dec = (torch.rand(nst, 2, B, 256, generator=g) < 0.5)
+    masks = [enc[0], enc[1]] + [dec[i, j] for i in range(nst) for j in range(2)]
+    mel_r, lin_r, attn_r = to.generate(sd, chars, emb, steps, -1, 10, masks, r=2)
+    mel, lin, attn = model.generate(chars, emb, steps=steps, style_idx=-1, min_stop_token=10, dropout_masks=(enc, dec))
+    assert mel.shape == mel_r.shape == (B, 80, steps)
+    assert _rel(mel.cpu(), mel_r) <= TOL and _rel(lin.cpu(), lin_r) <= TOL and _rel(attn.cpu(), attn_r) <= TOL
