@@ -415,11 +415,16 @@ int mb_gan_create(const mb_gan_config* cfg, mb_gan** out) {
       d.is_conv = (L.kind == OP_CONV);
       // (res_output reads its source un-activated while ups reads the same buffer through leaky-relu: one fp16 plane
       //  cannot serve both, so the nearest-upsample layers stay on the FP32 kernel unless explicitly requested)
-      d.force_f32 = (L.dst2 != BUF_NONE) || (L.nearest > 1 && !env_flag("MB_GAN_NEAREST_TC", false));
+      // Fre-GAN res_output: the first one reads S, which `ups` reads through leaky-relu (one fp16 plane cannot serve both): FP32
+      // kernel.  The later ones read the running `output` buffer, which nothing else consumes: they run on the tensor cores with
+      // the 3-term split over an un-activated hi/lo plane written by the preceding "output += x" op (MB_GAN_NEAREST_TC=0: FP32).
+      const bool nearest_f32 = L.nearest > 1 && (L.name.rfind("res_output.0.", 0) == 0 || !env_flag("MB_GAN_NEAREST_TC", true));
+      d.force_f32 = (L.dst2 != BUF_NONE) || nearest_f32;
       // 3-term split (FP32-equivalent operands): every layer in MB_PREC_F16X3; in MB_PREC_F16TC the serial layers nothing
       // downstream averages out - the transposed convs `ups.*` / `cond_up.*` (MB_TC_UPS_X3=0 disables)
       d.want_x3 = cfg->precision == MB_PREC_F16X3 ||
-                  (env_flag("MB_TC_UPS_X3", true) && (L.name.rfind("ups.", 0) == 0 || L.name.rfind("cond_up.", 0) == 0));
+                  (env_flag("MB_TC_UPS_X3", true) &&
+                   (L.name.rfind("ups.", 0) == 0 || L.name.rfind("cond_up.", 0) == 0 || L.name.rfind("res_output.", 0) == 0));
       d.taps = &L.taps;
       d.k = L.k;
       d.tc = &L.tc;
