@@ -71,6 +71,7 @@ struct TcPairParams {
   int a1_stages, a2_stages;
   int tiles_per_utt, n_work;
   uint32_t a1_stage_bytes, a2_bytes, a1_off, a2_off, w1_off, w2_off, bias_off, bar_off;
+  int epi_split;             // 1: epilogue warps 2-5 do E1, 6-9 do E2 (decoupled); 0: all eight do E1 then E2 (round 1)
   int f32in;                 // 1: the input is the fp32 F32B plane x32 (converted on the fly), no fp16 input plane
   uint32_t s32_stage_bytes, s32_off;
   int s32_stages;

@@ -18,6 +18,7 @@
 // quad, clamped to the utterance), four converter warps apply the leaky-relu, round to fp16 and write
 // the swizzled A1 operand; the residual add re-reads the same fp32 rows (L2 hits).  No fp16 plane is
 // read or written: 420 MB instead of 630 MB of HBM traffic per pair at C = 32, L = 51 200, B = 32.
+#include <cstdlib>
 #include <cstring>
 
 #include "gan_tc.h"
@@ -77,11 +78,12 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
       mbar_init(&s32_empty[i], 32 * kCvtWarps);
       mbar_init(&w_full[i], 1);
       mbar_init(&acc1_full[i], 1);
-      mbar_init(&acc1_empty[i], 32 * kEpiWarps);
-      mbar_init(&a2_full[i], 32 * kEpiWarps);
+      // epi_split: warps 2-5 run E1 for every unit, warps 6-9 run E2 (two decoupled pipelines); else all eight run E1 then E2
+      mbar_init(&acc1_empty[i], p.epi_split ? 128 : 32 * kEpiWarps);
+      mbar_init(&a2_full[i], p.epi_split ? 128 : 32 * kEpiWarps);
       mbar_init(&a2_empty[i], 1);
       mbar_init(&acc2_full[i], 1);
-      mbar_init(&acc2_empty[i], 32 * kEpiWarps);
+      mbar_init(&acc2_empty[i], p.epi_split ? 128 : 32 * kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
       mbar_wait(&a2_empty[aslot], aph ^ 1);
       tc_fence_after();
       uint8_t* a2 = a2_base + (size_t)aslot * p.a2_bytes;
-      for (int u = grp; u < NUNITS; u += 2) {
+      for (int u = (p.epi_split ? 0 : grp); u < NUNITS; u += (p.epi_split ? 1 : 2)) {
         const int mt = u / UPT;
         const int col0 = (u - mt * UPT) << 5;
         const int j = mt * 128 + row_in_tile;   // xt row within the item
@@ -323,8 +325,8 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
       const int cslot = it & 1, cph = (it >> 1) & 1;
       bool waited = false;
 #pragma unroll
-      for (int ui = 0; ui < UPG; ++ui) {
-        const int u = grp + 2 * ui;
+      for (int ui = 0; ui < NUNITS; ++ui) {
+        const int u = p.epi_split ? ui : grp + 2 * ui;
         if (u >= NUNITS) break;
         const int mt = u / UPT;
         const int col0 = (u - mt * UPT) << 5;
@@ -434,11 +436,20 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
       mbar_arrive(&acc2_empty[cslot]);
     };
 
-    for (int it = 0; it < n_items; ++it) {
-      e1(it);
-      if (it > 0) e2(it - 1);
+    if (p.epi_split) {
+      // decoupled: E2(it) no longer waits behind E1(it+1) (whose accumulator may be late), E1 never waits behind E2's global traffic
+      if (grp == 0) {
+        for (int it = 0; it < n_items; ++it) e1(it);
+      } else {
+        for (int it = 0; it < n_items; ++it) e2(it);
+      }
+    } else {
+      for (int it = 0; it < n_items; ++it) {
+        e1(it);
+        if (it > 0) e2(it - 1);
+      }
+      if (n_items > 0) e2(n_items - 1);
     }
-    if (n_items > 0) e2(n_items - 1);
   }
 
   tc_fence_before();
@@ -510,6 +521,11 @@ bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
 int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
   p.tiles_per_utt = (p.L + p.M_out - 1) / p.M_out;
   p.n_work = B * p.tiles_per_utt;
+  static const int split = [] {
+    const char* e = getenv("MB_TC_PAIR_SPLIT");  // A/B switch: 1 = E1 and E2 on separate warp groups
+    return e ? atoi(e) : 1;
+  }();
+  p.epi_split = split ? 1 : 0;
   void (*kern)(const TcPairParams) = nullptr;
   if (p.f32in && p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32, true>;
   else if (p.f32in && p.C == 32 && p.MT == 2) kern = tc_pair_kernel<32, 2, 32, true>;
