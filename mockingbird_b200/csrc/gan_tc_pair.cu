@@ -522,8 +522,10 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
   p.tiles_per_utt = (p.L + p.M_out - 1) / p.M_out;
   p.n_work = B * p.tiles_per_utt;
   static const int split = [] {
-    const char* e = getenv("MB_TC_PAIR_SPLIT");  // A/B switch: 1 = E1 and E2 on separate warp groups
-    return e ? atoi(e) : 1;
+    // A/B switch: 1 = E1 and E2 on separate warp groups.  Measured (profiles/r02_layers_split{0,1}.tsv): SLOWER, 5.51 vs 5.01 ms per
+    // step - four warps per role keep fewer loads in flight than eight warps doing both in turn; the default stays 0.
+    const char* e = getenv("MB_TC_PAIR_SPLIT");
+    return e ? atoi(e) : 0;
   }();
   p.epi_split = split ? 1 : 0;
   void (*kern)(const TcPairParams) = nullptr;
