@@ -31,13 +31,16 @@ namespace {
 
 using namespace tcdev;
 
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kCvtWarps = 2;
-constexpr int kThreadsF32 = kThreads + 32 * kCvtWarps;
+constexpr int pair_threads(int ew, bool f32in) { return 64 + 32 * ew + (f32in ? 32 * kCvtWarps : 0); }
 
-template <int N, int MT, int CW, bool F32IN>
-__global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_kernel(const __grid_constant__ TcPairParams p) {
+// EW epilogue warps (8 or 16: EW/4 groups, each covering the four TMEM lane quarters), UC accumulator columns per epilogue
+// unit (32, or 16 so that sixteen warps fit the register file: 640 threads x <= 102 registers).  More epilogue warps keep
+// more residual loads / stores in flight: the pair kernels are bound by epilogue memory-level parallelism
+// (profiles/r02_layers_split{0,1}.tsv: halving the warps per epilogue role cost 30-50 %).
+template <int N, int MT, int CW, bool F32IN, int EW = 8, int UC = 32>
+__global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(const __grid_constant__ TcPairParams p) {
+  constexpr int kEpiWarps = EW;
   constexpr uint32_t ROWB = CW * 2;
   constexpr int NK16 = CW / 16;
   constexpr uint32_t MT_STEP = (128u * ROWB) >> 4;
@@ -79,11 +82,11 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
       mbar_init(&w_full[i], 1);
       mbar_init(&acc1_full[i], 1);
       // epi_split: warps 2-5 run E1 for every unit, warps 6-9 run E2 (two decoupled pipelines); else all eight run E1 then E2
-      mbar_init(&acc1_empty[i], p.epi_split ? 128 : 32 * kEpiWarps);
-      mbar_init(&a2_full[i], p.epi_split ? 128 : 32 * kEpiWarps);
+      mbar_init(&acc1_empty[i], p.epi_split ? 16 * kEpiWarps : 32 * kEpiWarps);
+      mbar_init(&a2_full[i], p.epi_split ? 16 * kEpiWarps : 32 * kEpiWarps);
       mbar_init(&a2_empty[i], 1);
       mbar_init(&acc2_full[i], 1);
-      mbar_init(&acc2_empty[i], p.epi_split ? 128 : 32 * kEpiWarps);
+      mbar_init(&acc2_empty[i], p.epi_split ? 16 * kEpiWarps : 32 * kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < N; i += (F32IN ? kThreadsF32 : kThreads)) {
+  for (int i = threadIdx.x; i < N; i += (int)blockDim.x) {
     bias1_s[i] = p.bias1[i];
     bias2_s[i] = p.bias2[i];
   }
@@ -263,8 +266,12 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
     const int quarter = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
-    constexpr int UPT = N / 32;          // 32-column units per row tile
+    constexpr int UPT = N / UC;          // UC-column units per row tile
     constexpr int NUNITS = MT * UPT;
+    constexpr int G = EW / 4;            // epilogue groups
+    // unit schedule of this group: all groups share E1 then E2, or (epi_split) the lower half of the groups runs E1, the upper E2
+    const int ustride = p.epi_split ? G / 2 : G;
+    const int ufirst = p.epi_split ? grp % (G / 2) : grp;
     const int C4 = N >> 2;
     constexpr int OCW = (N >= 64) ? 64 : N;  // output plane row chunk (f16_cw)
 
@@ -279,18 +286,18 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
       mbar_wait(&a2_empty[aslot], aph ^ 1);
       tc_fence_after();
       uint8_t* a2 = a2_base + (size_t)aslot * p.a2_bytes;
-      for (int u = (p.epi_split ? 0 : grp); u < NUNITS; u += (p.epi_split ? 1 : 2)) {
+      for (int u = ufirst; u < NUNITS; u += ustride) {
         const int mt = u / UPT;
-        const int col0 = (u - mt * UPT) << 5;
+        const int col0 = (u - mt * UPT) * UC;
         const int j = mt * 128 + row_in_tile;   // xt row within the item
         const int g = m0 - p.h2 + j;            // global xt row
         const bool live = (g >= 0 && g < valid);
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((cslot * MT + mt) * N + col0), raw);
+        uint32_t raw[UC];
+        tmem_ld<UC>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((cslot * MT + mt) * N + col0), raw);
         uint8_t* rowp = a2 + (size_t)j * ROWB;
         const int sw = f16_swz(CW, j);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < UC / 8; ++c) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -326,70 +333,70 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
       bool waited = false;
 #pragma unroll
       for (int ui = 0; ui < NUNITS; ++ui) {
-        const int u = p.epi_split ? ui : grp + 2 * ui;
+        const int u = ufirst + ustride * ui;
         if (u >= NUNITS) break;
         const int mt = u / UPT;
-        const int col0 = (u - mt * UPT) << 5;
+        const int col0 = (u - mt * UPT) * UC;
         const int i = mt * 128 + row_in_tile;
         const int lo = m0 + i;
         const bool inb = (i < p.M_out) && (lo < p.L);
         const bool live = inb && lo < valid;
         const size_t i32 = ((size_t)b * C4 + (col0 >> 2)) * p.L + lo;
-        float4 rv[8], ov[8];
-        uint4 rh[4];
+        float4 rv[UC / 4], ov[UC / 4];
+        uint4 rh[UC / 8];
         if (inb && p.res32) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.L];
+          for (int g = 0; g < UC / 4; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.L];
         }
         if (inb && p.res16) {
           const int rr = kPadRows + lo;
           const size_t rbase = ((size_t)b * p.res_Lp + rr) * (size_t)(OCW >> 3);
           const int sw = f16_swz(OCW, rr);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) rh[g] = reinterpret_cast<const uint4*>(p.res16)[rbase + (size_t)(((col0 >> 3) + g) ^ sw)];
+          for (int g = 0; g < UC / 8; ++g) rh[g] = reinterpret_cast<const uint4*>(p.res16)[rbase + (size_t)(((col0 >> 3) + g) ^ sw)];
         }
         if (inb && p.mode != EPI_STORE) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) ov[g] = reinterpret_cast<const float4*>(p.y32)[i32 + (size_t)g * p.L];
+          for (int g = 0; g < UC / 4; ++g) ov[g] = reinterpret_cast<const float4*>(p.y32)[i32 + (size_t)g * p.L];
         }
         if (!waited) {
           mbar_wait(&acc2_full[cslot], cph);
           tc_fence_after();
           waited = true;
         }
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(((2 + cslot) * MT + mt) * N + col0), raw);
+        uint32_t raw[UC];
+        tmem_ld<UC>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(((2 + cslot) * MT + mt) * N + col0), raw);
         if (!inb) continue;
-        float v[32];
+        float v[UC];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(raw[e]) + bias2_s[col0 + e];
+        for (int e = 0; e < UC; ++e) v[e] = __uint_as_float(raw[e]) + bias2_s[col0 + e];
         if (p.res32) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < UC / 4; ++g) {
             v[4 * g + 0] += rv[g].x; v[4 * g + 1] += rv[g].y; v[4 * g + 2] += rv[g].z; v[4 * g + 3] += rv[g].w;
           }
         }
         if (p.res16) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) add_res16(&v[8 * g], rh[g], p.res_inv);
+          for (int g = 0; g < UC / 8; ++g) add_res16(&v[8 * g], rh[g], p.res_inv);
         }
         if (p.mode != EPI_STORE) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < UC / 4; ++g) {
             v[4 * g + 0] += ov[g].x; v[4 * g + 1] += ov[g].y; v[4 * g + 2] += ov[g].z; v[4 * g + 3] += ov[g].w;
           }
           if (p.mode == EPI_ADD_DIV) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] /= p.div;
+            for (int e = 0; e < UC; ++e) v[e] /= p.div;
           }
         }
         if (!live) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = 0.f;
+          for (int e = 0; e < UC; ++e) v[e] = 0.f;
         }
         if (p.y32) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
+          for (int g = 0; g < UC / 4; ++g)
             reinterpret_cast<float4*>(p.y32)[i32 + (size_t)g * p.L] =
                 make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
         }
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
           const int rr = kPadRows + lo;
           const int sw = f16_swz(OCW, rr);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < UC / 8; ++g) {
             __half2 h0 = __floats2half2_rn(lrelu(v[8 * g + 0], p.out_slope), lrelu(v[8 * g + 1], p.out_slope));
             __half2 h1 = __floats2half2_rn(lrelu(v[8 * g + 2], p.out_slope), lrelu(v[8 * g + 3], p.out_slope));
             __half2 h2 = __floats2half2_rn(lrelu(v[8 * g + 4], p.out_slope), lrelu(v[8 * g + 5], p.out_slope));
@@ -438,7 +445,7 @@ __global__ void __launch_bounds__(F32IN ? kThreadsF32 : kThreads, 1) tc_pair_ker
 
     if (p.epi_split) {
       // decoupled: E2(it) no longer waits behind E1(it+1) (whose accumulator may be late), E1 never waits behind E2's global traffic
-      if (grp == 0) {
+      if (grp < G / 2) {
         for (int it = 0; it < n_items; ++it) e1(it);
       } else {
         for (int it = 0; it < n_items; ++it) e2(it);
@@ -529,7 +536,22 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
   }();
   p.epi_split = split ? 1 : 0;
   void (*kern)(const TcPairParams) = nullptr;
-  if (p.f32in && p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32, true>;
+  static const int ew16 = [] {
+    const char* e = getenv("MB_TC_PAIR_EW16");  // A/B switch: 1 = sixteen epilogue warps working on 16-column units
+    return e ? atoi(e) : 0;
+  }();
+  int threads = pair_threads(8, p.f32in != 0);
+  if (ew16 && p.MT >= 2) {
+    threads = pair_threads(16, p.f32in != 0);
+    if (p.f32in && p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32, true, 16, 16>;
+    else if (p.f32in && p.C == 32 && p.MT == 2) kern = tc_pair_kernel<32, 2, 32, true, 16, 16>;
+    else if (!p.f32in && p.C == 64 && p.MT == 2) kern = tc_pair_kernel<64, 2, 64, false, 16, 16>;
+    else if (!p.f32in && p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32, false, 16, 16>;
+    else if (!p.f32in && p.C == 32 && p.MT == 2) kern = tc_pair_kernel<32, 2, 32, false, 16, 16>;
+    else threads = pair_threads(8, p.f32in != 0);
+  }
+  if (kern) {
+  } else if (p.f32in && p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32, true>;
   else if (p.f32in && p.C == 32 && p.MT == 2) kern = tc_pair_kernel<32, 2, 32, true>;
   else if (p.f32in && p.C == 32 && p.MT == 1) kern = tc_pair_kernel<32, 1, 32, true>;
   else if (p.f32in) kern = nullptr;
@@ -548,7 +570,7 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(p.f32in ? kThreadsF32 : kThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = kSmemMax;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
