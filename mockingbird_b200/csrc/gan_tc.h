@@ -75,6 +75,7 @@ struct TcPairParams {
   int f32in;                 // 1: the input is the fp32 F32B plane x32 (converted on the fly), no fp16 input plane
   uint32_t s32_stage_bytes, s32_off;
   int s32_stages;
+  int s32_pieces;            // row pieces of the fp32 staging window (one mbarrier each): 2 or 4
   const float* x32;
   float slope_in;            // leaky-relu applied to the input by the converter (c1's in_slope)
   const __half* x16;

@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
   uint64_t* a2_empty = bars + 12;      // [2]
   uint64_t* acc2_full = bars + 14;     // [2]
   uint64_t* acc2_empty = bars + 16;    // [2]
-  uint64_t* s32_full = bars + 18;      // [2]  (F32IN: fp32 staging of the input window)
-  uint64_t* s32_empty = bars + 20;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* s32_full = bars + 18;      // [4]  (F32IN: fp32 staging of the input window, p.s32_pieces row pieces)
+  uint64_t* s32_empty = bars + 22;     // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   uint8_t* s32_base = smem + p.s32_off;
 
   const int warp = threadIdx.x >> 5;
@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
       mbar_init(&a1_empty[i], 1);
       mbar_init(&s32_full[i], 1);
       mbar_init(&s32_empty[i], 32 * kCvtWarps);
+      mbar_init(&s32_full[i + 2], 1);
+      mbar_init(&s32_empty[i + 2], 32 * kCvtWarps);
       mbar_init(&w_full[i], 1);
       mbar_init(&acc1_full[i], 1);
       // epi_split: warps 2-5 run E1 for every unit, warps 6-9 run E2 (two decoupled pipelines); else all eight run E1 then E2
@@ -121,11 +123,12 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
         const int b = work / p.tiles_per_utt;
         const int m0 = (work - b * p.tiles_per_utt) * p.M_out;
         if constexpr (F32IN) {
-          // the fp32 window is staged in two row halves (two barriers): while the converter drains one half
-          // the other half's copies are already in flight
+          // the fp32 window is staged in p.s32_pieces row pieces (one barrier each): while the converter drains one piece the
+          // copies of the others are in flight.  Four pieces instead of two keep more loads in flight per SM: with two the
+          // kernel ran at ~5.8 us per item = two exposed DRAM round trips (profiles/r02_pair32_k3_summary.txt)
           const int g0 = m0 - halo;
-          const int HW = p.W1 >> 1;
-          for (int hf = 0; hf < 2; ++hf) {
+          const int HW = p.W1 / p.s32_pieces;
+          for (int hf = 0; hf < p.s32_pieces; ++hf) {
             mbar_wait(&s32_empty[hf], (it & 1) ^ 1);
             const int r0 = g0 + hf * HW;
             const int lo = r0 < 0 ? 0 : r0;
@@ -229,8 +232,8 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
       mbar_wait(&a1_empty[aslot], aph ^ 1);
       uint8_t* a1 = a1_base + (size_t)aslot * p.a1_stage_bytes;
       const int g0 = m0 - halo;
-      const int HW = p.W1 >> 1;
-      for (int hf = 0; hf < 2; ++hf) {
+      const int HW = p.W1 / p.s32_pieces;
+      for (int hf = 0; hf < p.s32_pieces; ++hf) {
         mbar_wait(&s32_full[hf], it & 1);
         const uint8_t* s32 = s32_base + (size_t)hf * p.s32_stage_bytes;
         for (int jj = tid; jj < HW; jj += 32 * kCvtWarps) {
@@ -493,8 +496,14 @@ bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
       const int W2 = (mt * 128 + 16 + 7) & ~7;
       const uint32_t a1b = (uint32_t)align_up((size_t)W1 * row_bytes, 1024);
       const uint32_t a2b = (uint32_t)align_up((size_t)W2 * row_bytes, 1024);
-      const uint32_t s32b = f32in ? (uint32_t)align_up((size_t)(W1 / 2) * C * 4, 1024) : 0u;  // one row half (W1 % 16 == 0 below)
-      const uint32_t total = 2 * s32b + st[1] * a1b + st[2] * a2b + 2 * wbytes + 1024 + 1024;
+      static const int pieces = [] {
+        const char* e = getenv("MB_TC_PAIR_S32P");  // A/B switch: row pieces of the fp32 staging window (2 or 4)
+        const int v = e ? atoi(e) : 4;
+        return v == 2 ? 2 : 4;
+      }();
+      const uint32_t s32b = f32in ? (uint32_t)align_up((size_t)(W1 / pieces) * C * 4, 1024) : 0u;  // one row piece (W1 % 16 == 0)
+      const uint32_t total = pieces * s32b + st[1] * a1b + st[2] * a2b + 2 * wbytes + 1024 + 1024;
+      p->s32_pieces = pieces;
       if (total > usable) continue;
       p->f32in = f32in ? 1 : 0;
       p->s32_stage_bytes = s32b;
@@ -537,8 +546,10 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
   p.epi_split = split ? 1 : 0;
   void (*kern)(const TcPairParams) = nullptr;
   static const int ew16 = [] {
-    const char* e = getenv("MB_TC_PAIR_EW16");  // A/B switch: 1 = sixteen epilogue warps working on 16-column units
-    return e ? atoi(e) : 0;
+    // A/B switch: 1 (default) = sixteen epilogue warps working on 16-column units.  Measured (profiles/r02_layers_ew16_{0,1}.tsv):
+    // 5.125 -> 5.012 ms per profiled forward, C = 64 k = 3 pairs -20 %, accumulate-mode pairs of the full-rate stage -8..-17 %.
+    const char* e = getenv("MB_TC_PAIR_EW16");
+    return e ? atoi(e) : 1;
   }();
   int threads = pair_threads(8, p.f32in != 0);
   if (ew16 && p.MT >= 2) {
