@@ -124,8 +124,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
         const int m0 = (work - b * p.tiles_per_utt) * p.M_out;
         if constexpr (F32IN) {
           // the fp32 window is staged in p.s32_pieces row pieces (one barrier each): while the converter drains one piece the
-          // copies of the others are in flight.  Four pieces instead of two keep more loads in flight per SM: with two the
-          // kernel ran at ~5.8 us per item = two exposed DRAM round trips (profiles/r02_pair32_k3_summary.txt)
+          // copies of the others are in flight
           const int g0 = m0 - halo;
           const int HW = p.W1 / p.s32_pieces;
           for (int hf = 0; hf < p.s32_pieces; ++hf) {
@@ -497,9 +496,11 @@ bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
       const uint32_t a1b = (uint32_t)align_up((size_t)W1 * row_bytes, 1024);
       const uint32_t a2b = (uint32_t)align_up((size_t)W2 * row_bytes, 1024);
       static const int pieces = [] {
-        const char* e = getenv("MB_TC_PAIR_S32P");  // A/B switch: row pieces of the fp32 staging window (2 or 4)
-        const int v = e ? atoi(e) : 4;
-        return v == 2 ? 2 : 4;
+        // A/B switch: row pieces of the fp32 staging window, 2 (default) or 4.  Measured: 4 is slightly SLOWER (5.09 vs 5.00 ms per
+        // profiled forward) - the bytes in flight are set by the window's size, not by how it is cut
+        const char* e = getenv("MB_TC_PAIR_S32P");
+        const int v = e ? atoi(e) : 2;
+        return v == 4 ? 4 : 2;
       }();
       const uint32_t s32b = f32in ? (uint32_t)align_up((size_t)(W1 / pieces) * C * 4, 1024) : 0u;  // one row piece (W1 % 16 == 0)
       const uint32_t total = pieces * s32b + st[1] * a1b + st[2] * a2b + 2 * wbytes + 1024 + 1024;
