@@ -40,8 +40,7 @@ namespace mb {
 
 namespace {
 
-constexpr int kEpiWarps = 8;
-constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+__host__ __device__ constexpr int tc_threads(int ew) { return 64 + 32 * ew; }
 constexpr int kAStages = 2;
 constexpr int kAccStages = 2;
 constexpr int kMaxWStages = 16;
@@ -101,8 +100,11 @@ __device__ __forceinline__ WorkItem decode_work(const TcParams& p, int work) {
 // N = Cout, MT = row tiles per work item, CW = channels per operand row (64: SWIZZLE_128B, 32: SWIZZLE_64B).
 // They are compile-time so that every MMA's descriptor is "base + immediate" (the single issuing
 // thread is otherwise the bottleneck: ~190 cycles per MMA with run-time address arithmetic).
-template <int N, int MT, int CW>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
+// EW epilogue warps (8, or 16 working on UC = 16-column units so that 576 threads fit the register file): see gan_tc_pair.cu.
+template <int N, int MT, int CW, int EW = 8, int UC = 32>
+__global__ void __launch_bounds__(tc_threads(EW), 1) tc_conv_kernel(const __grid_constant__ TcParams p) {
+  constexpr int kEpiWarps = EW;
+  constexpr int kTcThreads = tc_threads(EW);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024 B alignment
   uint8_t* a_base = smem + p.a_off;
@@ -274,75 +276,76 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     int acc_stage = 0, acc_phase = 0;
     const int C4 = p.Cout >> 2;
     const int ocw = f16_cw(p.Cout);  // output plane: channels per row chunk
-    const int units_per_tile = p.Cout >> 5;
+    const int units_per_tile = p.Cout / UC;
     const int n_units = p.MT * units_per_tile;
+    constexpr int G = EW / 4;
     for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
       const WorkItem wi = decode_work(p, work);
       const int valid_out = p.lengths ? min(p.Lout, p.lengths[wi.b] * p.len_mul_out) : p.Lout;
       bool waited = false;
-      for (int u = grp; u < n_units; u += 2) {
+      for (int u = grp; u < n_units; u += G) {
         const int mt = u / units_per_tile;
-        const int col0 = (u - mt * units_per_tile) << 5;
+        const int col0 = (u - mt * units_per_tile) * UC;
         const int q = wi.m0 + mt * 128 + row_in_tile;
         const int lo = q * p.stride + wi.r;
         const bool inb = q < p.Lin;
         const bool live = inb && lo < valid_out;
         const size_t i32 = ((size_t)wi.b * C4 + (col0 >> 2)) * p.Lout + lo;  // + g * Lout per 4 channels
-        float4 rv[8], ov[8];
-        uint4 rh[4];
+        float4 rv[UC / 4], ov[UC / 4];
+        uint4 rh[UC / 8];
         if (inb && p.res32) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.Lout];
+          for (int g = 0; g < UC / 4; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.Lout];
         }
         if (inb && p.res16) {
           const int rr = kPadRows + lo;
           const size_t rbase = (((size_t)wi.b * (p.Cout / ocw) + col0 / ocw) * p.res_Lp + rr) * (size_t)(ocw >> 3);
           const int c0 = (col0 & (ocw - 1)) >> 3, sw = f16_swz(ocw, rr);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) rh[g] = reinterpret_cast<const uint4*>(p.res16)[rbase + (size_t)((c0 + g) ^ sw)];
+          for (int g = 0; g < UC / 8; ++g) rh[g] = reinterpret_cast<const uint4*>(p.res16)[rbase + (size_t)((c0 + g) ^ sw)];
         }
         if (inb && p.mode != EPI_STORE) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) ov[g] = reinterpret_cast<const float4*>(p.y32)[i32 + (size_t)g * p.Lout];
+          for (int g = 0; g < UC / 4; ++g) ov[g] = reinterpret_cast<const float4*>(p.y32)[i32 + (size_t)g * p.Lout];
         }
         if (!waited) {
           mbar_wait(&acc_full[acc_stage], acc_phase);
           tc_fence_after();
           waited = true;
         }
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc_stage * p.MT + mt) * p.Cout + col0), raw);
+        uint32_t raw[UC];
+        tmem_ld<UC>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc_stage * p.MT + mt) * p.Cout + col0), raw);
         if (!inb) continue;
-        float v[32];
+        float v[UC];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * p.acc_scale + bias_s[col0 + i];
+        for (int i = 0; i < UC; ++i) v[i] = __uint_as_float(raw[i]) * p.acc_scale + bias_s[col0 + i];
         if (p.res32) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < UC / 4; ++g) {
             v[4 * g + 0] += rv[g].x; v[4 * g + 1] += rv[g].y; v[4 * g + 2] += rv[g].z; v[4 * g + 3] += rv[g].w;
           }
         }
         if (p.res16) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) add_res16(&v[8 * g], rh[g], p.res_inv);
+          for (int g = 0; g < UC / 8; ++g) add_res16(&v[8 * g], rh[g], p.res_inv);
         }
         if (p.mode != EPI_STORE) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < UC / 4; ++g) {
             v[4 * g + 0] += ov[g].x; v[4 * g + 1] += ov[g].y; v[4 * g + 2] += ov[g].z; v[4 * g + 3] += ov[g].w;
           }
           if (p.mode == EPI_ADD_DIV) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] /= p.div;
+            for (int i = 0; i < UC; ++i) v[i] /= p.div;
           }
         }
         if (!live) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          for (int i = 0; i < UC; ++i) v[i] = 0.f;
         }
         if (p.y32) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
+          for (int g = 0; g < UC / 4; ++g)
             reinterpret_cast<float4*>(p.y32)[i32 + (size_t)g * p.Lout] =
                 make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
         }
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
           const int ysw = f16_swz(p.y_cw, rr);
           const int ycw8 = p.y_cw >> 3;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < UC / 8; ++g) {
             float a[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) a[e] = lrelu(v[8 * g + e], p.out_slope);
@@ -702,7 +705,22 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   if (y_c0 != 0 && (p.y32 || p.res32 || p.res16)) return fail(MB_ERR_INVALID, "tc_conv(%s): channel-offset launch supports the fp16 plane only", op.name);
   if (p.mode != EPI_STORE && !p.y32) return fail(MB_ERR_INVALID, "tc_conv(%s): accumulate mode without fp32 plane", op.name);
   void (*kern)(const TcParams) = nullptr;
-  if (p.Cout == 256 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<256, 1, 64>;
+  static const int ew16 = [] {
+    const char* e = getenv("MB_TC_CONV_EW16");  // A/B switch: 1 = sixteen epilogue warps on 16-column units
+    return e ? atoi(e) : 0;
+  }();
+  int threads = tc_threads(8);
+  if (ew16) {
+    threads = tc_threads(16);
+    if (p.Cout == 256 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<256, 1, 64, 16, 16>;
+    else if (p.Cout == 128 && p.MT == 2 && p.cw == 64) kern = tc_conv_kernel<128, 2, 64, 16, 16>;
+    else if (p.Cout == 128 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<128, 1, 64, 16, 16>;
+    else if (p.Cout == 64 && p.MT == 4 && p.cw == 64) kern = tc_conv_kernel<64, 4, 64, 16, 16>;
+    else if (p.Cout == 32 && p.MT == 4 && p.cw == 64) kern = tc_conv_kernel<32, 4, 64, 16, 16>;
+    else threads = tc_threads(8);
+  }
+  if (kern) {
+  } else if (p.Cout == 256 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<256, 1, 64>;
   else if (p.Cout == 128 && p.MT == 2 && p.cw == 64) kern = tc_conv_kernel<128, 2, 64>;
   else if (p.Cout == 128 && p.MT == 1 && p.cw == 64) kern = tc_conv_kernel<128, 1, 64>;
   else if (p.Cout == 64 && p.MT == 4 && p.cw == 64) kern = tc_conv_kernel<64, 4, 64>;
@@ -723,7 +741,7 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kTcThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = kSmemMax;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -32,7 +32,7 @@ namespace {
 using namespace tcdev;
 
 constexpr int kCvtWarps = 2;
-constexpr int pair_threads(int ew, bool f32in) { return 64 + 32 * ew + (f32in ? 32 * kCvtWarps : 0); }
+__host__ __device__ constexpr int pair_threads(int ew, bool f32in) { return 64 + 32 * ew + (f32in ? 32 * kCvtWarps : 0); }
 
 // EW epilogue warps (8 or 16: EW/4 groups, each covering the four TMEM lane quarters), UC accumulator columns per epilogue
 // unit (32, or 16 so that sixteen warps fit the register file: 640 threads x <= 102 registers).  More epilogue warps keep
