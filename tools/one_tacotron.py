@@ -16,5 +16,9 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 syn = Synthesizer("unused.pt", verbose=False)
 model = syn.load_state(ri.tacotron_state_dict(0, r=2, randomize_bn=True))
 chars, emb, _ = bt.make_inputs()
+model.generate(chars.cuda(), emb.cuda(), steps=steps, style_idx=-1, min_stop_token=10)  # warm-up: packs images, builds the graph
+torch.cuda.synchronize()
+torch.cuda.profiler.start()  # ncu --profile-from-start off
 model.generate(chars.cuda(), emb.cuda(), steps=steps, style_idx=-1, min_stop_token=10)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
