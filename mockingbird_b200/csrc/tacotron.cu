@@ -1074,7 +1074,34 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       m1 = dm;
       m2 = dm + dmask_n;
     }
-    {
+    static const bool prenet_fused = [] {
+      const char* e = getenv("MB_TACO_PRENET_FUSED");  // A/B switch: 0 = two skinny GEMM launches (round 1)
+      return e ? atoi(e) != 0 : true;
+    }();
+    if (prenet_fused && NM <= 128 && 2 * D <= 256) {
+      // both PreNet layers in one launch; frame (step * r - 1) of every utterance, step 0 = the all-zero go frame
+      PrenetArgs pa;
+      memset(&pa, 0, sizeof(pa));
+      pa.x = mel_all - NM;
+      pa.x_ld = (long long)steps_alloc * NM;
+      pa.x_step = (long long)r * NM;
+      pa.x_first = mel_all + (size_t)B * steps_alloc * NM;
+      pa.W1 = P(h, "decoder.prenet.fc1.weight");
+      pa.b1 = P(h, "decoder.prenet.fc1.bias");
+      pa.W2 = P(h, "decoder.prenet.fc2.weight");
+      pa.b2 = P(h, "decoder.prenet.fc2.bias");
+      pa.m1 = m1;
+      pa.m2 = m2;
+      pa.mask_step = mstep;
+      pa.step_ptr = sp;
+      pa.step_j = sj;
+      pa.B = B;
+      pa.K = NM;
+      pa.H = 2 * D;
+      pa.y = ws + L.dp2;
+      pa.ldy = 2 * D;
+      TK(launch_prenet_fused(pa, st));
+    } else {
       // frame (step * r - 1) of every utterance; step 0 reads the zero block behind mel_all with row stride 0
       GemmArgs a = gemm1(mel_all - NM, NM, steps_alloc * NM, P(h, "decoder.prenet.fc1.weight"), NM,
                          P(h, "decoder.prenet.fc1.bias"), B, 2 * D, ws + L.dp1, 2 * D, ACT_RELU);

@@ -420,6 +420,87 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int ldsrc, int r
 
 }  // namespace
 
+constexpr int kPrenetRows = 4;  // batch rows per CTA
+
+__global__ void __launch_bounds__(256) prenet_fused_kernel(const PrenetArgs a) {
+  __shared__ float xs[kPrenetRows][128];
+  __shared__ float hs[kPrenetRows][256];
+  const int b0 = blockIdx.x * kPrenetRows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int si = step_index(a.step_ptr, a.step_j);
+  const bool go = (si == 0 && a.x_first != nullptr);
+  for (int i = threadIdx.x; i < kPrenetRows * a.K; i += 256) {
+    const int r = i / a.K, k = i - r * a.K;
+    const int b = b0 + r;
+    float v = 0.f;
+    if (b < a.B) v = go ? a.x_first[k] : a.x[(long long)b * a.x_ld + (long long)si * a.x_step + k];
+    xs[r][k] = v;
+  }
+  __syncthreads();
+  const uint8_t* m1 = a.m1 + (size_t)si * (size_t)a.mask_step;
+  const uint8_t* m2 = a.m2 + (size_t)si * (size_t)a.mask_step;
+  // layer 1: warp w computes outputs w, w+8, ...; lanes split k, rows share the weight loads
+  for (int n = warp; n < a.H; n += 8) {
+    float acc[kPrenetRows];
+#pragma unroll
+    for (int r = 0; r < kPrenetRows; ++r) acc[r] = 0.f;
+    const float* w = a.W1 + (size_t)n * a.K;
+    for (int k = lane; k < a.K; k += 32) {
+      const float wv = w[k];
+#pragma unroll
+      for (int r = 0; r < kPrenetRows; ++r) acc[r] = fmaf(wv, xs[r][k], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kPrenetRows; ++r)
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
+    if (lane < kPrenetRows) {
+      const int b = b0 + lane;
+      float v = acc[0];
+#pragma unroll
+      for (int r = 1; r < kPrenetRows; ++r) v = lane == r ? acc[r] : v;
+      v += a.b1[n];
+      v = v > 0.f ? v : 0.f;
+      if (b < a.B) v = m1[(size_t)b * a.H + n] ? v * 2.f : 0.f;
+      hs[lane][n] = v;
+    }
+  }
+  __syncthreads();
+  for (int n = warp; n < a.H; n += 8) {
+    float acc[kPrenetRows];
+#pragma unroll
+    for (int r = 0; r < kPrenetRows; ++r) acc[r] = 0.f;
+    const float* w = a.W2 + (size_t)n * a.H;
+    for (int k = lane; k < a.H; k += 32) {
+      const float wv = w[k];
+#pragma unroll
+      for (int r = 0; r < kPrenetRows; ++r) acc[r] = fmaf(wv, hs[r][k], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kPrenetRows; ++r)
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
+    if (lane < kPrenetRows) {
+      const int b = b0 + lane;
+      float v = acc[0];
+#pragma unroll
+      for (int r = 1; r < kPrenetRows; ++r) v = lane == r ? acc[r] : v;
+      v += a.b2[n];
+      v = v > 0.f ? v : 0.f;
+      if (b < a.B) {
+        v = m2[(size_t)b * a.H + n] ? v * 2.f : 0.f;
+        a.y[(size_t)b * a.ldy + n] = v;
+      }
+    }
+  }
+}
+
+cudaError_t launch_prenet_fused(const PrenetArgs& a, cudaStream_t st) {
+  if (a.K > 128 || a.H > 256 || a.B <= 0) return cudaErrorInvalidValue;
+  prenet_fused_kernel<<<(a.B + kPrenetRows - 1) / kPrenetRows, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return cudaSuccess;
   bool shifted = false;

@@ -58,6 +58,28 @@ __device__ __forceinline__ int step_index(const int* step_ptr, int step_j) { ret
 
 cudaError_t launch_gemm(const GemmArgs& a, cudaStream_t st);
 
+// Decoder PreNet (sublayer/pre_net.py:11-27) as ONE launch: y = drop2(relu(W2 drop1(relu(W1 x + b1)) + b2)), dropout p = 0.5 with
+// injected / device-drawn keep masks (x2).  The intermediate never leaves shared memory; replaces two skinny GEMM launches
+// (12 us each, latency-bound) per decoder step.  Same step indirection as GemmArgs (CUDA-graph replay).
+struct PrenetArgs {
+  const float* x;          // frame (step*r - 1) of row b: x + b * x_ld + step * x_step (step 0: x_first, the zero go frame)
+  long long x_ld, x_step;
+  const float* x_first;
+  const float* W1;         // [H][K] row-major
+  const float* b1;
+  const float* W2;         // [H][H]
+  const float* b2;
+  const uint8_t* m1;       // [B][H] keep flags (+ step * mask_step)
+  const uint8_t* m2;
+  long long mask_step;
+  const int* step_ptr;
+  int step_j;
+  int B, K, H;             // K <= 128, H <= 256
+  float* y;                // [B][ldy]
+  int ldy;
+};
+cudaError_t launch_prenet_fused(const PrenetArgs& a, cudaStream_t st);
+
 // h' = GRU cell (ATen gru_cell): gi, gh [M][3H] pre-activations incl. biases; h in/out [M][ldh]
 cudaError_t launch_gru_cell(const float* gi, int ldgi, const float* gh, float* h, int ldh, float* out2, int ldout2,
                             int M, int H, cudaStream_t st);
