@@ -420,16 +420,64 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int ldsrc, int r
 
 }  // namespace
 
-constexpr int kPrenetRows = 4;  // batch rows per CTA
+constexpr int kPrenetRows = 4;     // batch rows per CTA
+constexpr int kPrenetWarps = 32;   // 1024 threads: 8 outputs per warp and layer, 4 at a time (4 independent weight streams in flight)
 
-__global__ void __launch_bounds__(256) prenet_fused_kernel(const PrenetArgs a) {
+// one dense layer for kPrenetRows rows held in shared memory: out[r][n] = mask(relu(b[n] + W[n][:] . in[r][:])) * 2
+template <int KMAX>
+__device__ __forceinline__ void prenet_layer(const float* __restrict__ W, const float* __restrict__ bias, int K, int H,
+                                             const float (*in)[KMAX], const uint8_t* __restrict__ mask, int b0, int B, int warp, int lane,
+                                             float (*out_s)[256], float* out_g, int ldy) {
+  for (int n0 = warp * 4; n0 < H; n0 += kPrenetWarps * 4) {
+    float acc[4][kPrenetRows];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int r = 0; r < kPrenetRows; ++r) acc[o][r] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      float wv[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) wv[o] = (n0 + o < H) ? W[(size_t)(n0 + o) * K + k] : 0.f;
+#pragma unroll
+      for (int r = 0; r < kPrenetRows; ++r) {
+        const float xv = in[r][k];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o][r] = fmaf(wv[o], xv, acc[o][r]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int r = 0; r < kPrenetRows; ++r)
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc[o][r] += __shfl_xor_sync(0xffffffffu, acc[o][r], off);
+    if (lane < 4 * kPrenetRows) {
+      const int o = lane >> 2, r = lane & 3;  // kPrenetRows == 4
+      float v = 0.f;
+#pragma unroll
+      for (int oo = 0; oo < 4; ++oo)
+#pragma unroll
+        for (int rr = 0; rr < kPrenetRows; ++rr) v = (oo == o && rr == r) ? acc[oo][rr] : v;
+      const int n = n0 + o, b = b0 + r;
+      if (n < H) {
+        v += bias[n];
+        v = v > 0.f ? v : 0.f;
+        if (b < B) v = mask[(size_t)b * H + n] ? v * 2.f : 0.f;
+        if (out_s) out_s[r][n] = v;
+        if (out_g && b < B) out_g[(size_t)b * ldy + n] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * kPrenetWarps) prenet_fused_kernel(const PrenetArgs a) {
   __shared__ float xs[kPrenetRows][128];
   __shared__ float hs[kPrenetRows][256];
   const int b0 = blockIdx.x * kPrenetRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int si = step_index(a.step_ptr, a.step_j);
   const bool go = (si == 0 && a.x_first != nullptr);
-  for (int i = threadIdx.x; i < kPrenetRows * a.K; i += 256) {
+  for (int i = threadIdx.x; i < kPrenetRows * a.K; i += blockDim.x) {
     const int r = i / a.K, k = i - r * a.K;
     const int b = b0 + r;
     float v = 0.f;
@@ -439,65 +487,14 @@ __global__ void __launch_bounds__(256) prenet_fused_kernel(const PrenetArgs a) {
   __syncthreads();
   const uint8_t* m1 = a.m1 + (size_t)si * (size_t)a.mask_step;
   const uint8_t* m2 = a.m2 + (size_t)si * (size_t)a.mask_step;
-  // layer 1: warp w computes outputs w, w+8, ...; lanes split k, rows share the weight loads
-  for (int n = warp; n < a.H; n += 8) {
-    float acc[kPrenetRows];
-#pragma unroll
-    for (int r = 0; r < kPrenetRows; ++r) acc[r] = 0.f;
-    const float* w = a.W1 + (size_t)n * a.K;
-    for (int k = lane; k < a.K; k += 32) {
-      const float wv = w[k];
-#pragma unroll
-      for (int r = 0; r < kPrenetRows; ++r) acc[r] = fmaf(wv, xs[r][k], acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < kPrenetRows; ++r)
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
-    if (lane < kPrenetRows) {
-      const int b = b0 + lane;
-      float v = acc[0];
-#pragma unroll
-      for (int r = 1; r < kPrenetRows; ++r) v = lane == r ? acc[r] : v;
-      v += a.b1[n];
-      v = v > 0.f ? v : 0.f;
-      if (b < a.B) v = m1[(size_t)b * a.H + n] ? v * 2.f : 0.f;
-      hs[lane][n] = v;
-    }
-  }
+  prenet_layer<128>(a.W1, a.b1, a.K, a.H, xs, m1, b0, a.B, warp, lane, hs, nullptr, 0);
   __syncthreads();
-  for (int n = warp; n < a.H; n += 8) {
-    float acc[kPrenetRows];
-#pragma unroll
-    for (int r = 0; r < kPrenetRows; ++r) acc[r] = 0.f;
-    const float* w = a.W2 + (size_t)n * a.H;
-    for (int k = lane; k < a.H; k += 32) {
-      const float wv = w[k];
-#pragma unroll
-      for (int r = 0; r < kPrenetRows; ++r) acc[r] = fmaf(wv, hs[r][k], acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < kPrenetRows; ++r)
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
-    if (lane < kPrenetRows) {
-      const int b = b0 + lane;
-      float v = acc[0];
-#pragma unroll
-      for (int r = 1; r < kPrenetRows; ++r) v = lane == r ? acc[r] : v;
-      v += a.b2[n];
-      v = v > 0.f ? v : 0.f;
-      if (b < a.B) {
-        v = m2[(size_t)b * a.H + n] ? v * 2.f : 0.f;
-        a.y[(size_t)b * a.ldy + n] = v;
-      }
-    }
-  }
+  prenet_layer<256>(a.W2, a.b2, a.H, a.H, hs, m2, b0, a.B, warp, lane, nullptr, a.y, a.ldy);
 }
 
 cudaError_t launch_prenet_fused(const PrenetArgs& a, cudaStream_t st) {
   if (a.K > 128 || a.H > 256 || a.B <= 0) return cudaErrorInvalidValue;
-  prenet_fused_kernel<<<(a.B + kPrenetRows - 1) / kPrenetRows, 256, 0, st>>>(a);
+  prenet_fused_kernel<<<(a.B + kPrenetRows - 1) / kPrenetRows, 32 * kPrenetWarps, 0, st>>>(a);
   return cudaGetLastError();
 }
 
