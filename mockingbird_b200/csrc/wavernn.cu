@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -181,7 +182,8 @@ struct LoopParams {
   int noise_B, row0;        // row0: global fold index of local row 0 (fold sharding across GPUs)
   uint64_t seed;
   int16_t* out_idx;         // [B][steps_total]
-  unsigned int* barrier;    // grid barrier counter (zeroed by the host before launch)
+  unsigned int* barrier;    // grid barrier counter / per-CTA epoch flags [NCTA] (zeroed by the host before launch)
+  int flagbar;              // 1: flag barrier, 0: single atomic counter
 };
 
 // per-CTA weight pack (floats):
@@ -241,7 +243,26 @@ __global__ void k_pack(PackSrc s, float* __restrict__ wpack) {
   }
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& target) {
+// Flag barrier (p.flagbar): every CTA publishes its epoch in its own word, threads 0..gridDim-1 of every CTA each poll one
+// word - no 128-way serialised atomic on a single L2 line, the polls run in parallel.  The counter variant is kept for A/B.
+__device__ __forceinline__ void grid_barrier_flags(unsigned int* flags, unsigned int& epoch) {
+  __syncthreads();
+  epoch += 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(epoch) : "memory");
+  }
+  if (threadIdx.x < gridDim.x) {
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+    } while (v < epoch);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void grid_barrier_counter(unsigned int* counter, unsigned int& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += gridDim.x;
@@ -254,6 +275,11 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __threadfence();  // also invalidates this SM's L1 so the plain loads below see the new data
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void grid_barrier(const LoopParams& p, unsigned int& target) {
+  if (p.flagbar) grid_barrier_flags(p.barrier, target);
+  else grid_barrier_counter(p.barrier, target);
 }
 
 // 4 rows x NC columns register tile over the k-range [k0, k0+klen) of one matrix:
@@ -388,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sample_loop(const LoopParams p)
       }
       __syncthreads();
     }
-    grid_barrier(p.barrier, bar_target);
+    grid_barrier(p, bar_target);
 
     // ================= phase B: rnn2 =================
     for (int rb = 0; rb < nrb; ++rb) {
@@ -453,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sample_loop(const LoopParams p)
       }
       __syncthreads();
     }
-    grid_barrier(p.barrier, bar_target);
+    grid_barrier(p, bar_target);
 
     // ================= phases C, D, E: fc1, fc2, fc3 =================
 #pragma unroll 1
@@ -519,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sample_loop(const LoopParams p)
         __syncthreads();
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");  // this step's noise row has landed (issued at the top of the step)
-      grid_barrier(p.barrier, bar_target);
+      grid_barrier(p, bar_target);
     }
 
     // ================= phase F: softmax + Categorical sample (one warp per row) =================
@@ -585,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sample_loop(const LoopParams p)
         }
       }
     }
-    grid_barrier(p.barrier, bar_target);
+    grid_barrier(p, bar_target);
   }
 }
 
@@ -671,7 +697,7 @@ WsLayout ws_layout(int T, int Bpad, int chunk_steps) {
   L.f2 = take((size_t)RNN * Bpad);
   L.logits = take((size_t)RNN * Bpad);
   L.xprev = take((size_t)Bpad);
-  L.barrier = take(64);
+  L.barrier = take(256);  // 1 KB: counter, or one epoch word per CTA
   L.total = o;
   return L;
 }
@@ -900,7 +926,7 @@ int mb_wavernn_generate_rows(mb_wavernn* h, const int32_t* fold_starts_host, int
   k_condI<<<nsteps * Bpad, 256, 0, st>>>(W(h, "I.weight"), W(h, "I.bias"), ws + L.melup, ws + L.aux, T, starts, B, Bpad,
                                          step0, nsteps, ws + L.condI);
   MB_LAUNCH_CHECK("k_condI");
-  MB_CUDA_CHECK(cudaMemsetAsync(ws + L.barrier, 0, 256, st));
+  MB_CUDA_CHECK(cudaMemsetAsync(ws + L.barrier, 0, 1024, st));
   LoopParams p;
   memset(&p, 0, sizeof(p));
   p.wpack = h->arena + h->pack_off;
@@ -928,6 +954,11 @@ int mb_wavernn_generate_rows(mb_wavernn* h, const int32_t* fold_starts_host, int
   p.seed = seed;
   p.out_idx = out_idx;
   p.barrier = reinterpret_cast<unsigned int*>(ws + L.barrier);
+  static const int flagbar = [] {
+    const char* e = getenv("MB_WAVERNN_FLAGBAR");  // A/B switch
+    return e ? atoi(e) : 1;
+  }();
+  p.flagbar = flagbar;
   const size_t smem = sizeof(float) * SMEM_FLOATS;
   static bool attr = false;
   if (!attr) {
