@@ -955,8 +955,10 @@ int mb_wavernn_generate_rows(mb_wavernn* h, const int32_t* fold_starts_host, int
   p.out_idx = out_idx;
   p.barrier = reinterpret_cast<unsigned int*>(ws + L.barrier);
   static const int flagbar = [] {
-    const char* e = getenv("MB_WAVERNN_FLAGBAR");  // A/B switch
-    return e ? atoi(e) : 1;
+    // A/B switch.  Measured: the flag barrier is much SLOWER (604 vs 428 ms per cfg-3 call: 128 x 128 polling threads swamp the
+    // four flag lines); the single-counter barrier stays the default.
+    const char* e = getenv("MB_WAVERNN_FLAGBAR");
+    return e ? atoi(e) : 0;
   }();
   p.flagbar = flagbar;
   const size_t smem = sizeof(float) * SMEM_FLOATS;
