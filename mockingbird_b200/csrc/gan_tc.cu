@@ -67,6 +67,7 @@ struct TcParams {
   const float* res32;
   const __half* res16;                 // residual taken from an (activated) fp16 plane instead: x = y >= 0 ? y : y * res_inv
   int res_Lp;
+  int res_hilo;                        // 1: the residual plane is a hi/lo plane (2 x Cout channels, 64-channel row chunks): x = inv_lrelu(hi + lo)
   float res_inv;
   float* y32;
   __half* y16;
@@ -297,12 +298,23 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) tc_conv_kernel(const __grid
 #pragma unroll
           for (int g = 0; g < UC / 4; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.Lout];
         }
-        if (inb && p.res16) {
+        if (inb && p.res16) {  // (the lo halves of a hi/lo residual share rv's registers: res32 and res16 are exclusive)
           const int rr = kPadRows + lo;
-          const size_t rbase = (((size_t)wi.b * (p.Cout / ocw) + col0 / ocw) * p.res_Lp + rr) * (size_t)(ocw >> 3);
-          const int c0 = (col0 & (ocw - 1)) >> 3, sw = f16_swz(ocw, rr);
+          if (!p.res_hilo) {
+            const size_t rbase = (((size_t)wi.b * (p.Cout / ocw) + col0 / ocw) * p.res_Lp + rr) * (size_t)(ocw >> 3);
+            const int c0 = (col0 & (ocw - 1)) >> 3, sw = f16_swz(ocw, rr);
 #pragma unroll
-          for (int g = 0; g < UC / 8; ++g) rh[g] = reinterpret_cast<const uint4*>(p.res16)[rbase + (size_t)((c0 + g) ^ sw)];
+            for (int g = 0; g < UC / 8; ++g) rh[g] = reinterpret_cast<const uint4*>(p.res16)[rbase + (size_t)((c0 + g) ^ sw)];
+          } else {
+            // hi/lo plane: rows of 64 channels; hi block = channels [0, Cout), lo block = [Cout, 2 Cout)
+            const int nch = (2 * p.Cout) >> 6, sw = f16_swz(64, rr);
+#pragma unroll
+            for (int g = 0; g < UC / 8; ++g) {
+              const int ch = col0 + 8 * g, cl = ch + p.Cout;
+              rh[g] = reinterpret_cast<const uint4*>(p.res16)[(((size_t)wi.b * nch + (ch >> 6)) * p.res_Lp + rr) * 8 + (size_t)(((ch & 63) >> 3) ^ sw)];
+              rv[g] = reinterpret_cast<const float4*>(p.res16)[(((size_t)wi.b * nch + (cl >> 6)) * p.res_Lp + rr) * 8 + (size_t)(((cl & 63) >> 3) ^ sw)];
+            }
+          }
         }
         if (inb && p.mode != EPI_STORE) {
 #pragma unroll
@@ -327,7 +339,10 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) tc_conv_kernel(const __grid
         }
         if (p.res16) {
 #pragma unroll
-          for (int g = 0; g < UC / 8; ++g) add_res16(&v[8 * g], rh[g], p.res_inv);
+          for (int g = 0; g < UC / 8; ++g) {
+            if (p.res_hilo) add_res16_hilo(&v[8 * g], rh[g], *reinterpret_cast<const uint4*>(&rv[g]), p.res_inv);
+            else add_res16(&v[8 * g], rh[g], p.res_inv);
+          }
         }
         if (p.mode != EPI_STORE) {
 #pragma unroll
@@ -600,6 +615,16 @@ bool tc_res16_enabled() {
   return on != 0;
 }
 
+// MB_TC_X3_RES16=0: 3-term-split layers keep an fp32 residual plane (default: residual = inv_lrelu(hi + lo) of the hi/lo plane)
+bool tc_x3_res16_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB_TC_X3_RES16");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
+}
+
 // MB_TC_PAIR32=0 disables the fp32-input pair kernel of the full-rate stage (falls back to the fp16-plane pair)
 bool tc_pair32_enabled() {
   static int on = -1;
@@ -688,6 +713,7 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.res32 = reinterpret_cast<const float*>(res32.p);
   p.res16 = reinterpret_cast<const __half*>(res16.p);
   p.res_Lp = f16_lp(res16.L);
+  p.res_hilo = res16.p ? res16.hilo : 0;
   p.res_inv = 1.f / res_slope;
   p.y32 = reinterpret_cast<float*>(y32.p);
   p.y16 = reinterpret_cast<__half*>(y16.p);
@@ -701,7 +727,8 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.div = t.div;
   p.lengths = lengths;
   p.len_mul_out = t.len_mul_out;
-  if (res16.p && (res16.hilo || res16.C != t.Cout)) return fail(MB_ERR_INVALID, "tc_conv(%s): fp16 residual plane must be a plain plane", op.name);
+  if (res16.p && !res16.hilo && res16.C != t.Cout) return fail(MB_ERR_INVALID, "tc_conv(%s): fp16 residual plane geometry", op.name);
+  if (res16.p && res16.hilo && res16.C != (t.Cout >= 64 ? 2 * t.Cout : 64)) return fail(MB_ERR_INVALID, "tc_conv(%s): hi/lo residual plane geometry", op.name);
   if (y_c0 != 0 && (p.y32 || p.res32 || p.res16)) return fail(MB_ERR_INVALID, "tc_conv(%s): channel-offset launch supports the fp16 plane only", op.name);
   if (p.mode != EPI_STORE && !p.y32) return fail(MB_ERR_INVALID, "tc_conv(%s): accumulate mode without fp32 plane", op.name);
   void (*kern)(const TcParams) = nullptr;
@@ -885,8 +912,10 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
   for (const TcOp& o : ops) full_rate = std::max(full_rate, o.rate_out);
   // residual taken from the activated fp16 plane (no fp32 residual plane) in every stage but the full-rate one
   auto res16_ok = [&](const TcOp& c) {
-    return tc_res16_enabled() && c.is_conv && c.tc.use_tc && !c.tc.x3 && c.res >= 0 && c.res < nb && c.taps.stride == 1 &&
-           c.rate_out < full_rate;
+    // 3-term-split layers take the residual from the hi/lo plane their pair's first conv reads anyway (hi + lo carries 22 bits:
+    // FP32-equivalent), in every stage; plain fp16 layers from the activated fp16 plane in every stage but the full-rate one
+    if (!(tc_res16_enabled() && c.is_conv && c.tc.use_tc && c.res >= 0 && c.res < nb && c.taps.stride == 1)) return false;
+    return c.tc.x3 ? tc_x3_res16_enabled() : c.rate_out < full_rate;
   };
   // does a 3-term-split layer consume buffer `buf` (scanning forward from op `from` until the buffer is overwritten)?
   auto wants_hilo = [&](int buf, int from) {
@@ -970,7 +999,11 @@ int tc_forward(const std::vector<TcOp>& ops, const std::vector<TcBufReq>& bufs, 
     const TcOp& oop = fuse ? ops[i + 1] : op;  // the op whose outputs this launch produces
     const char* fused_x16 = fuse ? p16[map16[op.src]] : nullptr;
     const bool use_res16 = res16_ok(oop);
-    const TRef res16 = use_res16 ? make_ref(p16[map16[oop.res]], LAYOUT_F16B, oop.cout, Lout) : TRef{};
+    TRef res16 = use_res16 ? make_ref(p16[map16[oop.res]], LAYOUT_F16B, oop.cout, Lout) : TRef{};
+    if (use_res16 && cur16[map16[oop.res]].hilo) {  // the residual buffer currently holds a hi/lo plane (3-term-split consumers)
+      res16.C = cur16[map16[oop.res]].C;
+      res16.hilo = 1;
+    }
     const float res_slope = use_res16 ? plane_slope[map16[oop.res]] : 1.f;
     const TRef res32 = (oop.res >= 0 && !use_res16) ? make_ref(p32[map32[oop.res]], LAYOUT_F32B, oop.cout, Lout) : TRef{};
     const char* fused_x32 = (fuse_kind[i] == 2) ? p32[map32[op.src]] : nullptr;

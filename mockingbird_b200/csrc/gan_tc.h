@@ -101,6 +101,9 @@ struct TcPairParams {
 };
 bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p);
 int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st);
+// gan_tc_pair32s.cu: fp32-input pair with the residual / result rows kept in shared memory (bulk-TMA in, bulk-TMA out)
+bool tc_pair32s_eligible(const TcPairParams& p);
+int launch_tc_pair32s(const TcPairParams& p, int B, cudaStream_t st, bool* done);
 
 int tc_debug_layer(const TcOp& op, const char* tc_arena, const float* x, const float* residual, int B, int Lin,
                    float* y, void* workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -123,5 +123,18 @@ __device__ __forceinline__ void add_res16(float* v, const uint4& pk, float inv) 
 }
 
 
+// same from a hi/lo plane: y = hi + lo (22 significant bits)
+__device__ __forceinline__ void add_res16_hilo(float* v, const uint4& ph, const uint4& pl, float inv) {
+  const __half2* h = reinterpret_cast<const __half2*>(&ph);
+  const __half2* l = reinterpret_cast<const __half2*>(&pl);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 fh = __half22float2(h[e]), fl = __half22float2(l[e]);
+    const float y0 = fh.x + fl.x, y1 = fh.y + fl.y;
+    v[2 * e + 0] += y0 >= 0.f ? y0 : y0 * inv;
+    v[2 * e + 1] += y1 >= 0.f ? y1 : y1 * inv;
+  }
+}
+
 }  // namespace tcdev
 }  // namespace mb

@@ -536,6 +536,11 @@ bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
 }
 
 int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
+  if (tc_pair32s_eligible(p)) {
+    bool done = false;
+    int rc = launch_tc_pair32s(p, B, st, &done);
+    if (rc != MB_OK || done) return rc;
+  }
   p.tiles_per_utt = (p.L + p.M_out - 1) / p.M_out;
   p.n_work = B * p.tiles_per_utt;
   static const int split = [] {
