@@ -76,6 +76,8 @@ struct TcPairParams {
   uint32_t s32_stage_bytes, s32_off;
   int s32_stages;
   int s32_pieces;            // row pieces of the fp32 staging window (one mbarrier each): 2 or 4
+  int s32_r0;                // > 0: two UNEQUAL pieces, window rows [0, s32_r0) and [s32_r0, W1) (RT kernels: piece = halo + whole row tiles)
+  int rt;                    // 1: residual preloaded into the second accumulator by the converter warps (tc_pair_kernel<..., RT = true>)
   const float* x32;
   float slope_in;            // leaky-relu applied to the input by the converter (c1's in_slope)
   const __half* x16;
@@ -98,6 +100,7 @@ struct TcPairParams {
   float div;
   const int32_t* lengths;
   int len_mul;
+  long long* trace;          // debug (MB_TC_PAIR_TRACE): clock64 stamps of CTA 0's roles, [role 4][item 64][event 8]
 };
 bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p);
 int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st);

@@ -20,6 +20,8 @@
 // read or written: 420 MB instead of 630 MB of HBM traffic per pair at C = 32, L = 51 200, B = 32.
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
+#include <vector>
 
 #include "gan_tc.h"
 #include "gan_tc_dev.cuh"
@@ -31,16 +33,25 @@ namespace {
 
 using namespace tcdev;
 
-constexpr int kCvtWarps = 2;
-__host__ __device__ constexpr int pair_threads(int ew, bool f32in) { return 64 + 32 * ew + (f32in ? 32 * kCvtWarps : 0); }
+// converter warps of the F32IN variants: two, or four (one per TMEM lane quarter) when they also preload the residual into TMEM
+__host__ __device__ constexpr int pair_threads(int ew, bool f32in, int cv = 2) { return 64 + 32 * ew + (f32in ? 32 * cv : 0); }
 
 // EW epilogue warps (8 or 16: EW/4 groups, each covering the four TMEM lane quarters), UC accumulator columns per epilogue
 // unit (32, or 16 so that sixteen warps fit the register file: 640 threads x <= 102 registers).  More epilogue warps keep
 // more residual loads / stores in flight: the pair kernels are bound by epilogue memory-level parallelism
 // (profiles/r02_layers_split{0,1}.tsv: halving the warps per epilogue role cost 30-50 %).
-template <int N, int MT, int CW, bool F32IN, int EW = 8, int UC = 32>
-__global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(const __grid_constant__ TcPairParams p) {
+//
+// RT (F32IN only, "residual through TMEM"): the second epilogue of the F32IN kernel used to re-read the fp32 residual rows from L2 and
+// stalled on that load (profiles/r02_pair32_k3_summary.txt).  With RT the four converter warps, which have the fp32 window in
+// shared memory anyway, write the residual rows into the second accumulator with tcgen05.st before MMA2 runs, and MMA2 accumulates
+// on top (enable-input-d = 1 from its first instruction): acc2 = x + c2(...).  E2 then only adds the bias and stores.
+// CV = converter warps (F32IN).  The role timelines (tools/trace_pair.sh, profiles/r02_pair32_trace_*.txt) show the two converter
+// warps busy ~9 000 of the ~10 000 cycles an item takes, but four warps do not shorten the item (see MB_TC_PAIR_CV below).
+template <int N, int MT, int CW, bool F32IN, int EW = 8, int UC = 32, bool RT = false, int CV = 2>
+__global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel(const __grid_constant__ TcPairParams p) {
+  static_assert(!RT || (F32IN && N == 32 && CV == 4), "RT: fp32-input pairs at 32 channels, one converter warp per TMEM lane quarter");
   constexpr int kEpiWarps = EW;
+  constexpr int kCvtWarps = CV;
   constexpr uint32_t ROWB = CW * 2;
   constexpr int NK16 = CW / 16;
   constexpr uint32_t MT_STEP = (128u * ROWB) >> 4;
@@ -68,10 +79,15 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
   uint64_t* s32_full = bars + 18;      // [4]  (F32IN: fp32 staging of the input window, p.s32_pieces row pieces)
   uint64_t* s32_empty = bars + 22;     // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint64_t* res_full = bars + 28;      // [2]  (RT: residual rows stored into acc2[i])
   uint8_t* s32_base = smem + p.s32_off;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // debug timeline of CTA 0 (p.trace != nullptr only under MB_TC_PAIR_TRACE): one stamping thread per role
+  auto stamp = [&](int role, int it, int ev) {
+    if (p.trace && blockIdx.x == 0 && it < 64) p.trace[(role * 64 + it) * 8 + ev] = clock64();
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -89,6 +105,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
       mbar_init(&a2_empty[i], 1);
       mbar_init(&acc2_full[i], 1);
       mbar_init(&acc2_empty[i], p.epi_split ? 16 * kEpiWarps : 32 * kEpiWarps);
+      mbar_init(&res_full[i], 32 * kCvtWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -110,6 +127,9 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
 
   const int n_items = (p.n_work > (int)blockIdx.x) ? (p.n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int halo = p.h1 + p.h2;
+  // fp32 staging pieces (F32IN): piece hf holds window rows [piece_lo(hf), piece_lo(hf) + piece_rows(hf)) as [N/4][rows][16 B]
+  auto piece_lo = [&](int hf) { return p.s32_r0 > 0 ? (hf ? p.s32_r0 : 0) : hf * (p.W1 / p.s32_pieces); };
+  auto piece_rows = [&](int hf) { return p.s32_r0 > 0 ? (hf ? p.W1 - p.s32_r0 : p.s32_r0) : p.W1 / p.s32_pieces; };
 
   if (warp == 0) {
     // ===================== copy producer =====================
@@ -126,10 +146,12 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
           // the fp32 window is staged in p.s32_pieces row pieces (one barrier each): while the converter drains one piece the
           // copies of the others are in flight
           const int g0 = m0 - halo;
-          const int HW = p.W1 / p.s32_pieces;
           for (int hf = 0; hf < p.s32_pieces; ++hf) {
+            const int HW = piece_rows(hf);
+            stamp(0, it, 2 * hf);
             mbar_wait(&s32_empty[hf], (it & 1) ^ 1);
-            const int r0 = g0 + hf * HW;
+            stamp(0, it, 2 * hf + 1);
+            const int r0 = g0 + piece_lo(hf);
             const int lo = r0 < 0 ? 0 : r0;
             const int hi = (r0 + HW < p.L) ? r0 + HW : p.L;
             const uint32_t qbytes = hi > lo ? (uint32_t)(hi - lo) * 16u : 0u;
@@ -166,11 +188,14 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
         mbar_wait(&w_full[1], 0);
         w2_seen = true;
       }
+      if (leader) stamp(2, j, 3);
       mbar_wait(&a2_full[aslot], aph);
-      mbar_wait(&acc2_empty[cslot], cph ^ 1);
+      if constexpr (RT) mbar_wait(&res_full[cslot], cph);  // (the converter warps waited for acc2_empty before writing the residual)
+      else mbar_wait(&acc2_empty[cslot], cph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)((2 + cslot) * MT * N);
       const uint32_t a_addr = smem_u32(a2_base + (size_t)aslot * p.a2_bytes);
+      if (leader) stamp(2, j, 4);
       if (leader) {
         for (int t = 0; t < p.k; ++t) {
           const uint64_t a0 = desc_hi + (uint64_t)((a_addr + (uint32_t)t * ROWB) >> 4);
@@ -180,10 +205,11 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
               tc_mma_f16(d_tmem + (uint32_t)(mt * N), a0 + (uint64_t)(2 * s + mt * MT_STEP), b0 + (uint64_t)(2 * s), idesc,
-                         (t | s) ? 1u : 0u);
+                         (RT || (t | s)) ? 1u : 0u);
         }
         tc_commit(&a2_empty[aslot]);
         tc_commit(&acc2_full[cslot]);
+        stamp(2, j, 5);
       }
     };
     for (int it = 0; it < n_items; ++it) {
@@ -196,9 +222,11 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
         mbar_wait(&w_full[0], 0);
         w1_seen = true;
       }
+      if (leader) stamp(2, it, 0);
       mbar_wait(&a1_full[slot], ph);
       mbar_wait(&acc1_empty[cslot], cph ^ 1);
       tc_fence_after();
+      if (leader) stamp(2, it, 1);
       const int delta = F32IN ? 0 : ((kPadRows + m0 - halo) & 7);  // the converter writes window row 0 at smem row 0
       const uint32_t d_tmem = tmem_base + (uint32_t)(cslot * MT * N);
       const uint32_t a_addr = smem_u32(a1_base + (size_t)slot * p.a1_stage_bytes);
@@ -215,6 +243,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
         }
         tc_commit(&a1_empty[slot]);
         tc_commit(&acc1_full[cslot]);
+        stamp(2, it, 2);
       }
       if (it > 0) mma2(it - 1);
     }
@@ -228,15 +257,20 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
       const int m0 = (work - b * p.tiles_per_utt) * p.M_out;
       const int valid = p.lengths ? min(p.L, p.lengths[b] * p.len_mul) : p.L;
       const int aslot = it % p.a1_stages, aph = (it / p.a1_stages) & 1;
+      if (tid == 0) stamp(1, it, 0);
       mbar_wait(&a1_empty[aslot], aph ^ 1);
+      if (tid == 0) stamp(1, it, 1);
       uint8_t* a1 = a1_base + (size_t)aslot * p.a1_stage_bytes;
       const int g0 = m0 - halo;
-      const int HW = p.W1 / p.s32_pieces;
+      [[maybe_unused]] const int cslot = it & 1, cph = (it >> 1) & 1;
+      [[maybe_unused]] const int quarter = warp & 3;
       for (int hf = 0; hf < p.s32_pieces; ++hf) {
+        const int HW = piece_rows(hf), j0 = piece_lo(hf);
         mbar_wait(&s32_full[hf], it & 1);
+        if (tid == 0 && hf < 2) stamp(1, it, 2 + 2 * hf);
         const uint8_t* s32 = s32_base + (size_t)hf * p.s32_stage_bytes;
         for (int jj = tid; jj < HW; jj += 32 * kCvtWarps) {
-          const int j = hf * HW + jj;
+          const int j = j0 + jj;
           const int g = g0 + j;
           const bool live = (g >= 0 && g < valid);
           const int sw = f16_swz(CW, j);
@@ -258,10 +292,50 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
             *reinterpret_cast<uint4*>(a1 + (size_t)j * ROWB + ((c ^ sw) << 4)) = pk;
           }
         }
+        if (hf == p.s32_pieces - 1) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.shared -> visible to the UMMA operand fetch
+          mbar_arrive(&a1_full[aslot]);
+        }
+        if constexpr (RT) {
+          // residual rows of the row tiles this piece covers (window rows halo + i) -> acc2[it & 1]; one TMEM lane quarter per
+          // converter warp.  The piece boundary is halo + a whole number of row tiles (tc_pair_plan), so a tile never straddles.
+          if (hf == 0) {
+            mbar_wait(&acc2_empty[cslot], cph ^ 1);  // E2(it - 2) has drained this accumulator
+            tc_fence_after();
+            if (tid == 0) stamp(1, it, 6);
+          }
+          const int mt_lo = hf * (MT / p.s32_pieces), mt_hi = (hf + 1) * (MT / p.s32_pieces);
+#pragma unroll 1
+          for (int mt = mt_lo; mt < mt_hi; ++mt) {
+            const int i = mt * 128 + quarter * 32 + lane;
+            const int jj = halo + i - j0;
+            const bool inb = (i < p.M_out) && (m0 + i < p.L);
+            uint32_t r[32];
+            if (inb) {
+#pragma unroll
+              for (int q = 0; q < N / 4; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(s32 + ((size_t)q * HW + jj) * 16);
+                r[4 * q + 0] = __float_as_uint(v.x);
+                r[4 * q + 1] = __float_as_uint(v.y);
+                r[4 * q + 2] = __float_as_uint(v.z);
+                r[4 * q + 3] = __float_as_uint(v.w);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) r[e] = 0u;
+            }
+            tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(((2 + cslot) * MT + mt) * N), r);
+          }
+        }
         mbar_arrive(&s32_empty[hf]);
+        if (tid == 0 && hf < 2) stamp(1, it, 3 + 2 * hf);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.shared -> visible to the UMMA operand fetch
-      mbar_arrive(&a1_full[aslot]);
+      if constexpr (RT) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(&res_full[cslot]);
+        if (tid == 0) stamp(1, it, 7);
+      }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -284,9 +358,11 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
       const int valid = p.lengths ? min(p.L, p.lengths[b] * p.len_mul) : p.L;
       const int cslot = it & 1, cph = (it >> 1) & 1;
       const int aslot = it % p.a2_stages, aph = (it / p.a2_stages) & 1;
+      if (warp == 2 && lane == 0) stamp(3, it, 0);
       mbar_wait(&acc1_full[cslot], cph);
       mbar_wait(&a2_empty[aslot], aph ^ 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) stamp(3, it, 1);
       uint8_t* a2 = a2_base + (size_t)aslot * p.a2_bytes;
       for (int u = ufirst; u < NUNITS; u += ustride) {
         const int mt = u / UPT;
@@ -323,6 +399,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // st.shared -> visible to the UMMA operand fetch
       mbar_arrive(&a2_full[aslot]);
       mbar_arrive(&acc1_empty[cslot]);
+      if (warp == 2 && lane == 0) stamp(3, it, 2);
     };
 
     constexpr int UPG = (NUNITS + 1) / 2;  // units per epilogue group
@@ -333,6 +410,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
       const int valid = p.lengths ? min(p.L, p.lengths[b] * p.len_mul) : p.L;
       const int cslot = it & 1, cph = (it >> 1) & 1;
       bool waited = false;
+      if (warp == 2 && lane == 0) stamp(3, it, 3);
 #pragma unroll
       for (int ui = 0; ui < NUNITS; ++ui) {
         const int u = ufirst + ustride * ui;
@@ -346,7 +424,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
         const size_t i32 = ((size_t)b * C4 + (col0 >> 2)) * p.L + lo;
         float4 rv[UC / 4], ov[UC / 4];
         uint4 rh[UC / 8];
-        if (inb && p.res32) {
+        if (!RT && inb && p.res32) {
 #pragma unroll
           for (int g = 0; g < UC / 4; ++g) rv[g] = reinterpret_cast<const float4*>(p.res32)[i32 + (size_t)g * p.L];
         }
@@ -365,6 +443,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
           mbar_wait(&acc2_full[cslot], cph);
           tc_fence_after();
           waited = true;
+          if (warp == 2 && lane == 0) stamp(3, it, 4);
         }
         uint32_t raw[UC];
         tmem_ld<UC>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(((2 + cslot) * MT + mt) * N + col0), raw);
@@ -372,7 +451,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
         float v[UC];
 #pragma unroll
         for (int e = 0; e < UC; ++e) v[e] = __uint_as_float(raw[e]) + bias2_s[col0 + e];
-        if (p.res32) {
+        if (!RT && p.res32) {
 #pragma unroll
           for (int g = 0; g < UC / 4; ++g) {
             v[4 * g + 0] += rv[g].x; v[4 * g + 1] += rv[g].y; v[4 * g + 2] += rv[g].z; v[4 * g + 3] += rv[g].w;
@@ -443,6 +522,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN), 1) tc_pair_kernel(con
       }
       tc_fence_before();
       mbar_arrive(&acc2_empty[cslot]);
+      if (warp == 2 && lane == 0) stamp(3, it, 5);
     };
 
     if (p.epi_split) {
@@ -473,6 +553,16 @@ constexpr uint32_t kSmemMax = 227 * 1024;
 
 }  // namespace
 
+// MB_TC_PAIR_RT=0: fp32-input pairs never preload their residual into TMEM (the second epilogue re-reads it from L2); the unequal
+// staging pieces the RT kernels need are planned whenever the switch is not 0 (the other kernels take any piece geometry)
+bool tc_pair_rt_enabled() {
+  static const int on = [] {
+    const char* e = getenv("MB_TC_PAIR_RT");
+    return e ? atoi(e) : 2;
+  }();
+  return on != 0;
+}
+
 bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
   if (C != 64 && C != 32) return false;
   if (f32in && C != 32) return false;  // instance list below
@@ -502,9 +592,17 @@ bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
         const int v = e ? atoi(e) : 2;
         return v == 4 ? 4 : 2;
       }();
-      const uint32_t s32b = f32in ? (uint32_t)align_up((size_t)(W1 / pieces) * C * 4, 1024) : 0u;  // one row piece (W1 % 16 == 0)
-      const uint32_t total = pieces * s32b + st[1] * a1b + st[2] * a2b + 2 * wbytes + 1024 + 1024;
-      p->s32_pieces = pieces;
+      // RT kernels: two unequal pieces cut at halo + half the row tiles (so that a tile's residual rows live in one piece)
+      const bool rt = f32in && tc_pair_rt_enabled();
+      const int rt_pieces = mt >= 2 ? 2 : 1;
+      const int r0 = (rt && rt_pieces == 2) ? (h1 + h2 + 128 * (mt / 2)) : 0;
+      const int np = rt ? rt_pieces : pieces;
+      const int piece_max = r0 > 0 ? (r0 > W1 - r0 ? r0 : W1 - r0) : W1 / np;
+      const uint32_t s32b = f32in ? (uint32_t)align_up((size_t)piece_max * C * 4, 1024) : 0u;  // one row piece (W1 % 16 == 0)
+      const uint32_t total = np * s32b + st[1] * a1b + st[2] * a2b + 2 * wbytes + 1024 + 1024;
+      p->s32_pieces = np;
+      p->s32_r0 = r0;
+      p->rt = rt ? 1 : 0;
       if (total > usable) continue;
       p->f32in = f32in ? 1 : 0;
       p->s32_stage_bytes = s32b;
@@ -557,8 +655,39 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
     const char* e = getenv("MB_TC_PAIR_EW16");
     return e ? atoi(e) : 1;
   }();
+  static const int rt_mode = [] {
+    // MB_TC_PAIR_RT: 0 = never, 1 = every eligible fp32-input pair, 2 (default) = only k <= 3.  Measured per pair (same file):
+    // k = 3: 0.137 -> 0.122 ms; k = 7: 0.143 -> 0.174; k = 11: 0.149 -> 0.204 - with more taps the converter's wait for
+    // acc2_empty (E2 of item i - 2) sits on the critical path and the pipeline serialises.
+    const char* e = getenv("MB_TC_PAIR_RT");
+    return e ? atoi(e) : 2;
+  }();
+  static const int cv4 = [] {
+    // MB_TC_PAIR_CV: converter warps of the fp32-input kernels that do not preload the residual: 2 (default) or 4.  Measured
+    // (profiles/r02_ab_pair_{A..E}.tsv): 4 is SLOWER (stage sum 1.477 vs 1.391 ms) although the two converter warps are the busiest
+    // role of the item pipeline - every role slows down when the others run (shared LSU / shared-memory pipe), so more converter
+    // threads only take bandwidth from the MMA operand fetch and the epilogues.
+    const char* e = getenv("MB_TC_PAIR_CV");
+    return (e ? atoi(e) : 2) == 4;
+  }();
+  const bool rt = p.rt && (rt_mode == 1 || p.k <= 3) && p.f32in && p.C == 32 && p.res32 && p.res32 == p.x32 && !p.res16;
   int threads = pair_threads(8, p.f32in != 0);
-  if (ew16 && p.MT >= 2) {
+  if (rt) {
+    threads = pair_threads(8, true, 4);
+    if (p.MT == 4) kern = tc_pair_kernel<32, 4, 32, true, 8, 32, true, 4>;
+    else if (p.MT == 2) kern = tc_pair_kernel<32, 2, 32, true, 8, 32, true, 4>;
+    else if (p.MT == 1) kern = tc_pair_kernel<32, 1, 32, true, 8, 32, true, 4>;
+  } else if (p.f32in && cv4 && p.C == 32 && p.MT >= 2) {
+    if (ew16) {
+      threads = pair_threads(16, true, 4);
+      if (p.MT == 4) kern = tc_pair_kernel<32, 4, 32, true, 16, 16, false, 4>;
+      else kern = tc_pair_kernel<32, 2, 32, true, 16, 16, false, 4>;
+    } else {
+      threads = pair_threads(8, true, 4);
+      if (p.MT == 4) kern = tc_pair_kernel<32, 4, 32, true, 8, 16, false, 4>;
+      else kern = tc_pair_kernel<32, 2, 32, true, 8, 16, false, 4>;
+    }
+  } else if (ew16 && p.MT >= 2) {
     threads = pair_threads(16, p.f32in != 0);
     if (p.f32in && p.C == 32 && p.MT == 4) kern = tc_pair_kernel<32, 4, 32, true, 16, 16>;
     else if (p.f32in && p.C == 32 && p.MT == 2) kern = tc_pair_kernel<32, 2, 32, true, 16, 16>;
@@ -595,8 +724,41 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // debug: MB_TC_PAIR_TRACE=<file> MB_TC_PAIR_TRACE_K=<k> dumps CTA 0's role timeline of the first fp32-input launch with k taps
+  static const char* trace_path = getenv("MB_TC_PAIR_TRACE");
+  static bool traced = false;
+  long long* trace_dev = nullptr;
+  p.trace = nullptr;
+  if (trace_path && !traced && p.f32in) {
+    const char* ek = getenv("MB_TC_PAIR_TRACE_K");
+    static int skip = getenv("MB_TC_PAIR_TRACE_SKIP") ? atoi(getenv("MB_TC_PAIR_TRACE_SKIP")) : 0;  // matching launches to let pass
+    if ((!ek || atoi(ek) == p.k) && skip-- <= 0) {
+      traced = true;
+      MB_CUDA_CHECK(cudaMalloc(&trace_dev, 4 * 64 * 8 * sizeof(long long)));
+      MB_CUDA_CHECK(cudaMemsetAsync(trace_dev, 0, 4 * 64 * 8 * sizeof(long long), st));
+      p.trace = trace_dev;
+    }
+  }
   MB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
   count_launch();
+  if (trace_dev) {
+    std::vector<long long> host(4 * 64 * 8);
+    MB_CUDA_CHECK(cudaStreamSynchronize(st));
+    MB_CUDA_CHECK(cudaMemcpy(host.data(), trace_dev, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(trace_dev);
+    p.trace = nullptr;
+    if (FILE* f = fopen(trace_path, "w")) {
+      fprintf(f, "# k=%d d1=%d MT=%d M_out=%d W1=%d a1_stages=%d a2_stages=%d threads=%d n_work=%d grid=%d\n", p.k, p.d1, p.MT, p.M_out,
+              p.W1, p.a1_stages, p.a2_stages, threads, p.n_work, grid);
+      for (int r = 0; r < 4; ++r)
+        for (int it = 0; it < 64; ++it) {
+          fprintf(f, "%d %d", r, it);
+          for (int e = 0; e < 8; ++e) fprintf(f, " %lld", host[(r * 64 + it) * 8 + e]);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+  }
   return MB_OK;
 }
 

@@ -8,8 +8,9 @@ call with ``mel [B, 80, T]`` -> ``wav [B, 1, T*hop]``.  All arithmetic runs in t
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional
+from typing import Dict, List, Optional, Sequence
 
+import numpy as np
 import torch
 
 from .. import _lib
@@ -295,3 +296,87 @@ class GanGenerator:
                 self._handle = C.c_void_p()
         except Exception:
             pass
+
+
+_pinned: Dict[str, torch.Tensor] = {}
+_D2H_PIECE = 1 << 18  # smallest D2H piece, elements (1 MiB)
+
+
+def _pinned_buffer(name: str, numel: int, dtype=torch.float32) -> torch.Tensor:
+    """grow-only pinned staging buffers (cudaHostAlloc per call costs more than the copies it serves)"""
+    buf = _pinned.get(name)
+    if buf is None or buf.numel() < numel:
+        buf = torch.empty(max(numel, 1), dtype=dtype).pin_memory()
+        _pinned[name] = buf
+    return buf
+
+
+def infer_waveforms_batched(generator, device, mels: Sequence[np.ndarray], batch_size: int = 32) -> List[np.ndarray]:
+    """Shared body of hifigan / fregan ``infer_waveforms``: length-sorted padded batches, each result equal to the per-utterance
+    call (padding is masked at every layer on the device).  All batches are enqueued back to back (pinned H2D -> forward -> pinned
+    D2H) and the host waits once at the end.  Host work is kept off the critical path (tools/time_e2e_host.py, cfg 2): the mels are
+    packed into the pinned staging with numpy slice assignments (0.30 -> 0.1 ms for 32 utterances), the lengths travel in a
+    pinned block too, and the copy out of the (reused) staging buffer (0.39 ms for 6.5 MB) overlaps the D2H transfer piece by piece."""
+    n_mels = 80  # hifigan/models.py:99, fregan/generator.py hard-code 80 mel channels
+    order = sorted(range(len(mels)), key=lambda i: -mels[i].shape[1])
+    out: List[Optional[np.ndarray]] = [None] * len(mels)
+    hop = generator.hop
+    batches = []
+    n_in = n_out = n_len = 0
+    for s in range(0, len(order), batch_size):
+        idx = order[s:s + batch_size]
+        tmax = max(mels[i].shape[1] for i in idx)
+        batches.append((idx, tmax, n_in, n_out, n_len))
+        n_in += len(idx) * n_mels * tmax
+        n_out += len(idx) * tmax * hop
+        n_len += len(idx)
+    host_in = _pinned_buffer("in", n_in)
+    host_out = _pinned_buffer("out", n_out)
+    host_len = _pinned_buffer("len", n_len, torch.int32)
+    in_np, len_np = host_in.numpy(), host_len.numpy()
+    pieces = []
+    for idx, tmax, o_in, o_out, o_len in batches:
+        if tmax == 0:
+            continue
+        nb = len(idx)
+        hin = in_np[o_in:o_in + nb * n_mels * tmax].reshape(nb, n_mels, tmax)
+        lens = [mels[i].shape[1] for i in idx]
+        if lens[-1] == tmax:  # (sorted: the last one is the shortest) equal lengths: one stacked copy
+            np.stack([np.asarray(mels[i]) for i in idx], out=hin, casting="unsafe")
+        else:
+            for r, i in enumerate(idx):
+                t = lens[r]
+                hin[r, :, :t] = mels[i]
+                if t < tmax:
+                    hin[r, :, t:] = 0.0
+        len_np[o_len:o_len + nb] = lens
+        dev = host_in[o_in:o_in + nb * n_mels * tmax].view(nb, n_mels, tmax).to(device, non_blocking=True)
+        dlen = host_len[o_len:o_len + nb].to(device, non_blocking=True)
+        wav = generator(dev, lengths=dlen)
+        # D2H in a few pieces, an event after each: the host copies piece i out of the (reused) staging buffer while piece
+        # i + 1 is still on the wire
+        flat = wav.view(-1)
+        n = flat.numel()
+        step = max(_D2H_PIECE, -(-n // 8))
+        for a in range(0, n, step):
+            b = min(n, a + step)
+            host_out[o_out + a:o_out + b].copy_(flat[a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            pieces.append((ev, o_out + a, o_out + b))
+    # ONE pass out of the staging buffer into a block this call owns (single-threaded on purpose: a multi-threaded torch copy
+    # spins up one OpenMP thread per visible core and stalls for milliseconds under a container CPU quota); results are views of it
+    block = np.empty(n_out, np.float32)
+    out_np = host_out.numpy()
+    for ev, a, b in pieces:
+        ev.synchronize()
+        block[a:b] = out_np[a:b]
+    for idx, tmax, o_in, o_out, o_len in batches:
+        if tmax == 0:
+            for i in idx:
+                out[i] = np.zeros(0, np.float32)
+            continue
+        wav = block[o_out:o_out + len(idx) * tmax * hop].reshape(len(idx), tmax * hop)
+        for r, i in enumerate(idx):
+            out[i] = wav[r, : mels[i].shape[1] * hop]
+    return out  # type: ignore[return-value]

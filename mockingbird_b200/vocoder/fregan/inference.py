@@ -17,6 +17,7 @@ import torch
 
 from ... import _lib
 from ...utils import AttrDict
+from .._gan import infer_waveforms_batched
 from .models import DEFAULT_CONFIG as DEFAULT_CONFIG_16K, FreGAN as Generator
 
 generator = None  # type: Optional[Generator]
@@ -100,23 +101,7 @@ def infer_waveform(mel, progress_callback=None):
 
 def infer_waveforms(mels: Sequence[np.ndarray], batch_size: int = 32) -> List[np.ndarray]:
     """Vocode many utterances as length-sorted padded batches; each result equals the per-utterance
-    call (padding is masked at every layer on the device)."""
+    call (padding is masked at every layer on the device).  See ``_gan.infer_waveforms_batched``."""
     if generator is None:
         raise Exception("Please load fre-gan in memory before using it")
-    order = sorted(range(len(mels)), key=lambda i: -mels[i].shape[1])
-    out: List[Optional[np.ndarray]] = [None] * len(mels)
-    hop = generator.hop
-    for s in range(0, len(order), batch_size):
-        idx = order[s:s + batch_size]
-        tmax = max(mels[i].shape[1] for i in idx)
-        host = torch.zeros(len(idx), 80, tmax, dtype=torch.float32).pin_memory()
-        lens = torch.empty(len(idx), dtype=torch.int32)
-        for r, i in enumerate(idx):
-            t = mels[i].shape[1]
-            host[r, :, :t] = torch.as_tensor(np.asarray(mels[i]), dtype=torch.float32)
-            lens[r] = t
-        dev = host.to(_device, non_blocking=True)
-        wav = generator(dev, lengths=lens.to(_device)).squeeze(1).cpu().numpy()
-        for r, i in enumerate(idx):
-            out[i] = wav[r, : mels[i].shape[1] * hop].copy()
-    return out  # type: ignore[return-value]
+    return infer_waveforms_batched(generator, _device, mels, batch_size)

@@ -17,6 +17,7 @@ import torch
 
 from ... import _lib
 from ...utils import AttrDict
+from .._gan import infer_waveforms_batched
 from .models import DEFAULT_CONFIG_16K, Generator
 
 generator = None  # type: Optional[Generator]
@@ -98,59 +99,9 @@ def infer_waveform(mel, progress_callback=None):
     return audio, output_sample_rate
 
 
-_pinned: dict = {}
-
-
-def _pinned_buffer(name: str, numel: int) -> torch.Tensor:
-    """grow-only pinned staging buffers (cudaHostAlloc per call costs more than the copies it serves)"""
-    buf = _pinned.get(name)
-    if buf is None or buf.numel() < numel:
-        buf = torch.empty(max(numel, 1), dtype=torch.float32).pin_memory()
-        _pinned[name] = buf
-    return buf
-
-
 def infer_waveforms(mels: Sequence[np.ndarray], batch_size: int = 32) -> List[np.ndarray]:
     """Vocode many utterances as length-sorted padded batches; each result equals the per-utterance
-    call (padding is masked at every layer on the device).  All batches are enqueued back to back
-    (pinned H2D -> forward -> pinned D2H) and the host waits once at the end."""
+    call (padding is masked at every layer on the device).  See ``_gan.infer_waveforms_batched``."""
     if generator is None:
         raise Exception("Please load hifi-gan in memory before using it")
-    order = sorted(range(len(mels)), key=lambda i: -mels[i].shape[1])
-    out: List[Optional[np.ndarray]] = [None] * len(mels)
-    hop = generator.hop
-    batches = []
-    n_in = n_out = 0
-    for s in range(0, len(order), batch_size):
-        idx = order[s:s + batch_size]
-        tmax = max(mels[i].shape[1] for i in idx)
-        batches.append((idx, tmax, n_in, n_out))
-        n_in += len(idx) * 80 * tmax
-        n_out += len(idx) * tmax * hop
-    host_in = _pinned_buffer("in", n_in)
-    host_out = _pinned_buffer("out", n_out)
-    for idx, tmax, o_in, o_out in batches:
-        if tmax == 0:
-            continue
-        hin = host_in[o_in:o_in + len(idx) * 80 * tmax].view(len(idx), 80, tmax)
-        lens = torch.empty(len(idx), dtype=torch.int32)
-        for r, i in enumerate(idx):
-            t = mels[i].shape[1]
-            hin[r, :, :t] = torch.as_tensor(np.asarray(mels[i]), dtype=torch.float32)
-            if t < tmax:
-                hin[r, :, t:] = 0.0
-            lens[r] = t
-        dev = hin.to(_device, non_blocking=True)
-        wav = generator(dev, lengths=lens.to(_device))
-        host_out[o_out:o_out + len(idx) * tmax * hop].view(len(idx), 1, tmax * hop).copy_(wav, non_blocking=True)
-    torch.cuda.current_stream(_device).synchronize()
-    block = np.array(host_out[:n_out].numpy(), copy=True)  # ONE copy out of the reused pinned staging; results are views of it
-    for idx, tmax, o_in, o_out in batches:
-        if tmax == 0:
-            for i in idx:
-                out[i] = np.zeros(0, np.float32)
-            continue
-        wav = block[o_out:o_out + len(idx) * tmax * hop].reshape(len(idx), tmax * hop)
-        for r, i in enumerate(idx):
-            out[i] = wav[r, : mels[i].shape[1] * hop]
-    return out  # type: ignore[return-value]
+    return infer_waveforms_batched(generator, _device, mels, batch_size)
