@@ -77,6 +77,8 @@ struct TcPairParams {
   int s32_stages;
   int s32_pieces;            // row pieces of the fp32 staging window (one mbarrier each): 2 or 4
   int s32_r0;                // > 0: two UNEQUAL pieces, window rows [0, s32_r0) and [s32_r0, W1) (RT kernels: piece = halo + whole row tiles)
+  int wstream, wstages;      // 1: both weight sets are streamed tap by tap through a ring of wstages slabs (C = 64, k >= 7: they do not fit beside
+                             // double-buffered operands); 0: both resident for the whole kernel
   int rt;                    // 1: residual preloaded into the second accumulator by the converter warps (tc_pair_kernel<..., RT = true>)
   const float* x32;
   float slope_in;            // leaky-relu applied to the input by the converter (c1's in_slope)

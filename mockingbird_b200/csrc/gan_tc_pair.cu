@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel
   uint64_t* s32_empty = bars + 22;     // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   uint64_t* res_full = bars + 28;      // [2]  (RT: residual rows stored into acc2[i])
+  uint64_t* wr_full = bars + 32;       // [8]  (wstream: weight slab ring)
+  uint64_t* wr_empty = bars + 40;      // [8]
   uint8_t* s32_base = smem + p.s32_off;
 
   const int warp = threadIdx.x >> 5;
@@ -106,6 +108,10 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel
       mbar_init(&acc2_full[i], 1);
       mbar_init(&acc2_empty[i], p.epi_split ? 16 * kEpiWarps : 32 * kEpiWarps);
       mbar_init(&res_full[i], 32 * kCvtWarps);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&wr_full[i], 1);
+      mbar_init(&wr_empty[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -134,10 +140,23 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel
   if (warp == 0) {
     // ===================== copy producer =====================
     if (lane == 0) {
-      mbar_expect_tx(&w_full[0], (uint32_t)p.k * SLAB);
-      bulk_g2s(smem_u32(w1_base), p.w1, (uint32_t)p.k * SLAB, &w_full[0]);
-      mbar_expect_tx(&w_full[1], (uint32_t)p.k * SLAB);
-      bulk_g2s(smem_u32(w2_base), p.w2, (uint32_t)p.k * SLAB, &w_full[1]);
+      if (!p.wstream) {
+        mbar_expect_tx(&w_full[0], (uint32_t)p.k * SLAB);
+        bulk_g2s(smem_u32(w1_base), p.w1, (uint32_t)p.k * SLAB, &w_full[0]);
+        mbar_expect_tx(&w_full[1], (uint32_t)p.k * SLAB);
+        bulk_g2s(smem_u32(w2_base), p.w2, (uint32_t)p.k * SLAB, &w_full[1]);
+      }
+      // wstream: the k slabs of a weight set go through the ring in exactly the order the MMA warp consumes them:
+      // W1 for MMA1(it), then W2 for MMA2(it - 1)
+      int ws = 0, wph = 0;
+      auto stream = [&](const __half* w) {
+        for (int t = 0; t < p.k; ++t) {
+          mbar_wait(&wr_empty[ws], wph ^ 1);
+          mbar_expect_tx(&wr_full[ws], SLAB);
+          bulk_g2s(smem_u32(w1_base + (size_t)ws * SLAB), w + (size_t)t * (SLAB >> 1), SLAB, &wr_full[ws]);
+          if (++ws == p.wstages) { ws = 0; wph ^= 1; }
+        }
+      };
       for (int it = 0; it < n_items; ++it) {
         const int work = blockIdx.x + it * gridDim.x;
         const int b = work / p.tiles_per_utt;
@@ -167,20 +186,28 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel
           }
         } else {
           const int slot = it % p.a1_stages, ph = (it / p.a1_stages) & 1;
+          stamp(0, it, 0);
           mbar_wait(&a1_empty[slot], ph ^ 1);
+          stamp(0, it, 1);
           const uint32_t bytes = (uint32_t)p.W1 * ROWB;
           mbar_expect_tx(&a1_full[slot], bytes);
           const int row0 = (kPadRows + m0 - halo) & ~7;
           const __half* src = p.x16 + ((size_t)b * p.x_Lp + (size_t)row0) * CW;
           bulk_g2s(smem_u32(a1_base + (size_t)slot * p.a1_stage_bytes), src, bytes, &a1_full[slot]);
         }
+        if (p.wstream) {
+          stream(p.w1);
+          if (it > 0) stream(p.w2);
+        }
       }
+      if (p.wstream && n_items > 0) stream(p.w2);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint64_t desc_hi = make_desc(0, 8u * ROWB, CW == 64 ? 2u : 4u, 0);
     const bool leader = elect_one();
-    bool w1_seen = false, w2_seen = false;
+    bool w1_seen = p.wstream != 0, w2_seen = p.wstream != 0;
+    int ws = 0, wph = 0;  // weight ring position (wstream)
     auto mma2 = [&](int j) {
       const int aslot = j % p.a2_stages, aph = (j / p.a2_stages) & 1;
       const int cslot = j & 1, cph = (j >> 1) & 1;
@@ -196,17 +223,27 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel
       const uint32_t d_tmem = tmem_base + (uint32_t)((2 + cslot) * MT * N);
       const uint32_t a_addr = smem_u32(a2_base + (size_t)aslot * p.a2_bytes);
       if (leader) stamp(2, j, 4);
-      if (leader) {
-        for (int t = 0; t < p.k; ++t) {
+      for (int t = 0; t < p.k; ++t) {
+        uint32_t w_addr = smem_u32(w2_base) + (uint32_t)t * SLAB;
+        if (p.wstream) {
+          mbar_wait(&wr_full[ws], wph);
+          tc_fence_after();
+          w_addr = smem_u32(w1_base) + (uint32_t)ws * SLAB;
+        }
+        if (leader) {
           const uint64_t a0 = desc_hi + (uint64_t)((a_addr + (uint32_t)t * ROWB) >> 4);
-          const uint64_t b0 = desc_hi + (uint64_t)((smem_u32(w2_base) + (uint32_t)t * SLAB) >> 4);
+          const uint64_t b0 = desc_hi + (uint64_t)(w_addr >> 4);
 #pragma unroll
           for (int s = 0; s < NK16; ++s)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
               tc_mma_f16(d_tmem + (uint32_t)(mt * N), a0 + (uint64_t)(2 * s + mt * MT_STEP), b0 + (uint64_t)(2 * s), idesc,
                          (RT || (t | s)) ? 1u : 0u);
+          if (p.wstream) tc_commit(&wr_empty[ws]);
         }
+        if (p.wstream && ++ws == p.wstages) { ws = 0; wph ^= 1; }
+      }
+      if (leader) {
         tc_commit(&a2_empty[aslot]);
         tc_commit(&acc2_full[cslot]);
         stamp(2, j, 5);
@@ -230,17 +267,27 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel
       const int delta = F32IN ? 0 : ((kPadRows + m0 - halo) & 7);  // the converter writes window row 0 at smem row 0
       const uint32_t d_tmem = tmem_base + (uint32_t)(cslot * MT * N);
       const uint32_t a_addr = smem_u32(a1_base + (size_t)slot * p.a1_stage_bytes);
-      if (leader) {
-        for (int t = 0; t < p.k; ++t) {
+      for (int t = 0; t < p.k; ++t) {
+        uint32_t w_addr = smem_u32(w1_base) + (uint32_t)t * SLAB;
+        if (p.wstream) {
+          mbar_wait(&wr_full[ws], wph);
+          tc_fence_after();
+          w_addr = smem_u32(w1_base) + (uint32_t)ws * SLAB;
+        }
+        if (leader) {
           const uint64_t a0 = desc_hi + (uint64_t)((a_addr + (uint32_t)(delta + t * p.d1) * ROWB) >> 4);
-          const uint64_t b0 = desc_hi + (uint64_t)((smem_u32(w1_base) + (uint32_t)t * SLAB) >> 4);
+          const uint64_t b0 = desc_hi + (uint64_t)(w_addr >> 4);
 #pragma unroll
           for (int s = 0; s < NK16; ++s)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
               tc_mma_f16(d_tmem + (uint32_t)(mt * N), a0 + (uint64_t)(2 * s + mt * MT_STEP), b0 + (uint64_t)(2 * s), idesc,
                          (t | s) ? 1u : 0u);
+          if (p.wstream) tc_commit(&wr_empty[ws]);
         }
+        if (p.wstream && ++ws == p.wstages) { ws = 0; wph ^= 1; }
+      }
+      if (leader) {
         tc_commit(&a1_empty[slot]);
         tc_commit(&acc1_full[cslot]);
         stamp(2, it, 2);
@@ -563,6 +610,20 @@ bool tc_pair_rt_enabled() {
   return on != 0;
 }
 
+// MB_TC_PAIR_WSTREAM=1: the C = 64 pairs with k >= 7 stream both weight sets through an 8-slab ring (frees the shared memory for
+// MT = 2 and double-buffered operands at k = 11).  Default 0: MEASURED SLOWER (profiles/r02_layers_wstream_{0,1}.tsv: k = 7
+// 0.124 -> 0.147 ms, k = 11 0.190 -> 0.203 ms per pair; only k = 11 dilation 5 gains, 0.247 -> 0.231).  The role timeline
+// (profiles/r02_pair16_trace_wstream_k7.txt) shows the MMA warp at 87 instead of 54 cycles per MMA: a slab is re-requested only when
+// the MMAs that read it have COMPLETED, and eight slabs (~3 000 cycles of MMA work) do not cover the loaded L2 latency of the copy
+// engine, which also carries the operand windows.  A deeper ring does not fit; the real fix is a 2-CTA pair sharing one weight copy.
+bool tc_pair_wstream_enabled() {
+  static const int on = [] {
+    const char* e = getenv("MB_TC_PAIR_WSTREAM");
+    return e ? atoi(e) : 0;
+  }();
+  return on != 0;
+}
+
 bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
   if (C != 64 && C != 32) return false;
   if (f32in && C != 32) return false;  // instance list below
@@ -599,7 +660,13 @@ bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
       const int np = rt ? rt_pieces : pieces;
       const int piece_max = r0 > 0 ? (r0 > W1 - r0 ? r0 : W1 - r0) : W1 / np;
       const uint32_t s32b = f32in ? (uint32_t)align_up((size_t)piece_max * C * 4, 1024) : 0u;  // one row piece (W1 % 16 == 0)
-      const uint32_t total = np * s32b + st[1] * a1b + st[2] * a2b + 2 * wbytes + 1024 + 1024;
+      // C = 64, k >= 7: both weight sets (2 x k x 8 KB) leave no room for double-buffered operands - stream them through a ring
+      const bool wstream = !f32in && C == 64 && k >= 7 && tc_pair_wstream_enabled();
+      const int wstages = 8;
+      const uint32_t wtotal = wstream ? (uint32_t)align_up((size_t)wstages * slab, 1024) : 2 * wbytes;
+      const uint32_t total = np * s32b + st[1] * a1b + st[2] * a2b + wtotal + 1024 + 1024;
+      p->wstream = wstream ? 1 : 0;
+      p->wstages = wstages;
       p->s32_pieces = np;
       p->s32_r0 = r0;
       p->rt = rt ? 1 : 0;
@@ -623,8 +690,8 @@ bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p) {
       p->a1_off = 0;
       p->a2_off = st[1] * a1b;
       p->w1_off = p->a2_off + st[2] * a2b;
-      p->w2_off = p->w1_off + wbytes;
-      p->bias_off = p->w2_off + wbytes;
+      p->w2_off = wstream ? p->w1_off : p->w1_off + wbytes;
+      p->bias_off = p->w1_off + wtotal;
       p->bar_off = p->bias_off + 1024;
       p->s32_off = p->bar_off + 1024;
       return true;
@@ -729,7 +796,8 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
   static bool traced = false;
   long long* trace_dev = nullptr;
   p.trace = nullptr;
-  if (trace_path && !traced && p.f32in) {
+  static const int trace_f32 = getenv("MB_TC_PAIR_TRACE_F32") ? atoi(getenv("MB_TC_PAIR_TRACE_F32")) : 1;  // 0: trace an fp16-plane pair
+  if (trace_path && !traced && (p.f32in != 0) == (trace_f32 != 0)) {
     const char* ek = getenv("MB_TC_PAIR_TRACE_K");
     static int skip = getenv("MB_TC_PAIR_TRACE_SKIP") ? atoi(getenv("MB_TC_PAIR_TRACE_SKIP")) : 0;  // matching launches to let pass
     if ((!ek || atoi(ek) == p.k) && skip-- <= 0) {
