@@ -30,13 +30,14 @@ namespace {
 //   scores  = softmax_t(u); cumulative += scores; ctx = scores @ seq[b]
 constexpr int ATT_D = 128, ATT_F = 32, ATT_K = 31;
 
-__global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__ pq, const float* __restrict__ proj,
+__global__ void __launch_bounds__(512) lsa_step_kernel(const float* __restrict__ pq, const float* __restrict__ proj,
                                                        const float* __restrict__ seq, int seq_dim,
                                                        const int32_t* __restrict__ chars, float* cum,
                                                        const float* __restrict__ conv_w, const float* __restrict__ conv_b,
                                                        const float* __restrict__ Lw, const float* __restrict__ vw,
                                                        float* __restrict__ scores_out, int scores_ld, float* ctx, int Tc,
-                                                       const int* step_ptr, int step_j) {
+                                                       const int* step_ptr, int step_j, const float* __restrict__ q_in,
+                                                       const float* __restrict__ Wq, const float* __restrict__ bq) {
   extern __shared__ float sm[];
   scores_out += (size_t)step_index(step_ptr, step_j) * Tc;  // this decoder step's row of the alignment matrix
   float* s_cw = sm;                         // [32][31]
@@ -57,7 +58,22 @@ __global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__
   }
   for (int i = tid; i < ATT_D; i += blockDim.x) {
     s_v[i] = vw[i];
-    s_pq[i] = pq[(size_t)b * ATT_D + i];
+    if (!q_in) s_pq[i] = pq[(size_t)b * ATT_D + i];
+  }
+  if (q_in) {
+    // processed query pq = W q + b (lsa.py:29) computed here instead of by a GEMM launch of its own: one warp per output,
+    // lanes over k (coalesced rows of W), 128 x 128 MACs per batch row
+    const int warp = tid >> 5, lane = tid & 31, nw = (int)(blockDim.x >> 5);
+    float qv[ATT_D / 32];
+#pragma unroll
+    for (int j = 0; j < ATT_D / 32; ++j) qv[j] = q_in[(size_t)b * ATT_D + lane + 32 * j];
+    for (int o = warp; o < ATT_D; o += nw) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < ATT_D / 32; ++j) a = fmaf(Wq[(size_t)o * ATT_D + lane + 32 * j], qv[j], a);
+      for (int sh = 16; sh; sh >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sh);
+      if (lane == 0) s_pq[o] = a + bq[o];
+    }
   }
   for (int i = tid; i < ATT_F; i += blockDim.x) s_cb[i] = conv_b[i];
   for (int i = tid; i < Tc + 30; i += blockDim.x) {
@@ -77,6 +93,7 @@ __global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__
   // energies: thread = (d, t parity); u[t] = sum_d v[d] * tanh(pq[d] + proj[t][d] + sum_f L[d][f] loc[t][f])
   {
     const int d = tid & (ATT_D - 1), tg = tid >> 7, wq = (tid >> 5) & 3;
+    const int ntg = (int)(blockDim.x >> 7);  // time-step groups of 128 threads (2 at 256 threads, 4 at 512)
     float lreg[ATT_F];
 #pragma unroll
     for (int f = 0; f < ATT_F; ++f) lreg[f] = s_Lt[f * ATT_D + d];
@@ -84,16 +101,16 @@ __global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__
     const float* pb = proj + (size_t)b * Tc * ATT_D + d;
     // blocks of 8 time steps: the 8 (independent) loads of the processed memory are issued before any is used -
     // a plain loop is bound by one L2 round trip per step
-    for (int t0 = tg; t0 < Tc; t0 += 16) {
+    for (int t0 = tg; t0 < Tc; t0 += 8 * ntg) {
       float pr[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int t = t0 + 2 * j;
+        const int t = t0 + ntg * j;
         pr[j] = t < Tc ? pb[(size_t)t * ATT_D] : 0.f;
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int t = t0 + 2 * j;
+        const int t = t0 + ntg * j;
         if (t >= Tc) break;  // warp-uniform
         float pl = 0.f;
         const float* lc = s_loc + (size_t)t * ATT_F;
@@ -153,7 +170,8 @@ __global__ void __launch_bounds__(256) lsa_step_kernel(const float* __restrict__
 // 16-byte loads in flight, which one CTA per batch row cannot provide.
 __global__ void __launch_bounds__(256) lsa_ctx_kernel(const float* __restrict__ scores, int scores_ld, const float* __restrict__ seq,
                                                       int seq_dim, int Tc, float* __restrict__ ctx, const int* step_ptr,
-                                                      int step_j) {
+                                                      int step_j, __half* sa_hi, __half* sa_lo, __half* sb_hi, __half* sb_lo,
+                                                      int s_rows_pad) {
   __shared__ float4 part[4][64];
   extern __shared__ float s_sc[];
   const int b = blockIdx.y, f4 = blockIdx.x * 64 + (threadIdx.x & 63), tg = threadIdx.x >> 6;
@@ -182,6 +200,10 @@ __global__ void __launch_bounds__(256) lsa_ctx_kernel(const float* __restrict__ 
     r.z = (p0.z + p1.z) + (p2.z + p3.z);
     r.w = (p0.w + p1.w) + (p2.w + p3.w);
     reinterpret_cast<float4*>(ctx + (size_t)b * seq_dim)[f4] = r;
+    // the context is the leading K segment of two tensor-core GEMMs (attention GRU input of the NEXT step, rnn_input of this one):
+    // write their hi / lo operand chunks here instead of launching act_split twice
+    if (sa_hi) taco::store_split_quad(r, b, s_rows_pad, f4 * 4, sa_hi, sa_lo);
+    if (sb_hi) taco::store_split_quad(r, b, s_rows_pad, f4 * 4, sb_hi, sb_lo);
   }
 }
 
@@ -251,6 +273,17 @@ __global__ void fill_masks_kernel(uint8_t* m, size_t n, uint64_t seed, uint32_t 
   m[i] = (uint8_t)((o[i & 3] >> 16) & 1u);  // Bernoulli(0.5) keep flag
 }
 
+// the PreNet dropout masks of ALL decoder steps in one launch (same bits as fill_masks_kernel called with stream_id = step)
+__global__ void fill_masks_steps_kernel(uint8_t* m, size_t n_per_step, int n_steps, uint64_t seed) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_per_step * (size_t)n_steps) return;
+  const uint32_t step = (uint32_t)(g / n_per_step);
+  const size_t i = g - (size_t)step * n_per_step;
+  uint32_t o[4];
+  mb_philox4x32((uint32_t)(i >> 2), (uint32_t)(i >> 34), step, 0x7461636fu, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  m[g] = (uint8_t)((o[i & 3] >> 16) & 1u);
+}
+
 // decoder step si = (step_ptr ? *step_ptr : 0) + step_j; frame t = si * r; flags[si] = stop rule of tacotron.py:275
 __global__ void stop_flag_kernel(const float* stopv, int B, float min_stop_token, int r, int* flags, const int* step_ptr,
                                  int step_j) {
@@ -258,6 +291,40 @@ __global__ void stop_flag_kernel(const float* stopv, int B, float min_stop_token
     const int si = step_index(step_ptr, step_j);
     bool all = true;
     for (int b = 0; b < B; ++b) all = all && (stopv[b] * 10.f > min_stop_token);
+    flags[si] = (all && si * r > 10) ? 1 : 0;
+  }
+}
+
+// stop projection (sigmoid(w . [x | ctx] + b), tacotron.py:131-133) of one batch row per CTA, then - in the CTA that takes the
+// last ticket - the stop rule over all rows.  Same summation order as rowdot_kernel.
+__global__ void __launch_bounds__(256) stop_step_kernel(const GemmArgs a, int B, float min_stop_token, int r, int* flags,
+                                                        const int* step_ptr, int step_j, unsigned int* ticket) {
+  __shared__ float red[8];
+  __shared__ bool last;
+  const int m = blockIdx.x, tid = threadIdx.x;
+  float s = 0.f;
+  for (int sgi = 0; sgi < a.nseg; ++sgi) {
+    const Seg sg = a.seg[sgi];
+    for (int k = tid; k < sg.K; k += 256) s = fmaf(sg.x[(size_t)m * sg.ld + k], a.W[sg.w_off + (size_t)k * sg.w_stride], s);
+  }
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    if (a.bias) v += a.bias[0];
+    a.Y[(size_t)m * a.ldy] = 1.f / (1.f + expf(-v));
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == (unsigned int)(B - 1);
+  }
+  __syncthreads();
+  if (last && tid == 0) {
+    *ticket = 0u;
+    __threadfence();
+    const int si = step_index(step_ptr, step_j);
+    bool all = true;
+    for (int b = 0; b < B; ++b) all = all && (__ldcg(a.Y + (size_t)b * a.ldy) * 10.f > min_stop_token);
     flags[si] = (all && si * r > 10) ? 1 : 0;
   }
 }
@@ -354,11 +421,31 @@ void cbhg_slots(mb_tacotron* h, const std::string& p, int K, int cin, int ch, in
   }
 }
 
+// byte offsets (inside Ws::fsp) of the hi planes of the operand tiles the decoder kernels write for each other; lo = hi + bytes
+struct FusedSplit {
+  size_t p1, p2, p3[2], p4[2], p5, b1, b2, b3, b5, total;
+};
+FusedSplit fused_split_layout(int Bc, int proj_dims, int D, int LD) {
+  FusedSplit f{};
+  f.b1 = tc_skinny_act_bytes(Bc, proj_dims + 2 * D);
+  f.b2 = tc_skinny_act_bytes(Bc, proj_dims + D);
+  f.b3 = tc_skinny_act_bytes(Bc, 2 * LD);
+  f.b5 = tc_skinny_act_bytes(Bc, LD);
+  size_t o = 0;
+  f.p1 = o; o += 2 * f.b1;
+  f.p2 = o; o += 2 * f.b2;
+  for (int q = 0; q < 2; ++q) { f.p3[q] = o; o += 2 * f.b3; }
+  for (int q = 0; q < 2; ++q) { f.p4[q] = o; o += 2 * f.b3; }
+  f.p5 = o; o += 2 * f.b5;
+  f.total = o;
+  return f;
+}
+
 struct Ws {
   // encoder
   size_t ids, emb, m_enc, p1, x0, bank, pool, pj1, y, hw12, gi_f, gi_b, gh, hst, seq, proj, style_q, style;
   // decoder
-  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, ah_hi, ah_lo, stopv, step, flags, dmask;
+  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, ah_hi, ah_lo, fsp, stopv, step, flags, dmask;
   size_t big_hi, big_lo, big_bytes;
   // outputs / postnet
   size_t mel_all, scores_all, pbank, ppool, ppj1, ppj2, py, phw12, pgi_f, pgi_b, pgh, phst, pout, lin;
@@ -411,11 +498,18 @@ Ws ws_layout(const mb_tacotron_config& c, int B, int Tc, int steps, int r) {
   L.a_lo = take(tc_skinny_act_bytes(B > 128 ? 128 : B, 2 * c.lstm_dims) / 4);
   L.ah_hi = take(2 * tc_skinny_act_bytes(B > 128 ? 128 : B, c.decoder_dims) / 4);  // attention-GRU state tiles, 2 parities
   L.ah_lo = take(2 * tc_skinny_act_bytes(B > 128 ? 128 : B, c.decoder_dims) / 4);
+  {
+    // operand tiles written by the producing kernels (fused act_split): P1 [ctx | prenet], P2 [ctx | attn_h], P3 / P4 [x | h] of the
+    // two LSTMs (two step parities each), P5 [x]; hi and lo of each; zeroed with the attention-GRU tiles at the start of generate()
+    const int Bc = B > 128 ? 128 : B;
+    const FusedSplit f = fused_split_layout(Bc, proj_dims, c.decoder_dims, c.lstm_dims);
+    L.fsp = take(f.total / 4);
+  }
   L.stopv = take(B);
   L.step = take(64);
   const int nst = (steps + r - 1) / r;
   L.flags = take(nst);
-  L.dmask = take(((size_t)2 * B * 2 * c.decoder_dims + 3) / 4 + 64);
+  L.dmask = take(((size_t)nst * 2 * B * 2 * c.decoder_dims + 3) / 4 + 64);  // PreNet dropout masks of every decoder step
   L.mel_all = take(Mp * c.n_mels + (size_t)r * c.n_mels);
   L.scores_all = take((size_t)B * nst * Tc);
   L.pbank = take(Mp * c.postnet_K * PD);
@@ -1045,6 +1139,7 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   // ------------------------------------------------------------------ decoder loop (tacotron.py:264-275)
   MB_CUDA_CHECK(cudaMemsetAsync(ws + L.attn_h, 0, sizeof(float) * (L.dp1 - L.attn_h), st));  // states, ctx, cum
   MB_CUDA_CHECK(cudaMemsetAsync(ws + L.ah_hi, 0, sizeof(float) * (L.stopv - L.ah_hi), st));  // h0 = 0 operand tiles
+  MB_CUDA_CHECK(cudaMemsetAsync(ws + L.step, 0, sizeof(float) * 64, st));  // step counter, stop-rule ticket
   float* mel_all = ws + L.mel_all;
   MB_CUDA_CHECK(cudaMemsetAsync(mel_all, 0, sizeof(float) * ((size_t)B * steps_alloc * NM + (size_t)r * NM), st));
   int* flags = reinterpret_cast<int*>(ws + L.flags);
@@ -1053,12 +1148,35 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   const size_t dmask_n = (size_t)B * 2 * D;
   const size_t lsa_smem = sizeof(float) * (ATT_F * ATT_K + ATT_D * ATT_F + 2 * ATT_D + ATT_F + (Tc + 30) + Tc + 32 + (size_t)Tc * ATT_F + (size_t)Tc * 4);
   if (lsa_smem > 48 * 1024) MB_CUDA_CHECK(cudaFuncSetAttribute(lsa_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsa_smem));
+  if (!dec_masks) {
+    const size_t total = 2 * dmask_n * (size_t)nst;
+    fill_masks_steps_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dm, 2 * dmask_n, nst, seed);
+    MB_LAUNCH_CHECK("fill_masks_steps_kernel");
+  }
   int done_step = -1;
   std::vector<int> hflags(nst, 0);
   int checked = 0;
   // One decoder step.  The step index is (sp ? *sp : 0) + sj, resolved ON THE DEVICE by the few kernels that
   // need it (PreNet input frame and dropout masks, alignment row, mel output frames, stop flag), so the same
   // launch sequence can be captured once into a CUDA graph and replayed for every group of steps.
+  // Fused operand split (MB_TACO_SPLIT_FUSED, default 1): the five act_split launches of a step disappear - every kernel that
+  // produces an input of a tensor-core GEMM (PreNet, context, attention GRU, rnn_input, the two LSTM cells) writes the fp16 hi / lo
+  // operand chunks itself, into per-consumer tiles (the LSTM tiles ping-pong on the step parity: a cell writes h' for the next step
+  // while other CTAs of the same launch still read this step's tiles).
+  static const bool split_fused_env = [] {
+    const char* e = getenv("MB_TACO_SPLIT_FUSED");
+    return e ? atoi(e) != 0 : true;
+  }();
+  static const bool prenet_fused_env = [] {
+    const char* e = getenv("MB_TACO_PRENET_FUSED");
+    return e ? atoi(e) != 0 : true;
+  }();
+  const bool fsplit = split_fused_env && prenet_fused_env && use_tc && D % 64 == 0 && proj_dims % 256 == 0 && LD % 64 == 0 &&
+                      (r * NM) % 4 == 0 && NM <= 128 && 2 * D <= 256 && B <= 128;
+  const FusedSplit fs = fused_split_layout(B > 128 ? 128 : B, proj_dims, D, LD);
+  char* fbase = reinterpret_cast<char*>(ws + L.fsp);
+  auto fhi = [&](size_t off) { return reinterpret_cast<__half*>(fbase + off); };
+  const int f_rows_pad = B <= 64 ? 64 : 128;
   auto emit_step = [&](const int* sp, int sj) -> int {
     // PreNet on the last frame of the previous step (go frame = zeros)
     const uint8_t* m1;
@@ -1068,16 +1186,13 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       m1 = dec_masks;
       m2 = m1 + dmask_n;
       mstep = (long long)(2 * dmask_n);
-    } else {
-      fill_masks_kernel<<<(unsigned)((2 * dmask_n + 255) / 256), 256, 0, st>>>(dm, 2 * dmask_n, seed, (uint32_t)sj, sp);
-      MB_LAUNCH_CHECK("fill_masks_kernel");
+    } else {  // generated for all steps before the loop (fill_masks_steps_kernel)
       m1 = dm;
       m2 = dm + dmask_n;
+      mstep = (long long)(2 * dmask_n);
     }
-    static const bool prenet_fused = [] {
-      const char* e = getenv("MB_TACO_PRENET_FUSED");  // A/B switch: 0 = two skinny GEMM launches (round 1)
-      return e ? atoi(e) != 0 : true;
-    }();
+    const bool prenet_fused = prenet_fused_env;  // A/B switch MB_TACO_PRENET_FUSED: 0 = two skinny GEMM launches (round 1)
+    const int par = sj & 1;  // graph groups start at even steps, so the parity of (base + sj) is that of sj
     if (prenet_fused && NM <= 128 && 2 * D <= 256) {
       // both PreNet layers in one launch; frame (step * r - 1) of every utterance, step 0 = the all-zero go frame
       PrenetArgs pa;
@@ -1100,6 +1215,12 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       pa.H = 2 * D;
       pa.y = ws + L.dp2;
       pa.ldy = 2 * D;
+      if (fsplit) {  // [ctx | prenet] tiles of the attention GRU's input GEMM
+        pa.s_hi = fhi(fs.p1);
+        pa.s_lo = fhi(fs.p1 + fs.b1);
+        pa.s_k0 = proj_dims;
+        pa.s_rows_pad = f_rows_pad;
+      }
       TK(launch_prenet_fused(pa, st));
     } else {
       // frame (step * r - 1) of every utterance; step 0 reads the zero block behind mel_all with row stride 0
@@ -1125,7 +1246,12 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
     if (use_tc && D % 64 == 0) {  // attention GRU on [context, prenet]: input projection + recurrent step on tensor cores
       __half* a_hi = reinterpret_cast<__half*>(ws + L.a_hi);
       __half* a_lo = reinterpret_cast<__half*>(ws + L.a_lo);
-      TK(launch_act_split(ws + L.ctx, proj_dims, proj_dims, ws + L.dp2, 2 * D, 2 * D, B, a_hi, a_lo, st));
+      if (fsplit) {
+        a_hi = fhi(fs.p1);
+        a_lo = fhi(fs.p1 + fs.b1);
+      } else {
+        TK(launch_act_split(ws + L.ctx, proj_dims, proj_dims, ws + L.dp2, 2 * D, 2 * D, B, a_hi, a_lo, st));
+      }
       TcSkinnyArgs ta;
       memset(&ta, 0, sizeof(ta));
       ta.a_hi = a_hi;
@@ -1141,9 +1267,13 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       ta.ldy = 3 * D;
       TK(launch_tc_skinny(ta, st));
       const size_t tb = tc_skinny_act_bytes(B, D);
-      const int par = sj & 1;  // graph groups start at even steps, so the parity of (base + sj) is that of sj
       TcGruArgs g;
       memset(&g, 0, sizeof(g));
+      if (fsplit) {  // attn_h is the trailing K segment of rnn_input's [ctx | attn_h] tiles
+        g.s_hi = fhi(fs.p2);
+        g.s_lo = fhi(fs.p2 + fs.b2);
+        g.s_k0 = proj_dims;
+      }
       g.a_hi[0] = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(ws + L.ah_hi) + par * tb);
       g.a_lo[0] = reinterpret_cast<const __half*>(reinterpret_cast<const char*>(ws + L.ah_lo) + par * tb);
       g.nxt_hi[0] = reinterpret_cast<__half*>(reinterpret_cast<char*>(ws + L.ah_hi) + (par ^ 1) * tb);
@@ -1182,29 +1312,49 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       TK(launch_gru_cell(ws + L.dgi, 3 * D, ws + L.dgh, ws + L.attn_h, D, nullptr, 0, B, D, st));
     }
     {  // location sensitive attention + context
-      GemmArgs a = gemm1(ws + L.attn_h, D, D, P(h, "decoder.attn_net.W.weight"), D, P(h, "decoder.attn_net.W.bias"), B, D,
-                         ws + L.pq, D);
-      TK(launch_gemm(a, st));
-      lsa_step_kernel<<<B, 256, lsa_smem, st>>>(ws + L.pq, ws + L.proj, seq, proj_dims, chars, ws + L.cum,
-                                                P(h, "decoder.attn_net.conv.weight"), P(h, "decoder.attn_net.conv.bias"),
-                                                P(h, "decoder.attn_net.L.weight"), P(h, "decoder.attn_net.v.weight"),
-                                                ws + L.scores_all, nst * Tc, (proj_dims % 256 == 0) ? nullptr : ws + L.ctx, Tc,
-                                                sp, sj);
+      // MB_TACO_LSA_FUSED (default 1): 512 threads per batch row (4 time-step groups in the energy phase) and the query
+      // projection W q + b inside the kernel; 0 = round-2 shape (256 threads, separate GEMM launch)
+      static const bool lsa_fused = [] {
+        const char* e = getenv("MB_TACO_LSA_FUSED");
+        return e ? atoi(e) != 0 : true;
+      }();
+      const bool qf = lsa_fused && D == ATT_D;
+      if (!qf) {
+        GemmArgs a = gemm1(ws + L.attn_h, D, D, P(h, "decoder.attn_net.W.weight"), D, P(h, "decoder.attn_net.W.bias"), B, D,
+                           ws + L.pq, D);
+        TK(launch_gemm(a, st));
+      }
+      lsa_step_kernel<<<B, lsa_fused ? 512 : 256, lsa_smem, st>>>(
+          ws + L.pq, ws + L.proj, seq, proj_dims, chars, ws + L.cum, P(h, "decoder.attn_net.conv.weight"),
+          P(h, "decoder.attn_net.conv.bias"), P(h, "decoder.attn_net.L.weight"), P(h, "decoder.attn_net.v.weight"),
+          ws + L.scores_all, nst * Tc, (proj_dims % 256 == 0) ? nullptr : ws + L.ctx, Tc, sp, sj, qf ? ws + L.attn_h : nullptr,
+          P(h, "decoder.attn_net.W.weight"), P(h, "decoder.attn_net.W.bias"));
       MB_LAUNCH_CHECK("lsa_step_kernel");
       if (proj_dims % 256 == 0) {
-        lsa_ctx_kernel<<<dim3(proj_dims / 256, B), 256, sizeof(float) * Tc, st>>>(ws + L.scores_all, nst * Tc, seq, proj_dims, Tc,
-                                                                                  ws + L.ctx, sp, sj);
+        lsa_ctx_kernel<<<dim3(proj_dims / 256, B), 256, sizeof(float) * Tc, st>>>(
+            ws + L.scores_all, nst * Tc, seq, proj_dims, Tc, ws + L.ctx, sp, sj, fsplit ? fhi(fs.p1) : nullptr,
+            fsplit ? fhi(fs.p1 + fs.b1) : nullptr, fsplit ? fhi(fs.p2) : nullptr, fsplit ? fhi(fs.p2 + fs.b2) : nullptr, f_rows_pad);
         MB_LAUNCH_CHECK("lsa_ctx_kernel");
       }
     }
     if (use_tc) {  // rnn_input on [context, attn_hidden] (tensor cores)
       __half* a_hi = reinterpret_cast<__half*>(ws + L.a_hi);
       __half* a_lo = reinterpret_cast<__half*>(ws + L.a_lo);
-      TK(launch_act_split(ws + L.ctx, proj_dims, proj_dims, ws + L.attn_h, D, D, B, a_hi, a_lo, st));
+      if (fsplit) {
+        a_hi = fhi(fs.p2);
+        a_lo = fhi(fs.p2 + fs.b2);
+      } else {
+        TK(launch_act_split(ws + L.ctx, proj_dims, proj_dims, ws + L.attn_h, D, D, B, a_hi, a_lo, st));
+      }
       TcSkinnyArgs ta;
       memset(&ta, 0, sizeof(ta));
       ta.a_hi = a_hi;
       ta.a_lo = a_lo;
+      if (fsplit) {  // x is the leading K segment of the first LSTM's [x | h1] tiles of this step
+        ta.s_hi[0] = fhi(fs.p3[par]);
+        ta.s_lo[0] = fhi(fs.p3[par] + fs.b3);
+        ta.s_k0[0] = 0;
+      }
       ta.w = reinterpret_cast<const __half*>(P(h, "decoder.rnn_input.tcw"));
       ta.bias = P(h, "decoder.rnn_input.tcb");
       ta.KB = (proj_dims + D + 63) / 64;
@@ -1239,9 +1389,23 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
         // gates GEMM on the tensor cores (3-term fp16 split, FP32 accumulate) with the cell update fused
         __half* a_hi = reinterpret_cast<__half*>(ws + L.a_hi);
         __half* a_lo = reinterpret_cast<__half*>(ws + L.a_lo);
-        TK(launch_act_split(ws + L.x, LD, LD, hh, LD, LD, B, a_hi, a_lo, st));
         TcSkinnyArgs ta;
         memset(&ta, 0, sizeof(ta));
+        if (fsplit) {
+          // this step's [x | h] tiles; x' (residual stream) goes to the next consumer's tiles, h' to this cell's tiles of the
+          // NEXT step (other parity)
+          const size_t* mine = l == 0 ? fs.p3 : fs.p4;
+          a_hi = fhi(mine[par]);
+          a_lo = fhi(mine[par] + fs.b3);
+          ta.s_hi[1] = fhi(mine[par ^ 1]);
+          ta.s_lo[1] = fhi(mine[par ^ 1] + fs.b3);
+          ta.s_k0[1] = LD;
+          ta.s_hi[0] = l == 0 ? fhi(fs.p4[par]) : fhi(fs.p5);
+          ta.s_lo[0] = l == 0 ? fhi(fs.p4[par] + fs.b3) : fhi(fs.p5 + fs.b5);
+          ta.s_k0[0] = 0;
+        } else {
+          TK(launch_act_split(ws + L.x, LD, LD, hh, LD, LD, B, a_hi, a_lo, st));
+        }
         ta.a_hi = a_hi;
         ta.a_lo = a_lo;
         ta.w = reinterpret_cast<const __half*>(P(h, n + ".tcw"));
@@ -1273,7 +1437,12 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       if (use_tc && (r * NM) % 4 == 0) {
         __half* a_hi = reinterpret_cast<__half*>(ws + L.a_hi);
         __half* a_lo = reinterpret_cast<__half*>(ws + L.a_lo);
-        TK(launch_act_split(ws + L.x, LD, LD, nullptr, 0, 0, B, a_hi, a_lo, st));
+        if (fsplit) {
+          a_hi = fhi(fs.p5);
+          a_lo = fhi(fs.p5 + fs.b5);
+        } else {
+          TK(launch_act_split(ws + L.x, LD, LD, nullptr, 0, 0, B, a_hi, a_lo, st));
+        }
         TcSkinnyArgs ta;
         memset(&ta, 0, sizeof(ta));
         ta.a_hi = a_hi;
@@ -1311,9 +1480,20 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       s.act = ACT_SIGMOID;
       s.Y = ws + L.stopv;
       s.ldy = 1;
-      TK(launch_gemm(s, st));
-      stop_flag_kernel<<<1, 32, 0, st>>>(ws + L.stopv, B, min_stop_token, r, flags, sp, sj);
-      MB_LAUNCH_CHECK("stop_flag_kernel");
+      static const bool stop_fused = [] {
+        const char* e = getenv("MB_TACO_STOP_FUSED");  // 0 = stop projection and stop rule as two launches (round 2)
+        return e ? atoi(e) != 0 : true;
+      }();
+      if (stop_fused) {
+        // the CTA that finishes last applies the stop rule (ticket counter behind the step counter, reset by that CTA)
+        stop_step_kernel<<<B, 256, 0, st>>>(s, B, min_stop_token, r, flags, sp, sj,
+                                            reinterpret_cast<unsigned int*>(ws + L.step) + 16);
+        MB_LAUNCH_CHECK("stop_step_kernel");
+      } else {
+        TK(launch_gemm(s, st));
+        stop_flag_kernel<<<1, 32, 0, st>>>(ws + L.stopv, B, min_stop_token, r, flags, sp, sj);
+        MB_LAUNCH_CHECK("stop_flag_kernel");
+      }
     }
     return MB_OK;
   };

@@ -427,7 +427,8 @@ constexpr int kPrenetWarps = 32;   // 1024 threads: 8 outputs per warp and layer
 template <int KMAX>
 __device__ __forceinline__ void prenet_layer(const float* __restrict__ W, const float* __restrict__ bias, int K, int H,
                                              const float (*in)[KMAX], const uint8_t* __restrict__ mask, int b0, int B, int warp, int lane,
-                                             float (*out_s)[256], float* out_g, int ldy) {
+                                             float (*out_s)[256], float* out_g, int ldy, __half* s_hi = nullptr,
+                                             __half* s_lo = nullptr, int s_k0 = 0, int s_rows_pad = 0) {
   for (int n0 = warp * 4; n0 < H; n0 += kPrenetWarps * 4) {
     float acc[4][kPrenetRows];
 #pragma unroll
@@ -465,6 +466,7 @@ __device__ __forceinline__ void prenet_layer(const float* __restrict__ W, const 
         if (b < B) v = mask[(size_t)b * H + n] ? v * 2.f : 0.f;
         if (out_s) out_s[r][n] = v;
         if (out_g && b < B) out_g[(size_t)b * ldy + n] = v;
+        if (s_hi && b < B) store_split_scalar(v, b, s_rows_pad, s_k0 + n, s_hi, s_lo);
       }
     }
   }
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(32 * kPrenetWarps) prenet_fused_kernel(const P
   const uint8_t* m2 = a.m2 + (size_t)si * (size_t)a.mask_step;
   prenet_layer<128>(a.W1, a.b1, a.K, a.H, xs, m1, b0, a.B, warp, lane, hs, nullptr, 0);
   __syncthreads();
-  prenet_layer<256>(a.W2, a.b2, a.H, a.H, hs, m2, b0, a.B, warp, lane, nullptr, a.y, a.ldy);
+  prenet_layer<256>(a.W2, a.b2, a.H, a.H, hs, m2, b0, a.B, warp, lane, nullptr, a.y, a.ldy, a.s_hi, a.s_lo, a.s_k0, a.s_rows_pad);
 }
 
 cudaError_t launch_prenet_fused(const PrenetArgs& a, cudaStream_t st) {

@@ -15,6 +15,34 @@
 namespace mb {
 namespace taco {
 
+// ---- fp16 hi / lo operand tiles [KB][rows_pad][64] (16-byte chunks XOR (row & 7)): element (m, k) of the K-major
+// SWIZZLE_128B layout the tensor-core GEMMs read (written by launch_act_split or directly by the producing kernels)
+__device__ __forceinline__ size_t split_tile_index(int m, int rows_pad, int k) {  // in halves
+  const int kb = k >> 6, c8 = (k & 63) >> 3, e = k & 7;
+  return (((size_t)kb * rows_pad + m) * 8 + (size_t)(c8 ^ (m & 7))) * 8 + (size_t)e;
+}
+__device__ __forceinline__ void store_split_scalar(float v, int m, int rows_pad, int k, __half* t_hi, __half* t_lo) {
+  const __half hi = __float2half_rn(v);
+  const size_t o = split_tile_index(m, rows_pad, k);
+  t_hi[o] = hi;
+  t_lo[o] = __float2half_rn(v - __half2float(hi));
+}
+// four consecutive k (k % 4 == 0)
+__device__ __forceinline__ void store_split_quad(const float4& v, int m, int rows_pad, int k, __half* t_hi, __half* t_lo) {
+  const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+  const size_t o = split_tile_index(m, rows_pad, k);
+  uint2 ph, pl;
+  ph.x = *reinterpret_cast<const uint32_t*>(&h01);
+  ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+  pl.x = *reinterpret_cast<const uint32_t*>(&l01);
+  pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+  *reinterpret_cast<uint2*>(t_hi + o) = ph;
+  *reinterpret_cast<uint2*>(t_lo + o) = pl;
+}
+
+
 constexpr int kMaxSeg = 5;
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2, ACT_TANH = 3 };
@@ -77,6 +105,9 @@ struct PrenetArgs {
   int B, K, H;             // K <= 128, H <= 256
   float* y;                // [B][ldy]
   int ldy;
+  __half* s_hi;            // optional: y also goes, split into fp16 hi / lo, into the operand tiles of the next tensor-core GEMM
+  __half* s_lo;            //   (columns [s_k0, s_k0 + H) of tiles [KB][s_rows_pad][64], the layout of launch_act_split)
+  int s_k0, s_rows_pad;
 };
 cudaError_t launch_prenet_fused(const PrenetArgs& a, cudaStream_t st);
 
@@ -114,6 +145,11 @@ struct TcSkinnyArgs {
   float* h;
   float* x;
   int H;
+  // optional split outputs (hi / lo operand tiles [KB][rows_pad][64] of the NEXT GEMMs, so that no act_split launch is needed):
+  //   slot 0: TCS_PLAIN y / TCS_LSTM x' (the residual stream) at columns s_k0[0] + n;  slot 1: TCS_LSTM h' at columns s_k0[1] + n
+  __half* s_hi[2];
+  __half* s_lo[2];
+  int s_k0[2];
 };
 // one recurrent GRU step for 1 or 2 directions (blockIdx.y); pointers per direction
 struct TcGruArgs {
@@ -128,6 +164,9 @@ struct TcGruArgs {
   float* out[2];          // output sequence slot of this step: row m at out + m * ldout
   float inv_scale[2];
   int ldgi, ldout, KB, M, H, rows_pad, ndir;
+  __half* s_hi;           // optional (direction 0): h_t also into columns [s_k0, s_k0 + H) of another GEMM's operand tiles
+  __half* s_lo;
+  int s_k0;
 };
 cudaError_t launch_tc_gru(const TcGruArgs& a, cudaStream_t st);
 // ---- large-M tensor-core GEMM / conv over time (CBHG stacks), 128 x 128 output tiles ---------------------------

@@ -206,11 +206,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
       *reinterpret_cast<float4*>(p.h + o + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
       *reinterpret_cast<float4*>(p.x + o) = make_float4(xn[0], xn[1], xn[2], xn[3]);
       *reinterpret_cast<float4*>(p.x + o + 4) = make_float4(xn[4], xn[5], xn[6], xn[7]);
+      if (p.s_hi[0]) store_split_chunk(xn, m, p.rows_pad, p.s_k0[0] + tile * 8, p.s_hi[0], p.s_lo[0]);
+      if (p.s_hi[1]) store_split_chunk(hn, m, p.rows_pad, p.s_k0[1] + tile * 8, p.s_hi[1], p.s_lo[1]);
     } else {
       float* y = p.y + (long long)step_index(p.step_ptr, p.step_j) * p.y_step + (size_t)m * p.ldy + (size_t)tile * 32;
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         if (tile * 32 + i < p.N) *reinterpret_cast<float4*>(y + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      if (p.s_hi[0]) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          if (tile * 32 + i + 8 <= p.N) store_split_chunk(v + i, m, p.rows_pad, p.s_k0[0] + tile * 32 + i, p.s_hi[0], p.s_lo[0]);
       }
     }
   });
@@ -241,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gru_kernel(const __grid_consta
                 *reinterpret_cast<float4*>(op) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                 *reinterpret_cast<float4*>(op + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
                 store_split_chunk(hn, m, p.rows_pad, tile * 8, p.nxt_hi[dir], p.nxt_lo[dir]);
+                if (dir == 0 && p.s_hi) store_split_chunk(hn, m, p.rows_pad, p.s_k0 + tile * 8, p.s_hi, p.s_lo);
               });
 }
 
