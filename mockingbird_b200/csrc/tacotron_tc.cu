@@ -29,7 +29,7 @@ namespace {
 
 using namespace tcdev;
 
-constexpr int kStages = 4;          // ring depth of the 32-column kernels
+constexpr int kStages = 4;          // ring depth of the 32-column kernels (5 stages measured no faster: 37.8 vs 36.0 ms on cfg 4)
 constexpr int kBigStages = 3;       // ring depth of the 128-column kernel (64 KB per stage)
 constexpr int kThreads = 192;
 constexpr uint32_t kATile = 16384;  // 128 rows x 128 B (rows >= rows_pad stay zero)
