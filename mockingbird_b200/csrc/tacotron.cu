@@ -369,6 +369,9 @@ struct mb_tacotron {
   std::set<std::string> big_packed;  // CBHG GEMMs whose tensor-core images ("<key>.bigw") are packed
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // side stream of the decoder loop (the parts of a step's GEMMs whose inputs are known a step early, the stop rule) + its events
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_side[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -445,7 +448,7 @@ struct Ws {
   // encoder
   size_t ids, emb, m_enc, p1, x0, bank, pool, pj1, y, hw12, gi_f, gi_b, gh, hst, seq, proj, style_q, style;
   // decoder
-  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, ah_hi, ah_lo, fsp, stopv, step, flags, dmask;
+  size_t attn_h, h1, c1, h2, c2, ctx, cum, dp1, dp2, dgi, dgh, pq, x, gates, a_hi, a_lo, ah_hi, ah_lo, fsp, pre1, pre2, gic, stopv, step, flags, dmask;
   size_t big_hi, big_lo, big_bytes;
   // outputs / postnet
   size_t mel_all, scores_all, pbank, ppool, ppj1, ppj2, py, phw12, pgi_f, pgi_b, pgh, phst, pout, lin;
@@ -505,6 +508,10 @@ Ws ws_layout(const mb_tacotron_config& c, int B, int Tc, int steps, int r) {
     const FusedSplit f = fused_split_layout(Bc, proj_dims, c.decoder_dims, c.lstm_dims);
     L.fsp = take(f.total / 4);
   }
+  // partial GEMM results computed a step early on the side stream: W_hh h of the two LSTMs, W_ih[:, ctx] ctx of the attention GRU
+  L.pre1 = take((size_t)B * 4 * c.lstm_dims);
+  L.pre2 = take((size_t)B * 4 * c.lstm_dims);
+  L.gic = take((size_t)B * 3 * c.decoder_dims);
   L.stopv = take(B);
   L.step = take(64);
   const int nst = (steps + r - 1) / r;
@@ -904,6 +911,9 @@ void mb_tacotron_destroy(mb_tacotron* h) {
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (cudaEvent_t e : h->ev_side)
+    if (e) cudaEventDestroy(e);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   delete h;
 }
 
@@ -1053,6 +1063,8 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
     MB_CUDA_CHECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     MB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
     MB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+    MB_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : h->ev_side) MB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   cudaStream_t st = h->own_stream;
   MB_CUDA_CHECK(cudaEventRecord(h->ev_in, caller));
@@ -1177,6 +1189,39 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   char* fbase = reinterpret_cast<char*>(ws + L.fsp);
   auto fhi = [&](size_t off) { return reinterpret_cast<__half*>(fbase + off); };
   const int f_rows_pad = B <= 64 ? 64 : 128;
+  // Step DAG (MB_TACO_DAG, default 1, needs the fused split): a step's critical path is a chain of ~10 latency-bound kernels.  Three
+  // of its GEMMs have a K segment that is known a whole step early - W_hh h_{t-1} of both LSTM cells and the context half of the
+  // attention GRU's input projection - so those halves run on a side stream (TCS_PLAIN over a k-block range, result added to the
+  // accumulator of the short main-path GEMM), and so does the stop projection / stop rule, which nothing in the next step needs.
+  // The side stream forks from / joins the main one with events, inside the captured graph as well.
+  static const bool dag_env = [] {
+    const char* e = getenv("MB_TACO_DAG");
+    return e ? atoi(e) != 0 : true;
+  }();
+  const bool dag = dag_env && fsplit && proj_dims % 64 == 0;
+  cudaStream_t sd = h->side_stream;
+  bool have_gic = false, have_p1 = false, have_p2 = false, have_stop = false, side_open = false;
+  // fork: side stream waits for everything enqueued on the main stream so far
+  auto side_after_main = [&](cudaEvent_t ev) -> int {
+    MB_CUDA_CHECK(cudaEventRecord(ev, st));
+    MB_CUDA_CHECK(cudaStreamWaitEvent(sd, ev, 0));
+    side_open = true;
+    return MB_OK;
+  };
+  auto main_after_side = [&](cudaEvent_t ev) -> int {
+    MB_CUDA_CHECK(cudaEventRecord(ev, sd));
+    MB_CUDA_CHECK(cudaStreamWaitEvent(st, ev, 0));
+    return MB_OK;
+  };
+  // join everything outstanding on the side stream (end of a captured group / of a directly launched step)
+  auto join_side = [&]() -> int {
+    if (side_open) {
+      int rcj = main_after_side(h->ev_side[7]);
+      if (rcj != MB_OK) return rcj;
+    }
+    side_open = have_gic = have_p1 = have_p2 = have_stop = false;
+    return MB_OK;
+  };
   auto emit_step = [&](const int* sp, int sj) -> int {
     // PreNet on the last frame of the previous step (go frame = zeros)
     const uint8_t* m1;
@@ -1259,6 +1304,17 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
       ta.w = reinterpret_cast<const __half*>(P(h, "decoder.attn_rnn.ih.tcw"));
       ta.bias = P(h, "decoder.attn_rnn.ih.tcb");
       ta.KB = (proj_dims + 2 * D + 63) / 64;
+      if (dag) {  // the context half was multiplied on the side stream after the previous step's attention (zero at step 0)
+        if (have_gic) {
+          MB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_side[1], 0));
+          have_gic = false;
+        }
+        ta.KBw = ta.KB;
+        ta.kb0 = proj_dims / 64;
+        ta.KB = ta.KBw - ta.kb0;
+        ta.pre = ws + L.gic;
+        ta.ldpre = 3 * D;
+      }
       ta.M = B;
       ta.N = 3 * D;
       ta.mode = TCS_PLAIN;
@@ -1331,10 +1387,35 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
           P(h, "decoder.attn_net.W.weight"), P(h, "decoder.attn_net.W.bias"));
       MB_LAUNCH_CHECK("lsa_step_kernel");
       if (proj_dims % 256 == 0) {
+        if (have_stop) {  // the previous step's stop projection (side stream) still reads ctx and x, which are rewritten from here on
+          MB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_side[6], 0));
+          have_stop = false;
+        }
         lsa_ctx_kernel<<<dim3(proj_dims / 256, B), 256, sizeof(float) * Tc, st>>>(
             ws + L.scores_all, nst * Tc, seq, proj_dims, Tc, ws + L.ctx, sp, sj, fsplit ? fhi(fs.p1) : nullptr,
             fsplit ? fhi(fs.p1 + fs.b1) : nullptr, fsplit ? fhi(fs.p2) : nullptr, fsplit ? fhi(fs.p2 + fs.b2) : nullptr, f_rows_pad);
         MB_LAUNCH_CHECK("lsa_ctx_kernel");
+      }
+      if (dag) {  // side stream: context half of the NEXT step's attention-GRU input projection
+        int rcs = side_after_main(h->ev_side[0]);
+        if (rcs != MB_OK) return rcs;
+        TcSkinnyArgs tp;
+        memset(&tp, 0, sizeof(tp));
+        tp.a_hi = fhi(fs.p1);
+        tp.a_lo = fhi(fs.p1 + fs.b1);
+        tp.w = reinterpret_cast<const __half*>(P(h, "decoder.attn_rnn.ih.tcw"));
+        tp.KBw = (proj_dims + 2 * D + 63) / 64;
+        tp.kb0 = 0;
+        tp.KB = proj_dims / 64;
+        tp.M = B;
+        tp.N = 3 * D;
+        tp.mode = TCS_PLAIN;
+        tp.inv_scale = h->tc_inv_scale["decoder.attn_rnn.ih"];
+        tp.y = ws + L.gic;
+        tp.ldy = 3 * D;
+        TK(launch_tc_skinny(tp, sd));
+        MB_CUDA_CHECK(cudaEventRecord(h->ev_side[1], sd));
+        have_gic = true;
       }
     }
     if (use_tc) {  // rnn_input on [context, attn_hidden] (tensor cores)
@@ -1411,6 +1492,18 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
         ta.w = reinterpret_cast<const __half*>(P(h, n + ".tcw"));
         ta.bias = P(h, n + ".tcb");
         ta.KB = 2 * LD / 64;
+        if (dag) {  // W_hh h_{t-1} was multiplied on the side stream right after the previous step's cell (zero at step 0)
+          bool& have = l == 0 ? have_p1 : have_p2;
+          if (have) {
+            MB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_side[l == 0 ? 3 : 5], 0));
+            have = false;
+          }
+          ta.KBw = ta.KB;
+          ta.kb0 = 0;
+          ta.KB = LD / 64;
+          ta.pre = ws + (l == 0 ? L.pre1 : L.pre2);
+          ta.ldpre = 4 * LD;
+        }
         ta.M = B;
         ta.N = 4 * LD;
         ta.mode = TCS_LSTM;
@@ -1420,6 +1513,28 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
         ta.x = ws + L.x;
         ta.H = LD;
         TK(launch_tc_skinny(ta, st));
+        if (dag) {  // side stream: W_hh h_t for the next step, from the h tiles this launch just wrote (other parity)
+          int rcs = side_after_main(h->ev_side[l == 0 ? 2 : 4]);
+          if (rcs != MB_OK) return rcs;
+          const size_t* mine = l == 0 ? fs.p3 : fs.p4;
+          TcSkinnyArgs tp;
+          memset(&tp, 0, sizeof(tp));
+          tp.a_hi = fhi(mine[par ^ 1]);
+          tp.a_lo = fhi(mine[par ^ 1] + fs.b3);
+          tp.w = reinterpret_cast<const __half*>(P(h, n + ".tcw"));
+          tp.KBw = 2 * LD / 64;
+          tp.kb0 = LD / 64;
+          tp.KB = LD / 64;
+          tp.M = B;
+          tp.N = 4 * LD;
+          tp.mode = TCS_PLAIN;
+          tp.inv_scale = h->tc_inv_scale[n];
+          tp.y = ws + (l == 0 ? L.pre1 : L.pre2);
+          tp.ldy = 4 * LD;
+          TK(launch_tc_skinny(tp, sd));
+          MB_CUDA_CHECK(cudaEventRecord(h->ev_side[l == 0 ? 3 : 5], sd));
+          (l == 0 ? have_p1 : have_p2) = true;
+        }
         continue;
       }
       GemmArgs a;
@@ -1485,10 +1600,15 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
         return e ? atoi(e) != 0 : true;
       }();
       if (stop_fused) {
-        // the CTA that finishes last applies the stop rule (ticket counter behind the step counter, reset by that CTA)
-        stop_step_kernel<<<B, 256, 0, st>>>(s, B, min_stop_token, r, flags, sp, sj,
-                                            reinterpret_cast<unsigned int*>(ws + L.step) + 16);
+        // the CTA that finishes last applies the stop rule (ticket counter behind the step counter, reset by that CTA).
+        // With the step DAG it runs on the side stream (after the second LSTM's fork): the next step does not need it.
+        stop_step_kernel<<<B, 256, 0, dag ? sd : st>>>(s, B, min_stop_token, r, flags, sp, sj,
+                                                       reinterpret_cast<unsigned int*>(ws + L.step) + 16);
         MB_LAUNCH_CHECK("stop_step_kernel");
+        if (dag) {
+          MB_CUDA_CHECK(cudaEventRecord(h->ev_side[6], sd));
+          have_stop = true;
+        }
       } else {
         TK(launch_gemm(s, st));
         stop_flag_kernel<<<1, 32, 0, st>>>(ws + L.stopv, B, min_stop_token, r, flags, sp, sj);
@@ -1526,6 +1646,7 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
     int rc_cap = MB_OK;
     if (ok) {
       for (int j = 0; j < kGraphSteps && rc_cap == MB_OK; ++j) rc_cap = emit_step(step_dev, j);
+      if (rc_cap == MB_OK) rc_cap = join_side();
       if (rc_cap == MB_OK) step_advance_kernel<<<1, 32, 0, st>>>(step_dev, kGraphSteps);
       ok = cudaStreamEndCapture(st, &graph) == cudaSuccess && rc_cap == MB_OK && graph != nullptr;
     }
@@ -1554,6 +1675,7 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
   }
   for (; si < nst && done_step < 0; ++si) {  // tail (or everything, without the graph): direct launches
     int rc2 = emit_step(nullptr, si);
+    if (rc2 == MB_OK) rc2 = join_side();
     if (rc2 != MB_OK) return rc2;
     if ((si % 16) == 15 || si == nst - 1) {
       rc2 = poll(si);

@@ -421,42 +421,59 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int ldsrc, int r
 }  // namespace
 
 constexpr int kPrenetRows = 4;     // batch rows per CTA
-constexpr int kPrenetWarps = 32;   // 1024 threads: 8 outputs per warp and layer, 4 at a time (4 independent weight streams in flight)
+constexpr int kPrenetWarps = 16;   // 512 threads (128 registers: 8 x 4 accumulators + 16 weights in flight)
+constexpr int kPrenetOut = 8;      // outputs per warp and pass: 16 warps x 8 = 128 outputs, two passes per layer
 
-// one dense layer for kPrenetRows rows held in shared memory: out[r][n] = mask(relu(b[n] + W[n][:] . in[r][:])) * 2
+// one dense layer for kPrenetRows rows held in shared memory: out[r][n] = mask(relu(b[n] + W[n][:] . in[r][:])) * 2.
+// The kernel is a chain of L2 round trips (16 CTAs read the same 344 KB of weights), so each lane keeps 16 independent weight loads
+// in flight (8 outputs x 2 k: 12 dependent round trips per step instead of 22); the per-lane accumulation order (k = lane, lane + 32, ...) is that of the 4-output version.
 template <int KMAX>
 __device__ __forceinline__ void prenet_layer(const float* __restrict__ W, const float* __restrict__ bias, int K, int H,
                                              const float (*in)[KMAX], const uint8_t* __restrict__ mask, int b0, int B, int warp, int lane,
                                              float (*out_s)[256], float* out_g, int ldy, __half* s_hi = nullptr,
                                              __half* s_lo = nullptr, int s_k0 = 0, int s_rows_pad = 0) {
-  for (int n0 = warp * 4; n0 < H; n0 += kPrenetWarps * 4) {
-    float acc[4][kPrenetRows];
+  for (int n0 = warp * kPrenetOut; n0 < H; n0 += kPrenetWarps * kPrenetOut) {
+    float acc[kPrenetOut][kPrenetRows];
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
+    for (int o = 0; o < kPrenetOut; ++o)
 #pragma unroll
       for (int r = 0; r < kPrenetRows; ++r) acc[o][r] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      float wv[4];
+    for (int k = lane; k < K; k += 64) {
+      const int k2 = k + 32;
+      const bool two = k2 < K;
+      float w0[kPrenetOut], w1[kPrenetOut];
 #pragma unroll
-      for (int o = 0; o < 4; ++o) wv[o] = (n0 + o < H) ? W[(size_t)(n0 + o) * K + k] : 0.f;
+      for (int o = 0; o < kPrenetOut; ++o) {
+        const bool ok = n0 + o < H;
+        w0[o] = ok ? W[(size_t)(n0 + o) * K + k] : 0.f;
+        w1[o] = (ok && two) ? W[(size_t)(n0 + o) * K + k2] : 0.f;
+      }
 #pragma unroll
       for (int r = 0; r < kPrenetRows; ++r) {
-        const float xv = in[r][k];
+        const float x0 = in[r][k];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) acc[o][r] = fmaf(wv[o], xv, acc[o][r]);
+        for (int o = 0; o < kPrenetOut; ++o) acc[o][r] = fmaf(w0[o], x0, acc[o][r]);
+      }
+      if (two) {
+#pragma unroll
+        for (int r = 0; r < kPrenetRows; ++r) {
+          const float x1 = in[r][k2];
+#pragma unroll
+          for (int o = 0; o < kPrenetOut; ++o) acc[o][r] = fmaf(w1[o], x1, acc[o][r]);
+        }
       }
     }
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
+    for (int o = 0; o < kPrenetOut; ++o)
 #pragma unroll
       for (int r = 0; r < kPrenetRows; ++r)
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) acc[o][r] += __shfl_xor_sync(0xffffffffu, acc[o][r], off);
-    if (lane < 4 * kPrenetRows) {
-      const int o = lane >> 2, r = lane & 3;  // kPrenetRows == 4
+    {
+      const int o = lane >> 2, r = lane & 3;  // kPrenetOut * kPrenetRows == 32: one (output, row) per lane
       float v = 0.f;
 #pragma unroll
-      for (int oo = 0; oo < 4; ++oo)
+      for (int oo = 0; oo < kPrenetOut; ++oo)
 #pragma unroll
         for (int rr = 0; rr < kPrenetRows; ++rr) v = (oo == o && rr == r) ? acc[oo][rr] : v;
       const int n = n0 + o, b = b0 + r;

@@ -150,6 +150,12 @@ struct TcSkinnyArgs {
   __half* s_hi[2];
   __half* s_lo[2];
   int s_k0[2];
+  // optional K range: only k-blocks [kb0, kb0 + KB) of a weight image packed with KBw k-blocks per tile (KBw = 0: KB) and of the
+  // activation tiles; `pre` [M][ldpre] (tile column order, i.e. what a TCS_PLAIN launch over the other k-blocks wrote) is added to
+  // the accumulator before the epilogue.  Lets the part of a GEMM whose input is known early run off the critical path.
+  int kb0, KBw;
+  const float* pre;
+  int ldpre;
 };
 // one recurrent GRU step for 1 or 2 directions (blockIdx.y); pointers per direction
 struct TcGruArgs {

@@ -47,7 +47,7 @@ __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); 
 template <int NT, int STAGES, typename Epi>
 __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half* a_lo_g, const __half* w_g, const float* bias,
                                               int n_valid, int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi,
-                                              size_t a_kb_stride = 0) {
+                                              size_t a_kb_stride = 0, int kb0 = 0, int KBw = 0) {
   constexpr int kStages = STAGES;
   constexpr uint32_t kWTile = w_tile_bytes<NT>();
   constexpr uint32_t kStageBytes = stage_bytes<NT>();
@@ -100,15 +100,16 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint8_t* wt = reinterpret_cast<const uint8_t*>(w_g) + (size_t)tile * KB * (2 * kWTile);
+      const uint8_t* wt = reinterpret_cast<const uint8_t*>(w_g) + (size_t)tile * (KBw > 0 ? KBw : KB) * (2 * kWTile);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % kStages, ph = (kb / kStages) & 1;
+        const size_t kg = (size_t)(kb0 + kb);  // k-block inside the activation tiles / the weight image
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * kStageBytes;
         mbar_expect_tx(&full[s], 2 * a_bytes + 2 * kWTile);
-        bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(a_hi_g) + (size_t)kb * a_kb_stride, a_bytes, &full[s]);
-        bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(a_lo_g) + (size_t)kb * a_kb_stride, a_bytes, &full[s]);
-        bulk_g2s(smem_u32(st + 2 * kATile), wt + (size_t)kb * (2 * kWTile), 2 * kWTile, &full[s]);
+        bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(a_hi_g) + kg * a_kb_stride, a_bytes, &full[s]);
+        bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(a_lo_g) + kg * a_kb_stride, a_bytes, &full[s]);
+        bulk_g2s(smem_u32(st + 2 * kATile), wt + kg * (2 * kWTile), 2 * kWTile, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -164,9 +165,9 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
 template <typename Epi>
 __device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* a_lo_g, const __half* w_g, const float* bias,
                                             int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi,
-                                            size_t a_kb_stride = 0) {
+                                            size_t a_kb_stride = 0, int kb0 = 0, int KBw = 0) {
   skinny_body_t<32, kStages>(a_hi_g, a_lo_g, w_g, bias, 0x7fffffff, KB, M, rows_pad, inv_scale, tile,
-                             [&](int m, float* v, int) { epi(m, v); }, a_kb_stride);
+                             [&](int m, float* v, int) { epi(m, v); }, a_kb_stride, kb0, KBw);
 }
 
 // 8 fp32 values of row m, hidden units [u0, u0 + 8) -> the 16-byte chunk of the hi / lo operand tiles of the NEXT GEMM
@@ -186,6 +187,14 @@ __device__ __forceinline__ void store_split_chunk(const float* x, int m, int row
 __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_constant__ TcSkinnyArgs p) {
   const int tile = blockIdx.x;
   skinny_body(p.a_hi, p.a_lo, p.w, p.bias, p.KB, p.M, p.rows_pad, p.inv_scale, tile, [&](int m, float* v) {
+    if (p.pre) {  // partial product over the other k-blocks, computed earlier by a TCS_PLAIN launch (tile column order)
+      const float4* pp = reinterpret_cast<const float4*>(p.pre + (size_t)m * p.ldpre + (size_t)tile * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 q = pp[i];
+        v[4 * i + 0] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+      }
+    }
     if (p.mode == TCS_LSTM) {
       const size_t o = (size_t)m * p.H + (size_t)tile * 8;
       float cn[8], hn[8], xn[8];
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
           if (tile * 32 + i + 8 <= p.N) store_split_chunk(v + i, m, p.rows_pad, p.s_k0[0] + tile * 32 + i, p.s_hi[0], p.s_lo[0]);
       }
     }
-  });
+  }, 0, p.kb0, p.KBw);
 }
 
 // One recurrent step of a (bi)directional GRU: blockIdx.y = direction, blockIdx.x = 8 hidden units.
