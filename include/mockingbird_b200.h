@@ -15,8 +15,8 @@
  *     (mb_*_arena_bytes), temporaries in a caller-provided workspace (mb_*_workspace_bytes).
  *     Derived weight images are (re)packed inside that arena at finalize, or - for the large-M GEMMs of the Tacotron CBHG
  *     stacks and the encoder's input projections - at the first use of a layer after any set_arena / set_weight (no
- *     cudaMalloc: the packers' scratch is a slot of the arena).  Exceptions, allocated at create: mb_tacotron owns one
- *     stream and two events, mb_mtstream its pinned host ring, a side stream and events.
+ *     cudaMalloc: the packers' scratch is a slot of the arena).  Exceptions (no device memory): mb_tacotron owns two
+ *     streams and ten events (created at its first generate call), mb_mtstream its pinned host ring, a side stream and events.
  *   - every launch goes to the cudaStream_t passed as `stream` (void* here so that the header
  *     needs no CUDA include); functions are asynchronous with respect to the host unless stated.
  *   - multi-GPU: the library links no communication library and has no global state.  The packed arena of every model
@@ -316,7 +316,10 @@ size_t mb_tacotron_workspace_bytes(const mb_tacotron* h, int32_t batch, int32_t 
  * The work runs on an internal non-blocking stream that is ordered after everything already enqueued on `stream`
  * and that `stream` waits for before the call returns (events) - the decoder loop is replayed from a CUDA graph
  * (groups of 8 steps; the step index lives in device memory) and capture is not legal on the legacy default
- * stream.  The call blocks the host while polling the early-stop rule of tacotron.py:275 every 16 decoder steps. */
+ * stream.  Inside the loop a second internal stream carries the parts of a step that the next step does not wait for
+ * (W_hh h of both LSTM cells and the context half of the attention GRU's input projection for the NEXT step, the stop
+ * projection); it forks from and joins the first one with events, also inside the captured graph.
+ * The call blocks the host while polling the early-stop rule of tacotron.py:275 every 16 decoder steps. */
 int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk, int32_t batch, int32_t n_chars,
                          int32_t steps, int32_t r, int32_t style_idx, float min_stop_token, const uint8_t* enc_masks,
                          const uint8_t* dec_masks, uint64_t seed, float* mel, float* linear, float* attn,

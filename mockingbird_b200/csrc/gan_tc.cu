@@ -79,6 +79,7 @@ struct TcParams {
   float acc_scale;                     // accumulator -> value (1, or 1/kX3WScale for 3-term-split layers)
   float out_slope;
   int mode;
+  int red_add;                         // EPI_ADD without fp16 output: S += v by red.global.add.v4.f32
   float div;
   const int32_t* lengths;
   int len_mul_out;
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) tc_conv_kernel(const __grid
             }
           }
         }
-        if (inb && p.mode != EPI_STORE) {
+        if (inb && p.mode != EPI_STORE && !p.red_add) {
 #pragma unroll
           for (int g = 0; g < UC / 4; ++g) ov[g] = reinterpret_cast<const float4*>(p.y32)[i32 + (size_t)g * p.Lout];
         }
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) tc_conv_kernel(const __grid
             else add_res16(&v[8 * g], rh[g], p.res_inv);
           }
         }
-        if (p.mode != EPI_STORE) {
+        if (p.mode != EPI_STORE && !p.red_add) {
 #pragma unroll
           for (int g = 0; g < UC / 4; ++g) {
             v[4 * g + 0] += ov[g].x; v[4 * g + 1] += ov[g].y; v[4 * g + 2] += ov[g].z; v[4 * g + 3] += ov[g].w;
@@ -358,7 +359,13 @@ __global__ void __launch_bounds__(tc_threads(EW), 1) tc_conv_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < UC; ++i) v[i] = 0.f;
         }
-        if (p.y32) {
+        if (p.red_add) {  // MRF sum of a middle resblock: S += v by vector reductions in L2 (rows past the length add nothing)
+          if (live) {
+#pragma unroll
+            for (int g = 0; g < UC / 4; ++g)
+              red_add_f32x4(p.y32 + (i32 + (size_t)g * p.Lout) * 4, v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          }
+        } else if (p.y32) {
 #pragma unroll
           for (int g = 0; g < UC / 4; ++g)
             reinterpret_cast<float4*>(p.y32)[i32 + (size_t)g * p.Lout] =
@@ -724,6 +731,7 @@ int launch_tc(const TcOp& op, const char* tc_arena, const TRef& x16, const TRef&
   p.y_lo_c = (y16.p && y16.hilo) ? (y16.C >> 1) : -1;
   p.out_slope = out_slope;
   p.mode = t.mode;
+  p.red_add = (p.mode == EPI_ADD && !y16.p && y32.p && tc_red_add_enabled()) ? 1 : 0;
   p.div = t.div;
   p.lengths = lengths;
   p.len_mul_out = t.len_mul_out;
@@ -791,6 +799,17 @@ TRef make_ref(void* p, int layout, int C, int L) {
 }
 
 }  // namespace
+
+// MB_TC_RED_ADD=0: accumulate-mode epilogues read, add and store the running sum themselves (round 2)
+bool tc_red_add_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MB_TC_RED_ADD");
+    on = e ? atoi(e) : 1;
+  }
+  return on != 0;
+}
+
 
 int tc_plan_layers(std::vector<TcLayerDesc>& layers, size_t* tc_arena_bytes) {
   size_t off = 0;

@@ -99,12 +99,15 @@ struct TcPairParams {
   int y_hilo;                // 1: y16 is a hi/lo plane (C == 64 only: chunk 0 = hi, chunk 1 = lo = fp16(v - hi))
   float out_slope;
   int mode;
+  int red_add;               // 1: mode == EPI_ADD without an fp16 output: the epilogue accumulates with red.global.add.v4.f32 (no read of y32)
   float div;
   const int32_t* lengths;
   int len_mul;
   long long* trace;          // debug (MB_TC_PAIR_TRACE): clock64 stamps of CTA 0's roles, [role 4][item 64][event 8]
 };
 bool tc_pair_plan(int C, int k, int d1, bool f32in, TcPairParams* p);
+// MB_TC_RED_ADD=0: accumulate-mode epilogues read, add and store the running sum themselves (round 2)
+bool tc_red_add_enabled();
 int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st);
 // gan_tc_pair32s.cu: fp32-input pair with the residual / result rows kept in shared memory (bulk-TMA in, bulk-TMA out)
 bool tc_pair32s_eligible(const TcPairParams& p);

@@ -123,6 +123,11 @@ __device__ __forceinline__ bool elect_one() {
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
+// fire-and-forget fp32 accumulation of four consecutive values (REDG.E.ADD.F32x4): the MRF running sum without a read in the epilogue
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // v[0..8) += x, where the fp16 plane holds y = lrelu(x) (8 channels, 16 bytes) and inv = 1 / slope
 __device__ __forceinline__ void add_res16(float* v, const uint4& pk, float inv) {
   const __half2* h = reinterpret_cast<const __half2*>(&pk);

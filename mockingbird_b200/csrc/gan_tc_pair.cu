@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel
 #pragma unroll
           for (int g = 0; g < UC / 8; ++g) rh[g] = reinterpret_cast<const uint4*>(p.res16)[rbase + (size_t)(((col0 >> 3) + g) ^ sw)];
         }
-        if (inb && p.mode != EPI_STORE) {
+        if (inb && p.mode != EPI_STORE && !p.red_add) {
 #pragma unroll
           for (int g = 0; g < UC / 4; ++g) ov[g] = reinterpret_cast<const float4*>(p.y32)[i32 + (size_t)g * p.L];
         }
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel
 #pragma unroll
           for (int g = 0; g < UC / 8; ++g) add_res16(&v[8 * g], rh[g], p.res_inv);
         }
-        if (p.mode != EPI_STORE) {
+        if (p.mode != EPI_STORE && !p.red_add) {
 #pragma unroll
           for (int g = 0; g < UC / 4; ++g) {
             v[4 * g + 0] += ov[g].x; v[4 * g + 1] += ov[g].y; v[4 * g + 2] += ov[g].z; v[4 * g + 3] += ov[g].w;
@@ -522,7 +522,13 @@ __global__ void __launch_bounds__(pair_threads(EW, F32IN, CV), 1) tc_pair_kernel
 #pragma unroll
           for (int e = 0; e < UC; ++e) v[e] = 0.f;
         }
-        if (p.y32) {
+        if (p.red_add) {  // MRF sum of a middle resblock: S += v by vector reductions in L2 (rows past the length add nothing)
+          if (live) {
+#pragma unroll
+            for (int g = 0; g < UC / 4; ++g)
+              red_add_f32x4(p.y32 + (i32 + (size_t)g * p.L) * 4, v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          }
+        } else if (p.y32) {
 #pragma unroll
           for (int g = 0; g < UC / 4; ++g)
             reinterpret_cast<float4*>(p.y32)[i32 + (size_t)g * p.L] =
@@ -715,6 +721,7 @@ int launch_tc_pair(TcPairParams& p, int B, cudaStream_t st) {
     return e ? atoi(e) : 0;
   }();
   p.epi_split = split ? 1 : 0;
+  p.red_add = (p.mode == EPI_ADD && !p.y16 && p.y32 && tc_red_add_enabled()) ? 1 : 0;
   void (*kern)(const TcPairParams) = nullptr;
   static const int ew16 = [] {
     // A/B switch: 1 (default) = sixteen epilogue warps working on 16-column units.  Measured (profiles/r02_layers_ew16_{0,1}.tsv):

@@ -1,4 +1,4 @@
-"""The f16tc path has run-time switches for A/B measurements (MB_TC_FUSE, MB_TC_RES16, MB_TC_PAIR32, MB_TC_PAIR32S, MB_TC_PAIR_RT, MB_TC_PAIR_WSTREAM,
+"""The f16tc path has run-time switches for A/B measurements (MB_TC_FUSE, MB_TC_RES16, MB_TC_PAIR32, MB_TC_PAIR32S, MB_TC_PAIR_RT, MB_TC_PAIR_WSTREAM, MB_TC_RED_ADD,
 MB_TC_SPLIT3, MB_TC_UPS_X3; read once per process).  Every combination a user can select must stay inside the 1e-3
 tolerance: each setting runs the golden comparison in a fresh interpreter."""
 import json
@@ -43,7 +43,7 @@ out["tail"] = tail
 print(json.dumps(out))
 """
 
-ENVS = [{}, {"MB_TC_UPS_X3": "0", "MB_TC_RES16": "0"}, {"MB_TC_FUSE": "0"}, {"MB_TC_RES16": "0"}, {"MB_TC_PAIR32": "0"}, {"MB_TC_PAIR32S": "1"}, {"MB_TC_PAIR_WSTREAM": "1", "MB_TC_PAIR_RT": "1"}, {"MB_TC_PAIR_RT": "0"}, {"MB_TC_SPLIT3": "0"},
+ENVS = [{}, {"MB_TC_UPS_X3": "0", "MB_TC_RES16": "0"}, {"MB_TC_FUSE": "0"}, {"MB_TC_RES16": "0"}, {"MB_TC_PAIR32": "0"}, {"MB_TC_PAIR32S": "1"}, {"MB_TC_PAIR_WSTREAM": "1", "MB_TC_PAIR_RT": "1"}, {"MB_TC_PAIR_RT": "0"}, {"MB_TC_RED_ADD": "0"}, {"MB_TC_SPLIT3": "0"},
         {"MB_TC_RES16": "0", "MB_TC_PAIR32": "0", "MB_TC_FUSE": "0"}]
 
 
