@@ -197,6 +197,73 @@ __global__ void __launch_bounds__(256) tapconv_cout1_kernel(TapConv p, TapConvIO
     if (l0 + i < p.Lin) epilogue_store(p, io, b, 0, l0 + i, valid_out, acc[i] + (bias ? bias[0] : 0.f));
 }
 
+// Cout == 1, shared-memory tile version (conv_post of the F32B plane, taps contiguous, Cin % 4 == 0).  The R-rows-per-thread kernel
+// above applies the input leaky-relu once per (thread, row) - (nt + R - 1) / R times per element - and is bound by those instructions and
+// its L1 reads (0.099 ms for 210 MB).  Here a block of 128 threads stages kPostTile + nt - 1 activated rows of all channel quads once
+// (coalesced 16-byte loads, leaky-relu applied once, rows outside the utterance = 0), then every thread produces 4 CONSECUTIVE outputs
+// from 10 rows per quad.  The tile is stored as four row planes (row r -> plane r & 3, slot r >> 2) so that the lanes of a warp, whose
+// first rows are 4 apart, read consecutive 16-byte slots.  Accumulation order per output = the order of the kernel above (channel quad,
+// tap, channel), so results are bit-identical; a masked row contributes fma(w, 0, acc) = acc.
+constexpr int kPostTile = 512;  // output rows per block (128 threads x 4)
+template <int NT, int CQ>  // CQ = Cin / 4 channel quads (compile time: the staging loop keeps CQ independent 16-byte loads in flight per thread)
+__global__ void __launch_bounds__(128) convpost_tile_kernel(TapConv p, TapConvIO io, const float* __restrict__ w,
+                                                            const float* __restrict__ bias) {
+  extern __shared__ __align__(16) float psm[];
+  constexpr int C4 = CQ;
+  constexpr int SLOTS = kPostTile / 4 + 2;           // slots per plane (rows r >> 2, r < kPostTile + NT - 1 <= kPostTile + 8)
+  float* wsm = psm;                                   // [NT][Cin]
+  float4* tile = reinterpret_cast<float4*>(psm + ((NT * p.Cin + 3) & ~3));  // [C4][4][SLOTS]
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < NT * p.Cin; i += 128) {
+    const int t = i / p.Cin, ci = i - t * p.Cin;
+    wsm[i] = w[((size_t)p.slab[0][t] * p.Cin + ci) * p.Cout];
+  }
+  const int l_blk = blockIdx.x * kPostTile;
+  const int o0 = p.off[0][0];
+  const int valid_in = p.lengths ? min(p.Lin, p.lengths[b] * p.len_mul_in) : p.Lin;
+  const int valid_out = p.lengths ? min(p.Lout, p.lengths[b] * p.len_mul_out) : p.Lout;
+  const float4* xp = reinterpret_cast<const float4*>(io.x.p) + (size_t)b * C4 * p.Lin;
+  const int rows = kPostTile + NT - 1;
+  for (int r = tid; r < rows; r += 128) {
+    const int li = l_blk + o0 + r;
+    const bool ok = (li >= 0 && li < valid_in);
+    float4 v[CQ];
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) v[q] = ok ? xp[(size_t)q * p.Lin + li] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) {
+      float4 a = v[q];
+      a.x = lrelu(a.x, p.in_slope); a.y = lrelu(a.y, p.in_slope); a.z = lrelu(a.z, p.in_slope); a.w = lrelu(a.w, p.in_slope);
+      tile[((size_t)q * 4 + (r & 3)) * SLOTS + (r >> 2)] = a;
+    }
+  }
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int q = 0; q < C4; ++q) {
+    float4 x[NT + 3];
+#pragma unroll
+    for (int j = 0; j < NT + 3; ++j) x[j] = tile[((size_t)q * 4 + (j & 3)) * SLOTS + tid + (j >> 2)];  // row 4 * tid + j
+    float4 wt[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) wt[t] = *reinterpret_cast<const float4*>(&wsm[t * p.Cin + q * 4]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        acc[i] = fmaf(wt[t].x, x[i + t].x, acc[i]);
+        acc[i] = fmaf(wt[t].y, x[i + t].y, acc[i]);
+        acc[i] = fmaf(wt[t].z, x[i + t].z, acc[i]);
+        acc[i] = fmaf(wt[t].w, x[i + t].w, acc[i]);
+      }
+  }
+  const float bv = bias ? bias[0] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = l_blk + 4 * tid + i;
+    if (l < p.Lin) epilogue_store(p, io, b, 0, l, valid_out, acc[i] + bv);
+  }
+}
+
 __global__ void add_inplace_kernel(TRef dst32, TRef src32, TRef dst16, float slope, int B) {
   const size_t n = (size_t)B * dst32.C * dst32.L;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,6 +347,34 @@ cudaError_t launch_tapconv_f32(const TapConv& p, const TapConvIO& io, const floa
 cudaError_t launch_tapconv_cout1_f32(const TapConv& p, const TapConvIO& io, const float* w, const float* bias,
                                      cudaStream_t stream) {
   if (p.Cout != 1 || p.stride != 1) return cudaErrorInvalidValue;
+  {
+    // MB_POST_TILE=1: shared-memory tile kernel for the F32B plane with 7 contiguous taps (conv_post of both generators).  Default 0:
+    // bit-identical output but MEASURED SLOWER than the R-rows-per-thread kernel (0.123 vs 0.099 ms; 0.191 ms before the staging loads
+    // were batched eight per thread): three 67 KB blocks per SM alternate between a load phase and a compute phase and keep fewer bytes in
+    // flight than 2048 resident threads that simply re-read their rows through L1.
+    static const bool tile_on = [] {
+      const char* e = getenv("MB_POST_TILE");
+      return e ? atoi(e) != 0 : false;
+    }();
+    const int nt = p.ntaps[0];
+    bool contiguous = true;
+    for (int t = 1; t < nt; ++t) contiguous = contiguous && (p.off[0][t] == p.off[0][0] + t);
+    if (tile_on && nt == 7 && contiguous && io.x.layout == LAYOUT_F32B && (p.Cin == 32 || p.Cin == 16)) {
+      const size_t smem = sizeof(float) * (((size_t)nt * p.Cin + 3) & ~(size_t)3) +
+                          sizeof(float4) * (size_t)(p.Cin >> 2) * 4 * (kPostTile / 4 + 2);
+      static bool attr = false;
+      if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(convpost_tile_kernel<7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(convpost_tile_kernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) return e;
+        attr = true;
+      }
+      dim3 grid((p.Lin + kPostTile - 1) / kPostTile, p.B);
+      if (p.Cin == 32) convpost_tile_kernel<7, 8><<<grid, 128, smem, stream>>>(p, io, w, bias);
+      else convpost_tile_kernel<7, 4><<<grid, 128, smem, stream>>>(p, io, w, bias);
+      return cudaGetLastError();
+    }
+  }
   static const int rows = [] {
     const char* e = getenv("MB_POST_ROWS");  // A/B switch: 1, 2 (default: measured fastest, 0.099 vs 0.127 / 0.122 ms) or 4 output rows per thread
     const int r = e ? atoi(e) : 2;

@@ -43,7 +43,7 @@ out["tail"] = tail
 print(json.dumps(out))
 """
 
-ENVS = [{}, {"MB_TC_UPS_X3": "0", "MB_TC_RES16": "0"}, {"MB_TC_FUSE": "0"}, {"MB_TC_RES16": "0"}, {"MB_TC_PAIR32": "0"}, {"MB_TC_PAIR32S": "1"}, {"MB_TC_PAIR_WSTREAM": "1", "MB_TC_PAIR_RT": "1"}, {"MB_TC_PAIR_RT": "0"}, {"MB_TC_RED_ADD": "0"}, {"MB_TC_SPLIT3": "0"},
+ENVS = [{}, {"MB_TC_UPS_X3": "0", "MB_TC_RES16": "0"}, {"MB_TC_FUSE": "0"}, {"MB_TC_RES16": "0"}, {"MB_TC_PAIR32": "0"}, {"MB_TC_PAIR32S": "1"}, {"MB_TC_PAIR_WSTREAM": "1", "MB_TC_PAIR_RT": "1"}, {"MB_TC_PAIR_RT": "0"}, {"MB_TC_RED_ADD": "0"}, {"MB_POST_TILE": "1"}, {"MB_TC_SPLIT3": "0"},
         {"MB_TC_RES16": "0", "MB_TC_PAIR32": "0", "MB_TC_FUSE": "0"}]
 
 
