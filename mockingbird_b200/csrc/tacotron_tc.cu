@@ -42,6 +42,34 @@ __host__ __device__ constexpr uint32_t stage_bytes() { return 2 * kATile + 2 * w
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
+// ---- thread-block-cluster helpers (activation-tile multicast of the skinny GEMMs) ----
+__device__ __forceinline__ uint32_t cluster_nctaid_x() {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(v));
+  return v;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(v));
+  return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the same shared-memory offset of every CTA in `mask`, complete_tx on the mbarrier at the same offset in each
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // Shared main loop: operands for output tile `tile` stream through the ring; `epi(m, v)` is called by the
 // epilogue warps with the 32 accumulator columns (already scaled, bias added) of row m.
 template <int NT, int STAGES, typename Epi>
@@ -63,11 +91,19 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = (uint32_t)rows_pad * 128u;
   if (a_kb_stride == 0) a_kb_stride = a_bytes;  // bytes between the k-blocks of the activation tiles
+  // Optionally launched as clusters of `csize` CTAs (launch_tc_skinny, MB_TACO_MC; off by default, see there): the activation tiles are
+  // the same for every output tile, so each CTA fetches 1 / csize of a tile and multicasts it to the whole cluster (L2 -> SM traffic of a
+  // decoder LSTM launch: 98 -> 41 MB).
+  // A stage is refilled only when ALL CTAs of the cluster have consumed it: every CTA's commit arrives on every CTA's `empty` barrier.
+  const uint32_t csize = cluster_nctaid_x();
+  const uint32_t crank = cluster_ctarank();
+  const bool mc = csize > 1;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], mc ? csize : 1u);
     }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -91,6 +127,7 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (mc) cluster_sync_all();  // every CTA's barriers are initialised before a peer's multicast / commit can reach them
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barriers, TMEM allocation, bias, zero fill) touched no tensor
   // another kernel writes and may overlap the tail of the previous launch (recurrences are chains of these
@@ -107,8 +144,15 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * kStageBytes;
         mbar_expect_tx(&full[s], 2 * a_bytes + 2 * kWTile);
-        bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(a_hi_g) + kg * a_kb_stride, a_bytes, &full[s]);
-        bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(a_lo_g) + kg * a_kb_stride, a_bytes, &full[s]);
+        if (mc) {
+          const uint32_t slice = a_bytes / csize, off = crank * slice;  // my byte range of both tiles, sent to every CTA of the cluster
+          bulk_g2s_mc(smem_u32(st + off), reinterpret_cast<const uint8_t*>(a_hi_g) + kg * a_kb_stride + off, slice, &full[s], cmask);
+          bulk_g2s_mc(smem_u32(st + kATile + off), reinterpret_cast<const uint8_t*>(a_lo_g) + kg * a_kb_stride + off, slice, &full[s],
+                      cmask);
+        } else {
+          bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(a_hi_g) + kg * a_kb_stride, a_bytes, &full[s]);
+          bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(a_lo_g) + kg * a_kb_stride, a_bytes, &full[s]);
+        }
         bulk_g2s(smem_u32(st + 2 * kATile), wt + kg * (2 * kWTile), 2 * kWTile, &full[s]);
       }
     }
@@ -132,7 +176,8 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
           tc_mma_f16(tmem_base, al + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, 1u);
           tc_mma_f16(tmem_base, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u);
         }
-        tc_commit(&empty[s]);
+        if (mc) tc_commit_mc(&empty[s], cmask);
+        else tc_commit(&empty[s]);
       }
     }
     if (leader) tc_commit(acc_full);
@@ -155,6 +200,7 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
   }
   tc_fence_before();
   __syncthreads();
+  if (mc) cluster_sync_all();  // no CTA leaves while a peer's commit may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NT) : "memory");
@@ -478,7 +524,7 @@ __global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned in
 
 // launch with the programmatic-stream-serialization attribute (MB_TACO_PDL=0: plain launches)
 template <typename Args>
-cudaError_t launch_pdl(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& args) {
+cudaError_t launch_pdl(void (*kern)(const Args), dim3 grid, size_t smem, cudaStream_t st, const Args& args, int cluster_x = 1) {
   static const bool pdl = [] {
     const char* e = getenv("MB_TACO_PDL");
     return e ? atoi(e) != 0 : true;
@@ -489,11 +535,22 @@ cudaError_t launch_pdl(void (*kern)(const Args), dim3 grid, size_t smem, cudaStr
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, args);
 }
 
@@ -605,7 +662,18 @@ cudaError_t launch_tc_skinny(const TcSkinnyArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  return launch_pdl(tc_skinny_kernel, dim3((a.N + 31) / 32), smem, st, p);
+  // MB_TACO_MC = 2 / 4 / 8: cluster size of the activation-tile multicast (launches whose tile count it divides).  Default 1 (no
+  // clusters): MEASURED SLOWER - cfg 4 takes 42.1 ms with clusters of 8 and 36.3 ms with 4 against 35.6 ms without (same box, ABAB).
+  // The launches are not bound by L2 traffic; co-scheduling 8 SMs of a GPC per cluster and refilling a stage only when the slowest
+  // of 8 CTAs has consumed it cost more than the 2.4 x smaller operand traffic saves.
+  static const int mc_env = [] {
+    const char* e = getenv("MB_TACO_MC");
+    const int v = e ? atoi(e) : 1;
+    return (v == 2 || v == 4 || v == 8) ? v : 1;
+  }();
+  const int tiles = (a.N + 31) / 32;
+  const int cl = (mc_env > 1 && tiles % mc_env == 0 && (p.rows_pad * 128) % (16 * mc_env) == 0) ? mc_env : 1;
+  return launch_pdl(tc_skinny_kernel, dim3(tiles), smem, st, p, cl);
 }
 
 }  // namespace taco
