@@ -156,6 +156,7 @@ struct TcSkinnyArgs {
   int kb0, KBw;
   const float* pre;
   int ldpre;
+  int compact;          // set by launch_tc_skinny: 8 KB activation slots, 8-stage ring (rows_pad == 64)
 };
 // one recurrent GRU step for 1 or 2 directions (blockIdx.y); pointers per direction
 struct TcGruArgs {

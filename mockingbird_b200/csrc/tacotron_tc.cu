@@ -75,13 +75,18 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
 template <int NT, int STAGES, typename Epi>
 __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half* a_lo_g, const __half* w_g, const float* bias,
                                               int n_valid, int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi,
-                                              size_t a_kb_stride = 0, int kb0 = 0, int KBw = 0) {
-  constexpr int kStages = STAGES;
+                                              size_t a_kb_stride = 0, int kb0 = 0, int KBw = 0, bool compact = false) {
   constexpr uint32_t kWTile = w_tile_bytes<NT>();
-  constexpr uint32_t kStageBytes = stage_bytes<NT>();
+  // `compact` (32-column kernels with <= 64 rows, MB_TACO_RING8): an activation slot is 8 KB instead of 16 - the M = 128 MMA still reads
+  // 128 rows, i.e. runs 8 KB into the following slot (A_lo resp. the weight tiles of the same stage: finite fp16 values), and the
+  // accumulator rows 64-127 it produces from them are never read (epilogue: m < M).  A stage shrinks from 40 to 24 KB, so the ring
+  // holds 8 k-blocks instead of 4: half as many dependent L2 round trips per launch, and no zero fill of the unused rows.
+  const int kStages = compact ? 2 * STAGES : STAGES;
+  const uint32_t kASlot = compact ? kATile / 2 : kATile;
+  const uint32_t kStageBytes = 2 * kASlot + 2 * kWTile;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* acc_full = bars + 2 * kStages;
@@ -114,11 +119,11 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x < NT) bias_s[threadIdx.x] = (bias && tile * NT + (int)threadIdx.x < n_valid) ? bias[tile * NT + threadIdx.x] : 0.f;
-  if (rows_pad < 128) {
+  if (rows_pad < 128 && !compact) {
     // rows [rows_pad, 128) of every A slot are never written by the copies: zero them once
     const int nst = KB < kStages ? KB : kStages;
     for (int s = 0; s < 2 * nst; ++s) {
-      uint8_t* slot = smem + (size_t)(s >> 1) * kStageBytes + (size_t)(s & 1) * kATile + a_bytes;
+      uint8_t* slot = smem + (size_t)(s >> 1) * kStageBytes + (size_t)(s & 1) * kASlot + a_bytes;
       for (uint32_t i = threadIdx.x * 16u; i < kATile - a_bytes; i += kThreads * 16u)
         *reinterpret_cast<uint4*>(slot + i) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -147,13 +152,13 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
         if (mc) {
           const uint32_t slice = a_bytes / csize, off = crank * slice;  // my byte range of both tiles, sent to every CTA of the cluster
           bulk_g2s_mc(smem_u32(st + off), reinterpret_cast<const uint8_t*>(a_hi_g) + kg * a_kb_stride + off, slice, &full[s], cmask);
-          bulk_g2s_mc(smem_u32(st + kATile + off), reinterpret_cast<const uint8_t*>(a_lo_g) + kg * a_kb_stride + off, slice, &full[s],
+          bulk_g2s_mc(smem_u32(st + kASlot + off), reinterpret_cast<const uint8_t*>(a_lo_g) + kg * a_kb_stride + off, slice, &full[s],
                       cmask);
         } else {
           bulk_g2s(smem_u32(st), reinterpret_cast<const uint8_t*>(a_hi_g) + kg * a_kb_stride, a_bytes, &full[s]);
-          bulk_g2s(smem_u32(st + kATile), reinterpret_cast<const uint8_t*>(a_lo_g) + kg * a_kb_stride, a_bytes, &full[s]);
+          bulk_g2s(smem_u32(st + kASlot), reinterpret_cast<const uint8_t*>(a_lo_g) + kg * a_kb_stride, a_bytes, &full[s]);
         }
-        bulk_g2s(smem_u32(st + 2 * kATile), wt + kg * (2 * kWTile), 2 * kWTile, &full[s]);
+        bulk_g2s(smem_u32(st + 2 * kASlot), wt + kg * (2 * kWTile), 2 * kWTile, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -166,9 +171,9 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
       tc_fence_after();
       const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
       const uint64_t ah = desc_hi + (uint64_t)(base >> 4);
-      const uint64_t al = desc_hi + (uint64_t)((base + kATile) >> 4);
-      const uint64_t wh = desc_hi + (uint64_t)((base + 2 * kATile) >> 4);
-      const uint64_t wl = desc_hi + (uint64_t)((base + 2 * kATile + kWTile) >> 4);
+      const uint64_t al = desc_hi + (uint64_t)((base + kASlot) >> 4);
+      const uint64_t wh = desc_hi + (uint64_t)((base + 2 * kASlot) >> 4);
+      const uint64_t wl = desc_hi + (uint64_t)((base + 2 * kASlot + kWTile) >> 4);
       if (leader) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -211,9 +216,9 @@ __device__ __forceinline__ void skinny_body_t(const __half* a_hi_g, const __half
 template <typename Epi>
 __device__ __forceinline__ void skinny_body(const __half* a_hi_g, const __half* a_lo_g, const __half* w_g, const float* bias,
                                             int KB, int M, int rows_pad, float inv_scale, int tile, Epi epi,
-                                            size_t a_kb_stride = 0, int kb0 = 0, int KBw = 0) {
+                                            size_t a_kb_stride = 0, int kb0 = 0, int KBw = 0, bool compact = false) {
   skinny_body_t<32, kStages>(a_hi_g, a_lo_g, w_g, bias, 0x7fffffff, KB, M, rows_pad, inv_scale, tile,
-                             [&](int m, float* v, int) { epi(m, v); }, a_kb_stride, kb0, KBw);
+                             [&](int m, float* v, int) { epi(m, v); }, a_kb_stride, kb0, KBw, compact);
 }
 
 // 8 fp32 values of row m, hidden units [u0, u0 + 8) -> the 16-byte chunk of the hi / lo operand tiles of the NEXT GEMM
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_skinny_kernel(const __grid_con
           if (tile * 32 + i + 8 <= p.N) store_split_chunk(v + i, m, p.rows_pad, p.s_k0[0] + tile * 32 + i, p.s_hi[0], p.s_lo[0]);
       }
     }
-  }, 0, p.kb0, p.KBw);
+  }, 0, p.kb0, p.KBw, p.compact != 0);
 }
 
 // One recurrent step of a (bi)directional GRU: blockIdx.y = direction, blockIdx.x = 8 hidden units.
@@ -655,7 +660,12 @@ cudaError_t launch_tc_skinny(const TcSkinnyArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.M > 128 || a.N <= 0 || a.KB <= 0) return cudaErrorInvalidValue;
   TcSkinnyArgs p = a;
   p.rows_pad = a.M <= 64 ? 64 : 128;
-  constexpr size_t smem = kStages * kStageBytes + 1024 + 1024;
+  static const bool ring8 = [] {
+    const char* e = getenv("MB_TACO_RING8");  // A/B switch: 0 = 4 stages of 40 KB for every batch size (round 2)
+    return e ? atoi(e) != 0 : true;
+  }();
+  p.compact = (ring8 && p.rows_pad == 64) ? 1 : 0;
+  constexpr size_t smem = (kStages * kStageBytes > 2 * kStages * (kATile + 2 * kWTile) ? kStages * kStageBytes : 2 * kStages * (kATile + 2 * kWTile)) + 1024 + 1024;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
