@@ -30,6 +30,28 @@ namespace {
 //   scores  = softmax_t(u); cumulative += scores; ctx = scores @ seq[b]
 constexpr int ATT_D = 128, ATT_F = 32, ATT_K = 31;
 
+// launch with the programmatic-stream-serialization attribute (MB_TACO_PDL2=0: plain launch): the kernel may start while the
+// previous one drains; it must not touch anything another kernel writes before its griddepcontrol.wait
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl2(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  static const bool pdl = [] {
+    const char* e = getenv("MB_TACO_PDL2");
+    return e ? atoi(e) != 0 : true;
+  }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __global__ void __launch_bounds__(512) lsa_step_kernel(const float* __restrict__ pq, const float* __restrict__ proj,
                                                        const float* __restrict__ seq, int seq_dim,
                                                        const int32_t* __restrict__ chars, float* cum,
@@ -56,8 +78,12 @@ __global__ void __launch_bounds__(512) lsa_step_kernel(const float* __restrict__
     const int d = i / ATT_F, f = i - d * ATT_F;
     s_Lt[f * ATT_D + d] = Lw[i];
   }
+  for (int i = tid; i < ATT_D; i += blockDim.x) s_v[i] = vw[i];
+  for (int i = tid; i < ATT_F; i += blockDim.x) s_cb[i] = conv_b[i];
+  // programmatic dependent launch: the weights above are never written by a kernel and were staged while the previous launch drained
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int i = tid; i < ATT_D; i += blockDim.x) {
-    s_v[i] = vw[i];
     if (!q_in) s_pq[i] = pq[(size_t)b * ATT_D + i];
   }
   if (q_in) {
@@ -75,7 +101,6 @@ __global__ void __launch_bounds__(512) lsa_step_kernel(const float* __restrict__
       if (lane == 0) s_pq[o] = a + bq[o];
     }
   }
-  for (int i = tid; i < ATT_F; i += blockDim.x) s_cb[i] = conv_b[i];
   for (int i = tid; i < Tc + 30; i += blockDim.x) {
     const int t = i - 15;
     s_cum[i] = (t >= 0 && t < Tc) ? cum[(size_t)b * Tc + t] : 0.f;
@@ -174,6 +199,8 @@ __global__ void __launch_bounds__(256) lsa_ctx_kernel(const float* __restrict__ 
                                                       int s_rows_pad) {
   __shared__ float4 part[4][64];
   extern __shared__ float s_sc[];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int b = blockIdx.y, f4 = blockIdx.x * 64 + (threadIdx.x & 63), tg = threadIdx.x >> 6;
   const float* sc = scores + (size_t)step_index(step_ptr, step_j) * Tc + (size_t)b * scores_ld;
   for (int t = threadIdx.x; t < Tc; t += 256) s_sc[t] = sc[t];
@@ -1380,20 +1407,22 @@ int mb_tacotron_generate(mb_tacotron* h, const int32_t* chars, const float* spk,
                            ws + L.pq, D);
         TK(launch_gemm(a, st));
       }
-      lsa_step_kernel<<<B, lsa_fused ? 512 : 256, lsa_smem, st>>>(
-          ws + L.pq, ws + L.proj, seq, proj_dims, chars, ws + L.cum, P(h, "decoder.attn_net.conv.weight"),
-          P(h, "decoder.attn_net.conv.bias"), P(h, "decoder.attn_net.L.weight"), P(h, "decoder.attn_net.v.weight"),
-          ws + L.scores_all, nst * Tc, (proj_dims % 256 == 0) ? nullptr : ws + L.ctx, Tc, sp, sj, qf ? ws + L.attn_h : nullptr,
-          P(h, "decoder.attn_net.W.weight"), P(h, "decoder.attn_net.W.bias"));
+      MB_CUDA_CHECK(launch_pdl2(lsa_step_kernel, dim3(B), dim3(lsa_fused ? 512 : 256), lsa_smem, st, ws + L.pq, ws + L.proj, seq,
+                                proj_dims, chars, ws + L.cum, P(h, "decoder.attn_net.conv.weight"),
+                                P(h, "decoder.attn_net.conv.bias"), P(h, "decoder.attn_net.L.weight"),
+                                P(h, "decoder.attn_net.v.weight"), ws + L.scores_all, nst * Tc,
+                                (proj_dims % 256 == 0) ? nullptr : ws + L.ctx, Tc, sp, sj, qf ? ws + L.attn_h : nullptr,
+                                P(h, "decoder.attn_net.W.weight"), P(h, "decoder.attn_net.W.bias")));
       MB_LAUNCH_CHECK("lsa_step_kernel");
       if (proj_dims % 256 == 0) {
         if (have_stop) {  // the previous step's stop projection (side stream) still reads ctx and x, which are rewritten from here on
           MB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_side[6], 0));
           have_stop = false;
         }
-        lsa_ctx_kernel<<<dim3(proj_dims / 256, B), 256, sizeof(float) * Tc, st>>>(
-            ws + L.scores_all, nst * Tc, seq, proj_dims, Tc, ws + L.ctx, sp, sj, fsplit ? fhi(fs.p1) : nullptr,
-            fsplit ? fhi(fs.p1 + fs.b1) : nullptr, fsplit ? fhi(fs.p2) : nullptr, fsplit ? fhi(fs.p2 + fs.b2) : nullptr, f_rows_pad);
+        MB_CUDA_CHECK(launch_pdl2(lsa_ctx_kernel, dim3(proj_dims / 256, B), dim3(256), sizeof(float) * Tc, st, ws + L.scores_all,
+                                  nst * Tc, seq, proj_dims, Tc, ws + L.ctx, sp, sj, fsplit ? fhi(fs.p1) : nullptr,
+                                  fsplit ? fhi(fs.p1 + fs.b1) : nullptr, fsplit ? fhi(fs.p2) : nullptr,
+                                  fsplit ? fhi(fs.p2 + fs.b2) : nullptr, f_rows_pad));
         MB_LAUNCH_CHECK("lsa_ctx_kernel");
       }
       if (dag) {  // side stream: context half of the NEXT step's attention-GRU input projection
